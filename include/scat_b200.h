@@ -1,0 +1,75 @@
+/* scat_b200.h - C ABI of libscat_b200.so, the sm_100a wavelet-scattering engine.
+ *
+ * Boundary replaced: the per-primitive backend protocol of the kymatio torch frontends
+ *   kymatio/frontend/base_frontend.py:32-50          (backend binding)
+ *   kymatio/scattering2d/core/scattering2d.py:3-9    (rfft, ifft, irfft, cdgmm,
+ *                                                     subsample_fourier, modulus, stack)
+ *   kymatio/scattering2d/frontend/torch_frontend.py:72-111 (caller of the core)
+ * and, for the fused path, the whole core call
+ *   kymatio/scattering2d/frontend/torch_frontend.py:98-99  scattering2d(...)
+ *
+ * Conventions: every function returns 0 on success, non-zero on error
+ * (scat_last_error() gives the message, thread-local).  All pointers named *_dev are
+ * device pointers owned by the caller (torch tensors); the library never allocates
+ * device memory, never synchronises the device and launches only on the given stream.
+ * dtype: 0 = float32, 1 = float64 (the reference's gradcheck runs in float64:
+ * tests/scattering2d/test_torch_scattering2d.py:238-248).
+ */
+#ifndef SCAT_B200_H
+#define SCAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scat_plan2d scat_plan2d;
+
+typedef struct scat_plan2d_desc {
+    int32_t M, N;          /* un-padded spatial size (ScatteringBase2D.shape)            */
+    int32_t J, L;          /* scales / angles        (base_frontend.py:8-17)              */
+    int32_t max_order;     /* 1 or 2                 (core/scattering2d.py:53-54)          */
+    int32_t pre_pad;       /* input already padded   (torch_frontend.py:16-18)             */
+    int32_t dtype;         /* 0 = f32, 1 = f64                                           */
+    int32_t reserved;
+} scat_plan2d_desc;
+
+/* library / device ---------------------------------------------------------------- */
+int  scat_version(void);
+const char* scat_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t scat_launch_count(void);
+
+/* 2-D plan ----------------------------------------------------------------------- */
+int  scat_plan2d_create(const scat_plan2d_desc* desc, scat_plan2d** out_plan);
+void scat_plan2d_destroy(scat_plan2d* plan);
+
+/* padded size, output size, number of channels K = 1 + LJ + L^2 J(J-1)/2 */
+int  scat_plan2d_info(const scat_plan2d* plan, int32_t* Mp, int32_t* Np, int32_t* out_h, int32_t* out_w,
+                      int32_t* K);
+
+/* bytes of plan constants (twiddles, scramble tables, scrambled filter bank) the caller
+ * must provide as one device buffer */
+size_t scat_plan2d_const_bytes(const scat_plan2d* plan);
+
+/* Bind the filter bank.  phi_dev[J]: low-pass at resolutions 0..J-1, natural order,
+ * (Mp/2^r, Np/2^r) real; psi_dev[n_psi]: band-pass levels flattened in the frontend's
+ * registration order (torch_frontend.py:28-43): for n in 0..J*L-1, for each level.
+ * Filters are copied (scrambled) into const_dev; the originals are not referenced later.
+ * Call again whenever the module buffers change (.to(), .double(), load_state_dict). */
+int  scat_plan2d_bind(scat_plan2d* plan, void* const_dev, const void* const* phi_dev, int32_t n_phi,
+                      const void* const* psi_dev, int32_t n_psi, void* stream);
+
+/* workspace bytes for a forward over `batch` images (the plan chunks large batches) */
+size_t scat_plan2d_workspace_bytes(const scat_plan2d* plan, int64_t batch);
+
+/* x_dev: (batch, M, N) real [or (batch, Mp, Np) when pre_pad]; out_dev: (batch, K, out_h, out_w) */
+int  scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, void* workspace_dev,
+                         size_t workspace_bytes, int64_t batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAT_B200_H */

@@ -1,0 +1,84 @@
+"""ctypes binding of libscat_b200.so (C ABI declared in include/scat_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails the
+product path raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C kymatio_b200/csrc``.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SCAT_B200_LIB", os.path.join(_HERE, "lib", "libscat_b200.so"))
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+_lib = None
+
+
+class ScatB200Error(RuntimeError):
+    pass
+
+
+class PlanDesc2D(ctypes.Structure):
+    _fields_ = [("M", ctypes.c_int32), ("N", ctypes.c_int32), ("J", ctypes.c_int32), ("L", ctypes.c_int32),
+                ("max_order", ctypes.c_int32), ("pre_pad", ctypes.c_int32), ("dtype", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol the
+# header declares is exported.
+_c = ctypes
+SIGNATURES = {
+    "scat_version": (_c.c_int, []),
+    "scat_last_error": (_c.c_char_p, []),
+    "scat_launch_count": (_c.c_uint64, []),
+    "scat_plan2d_create": (_c.c_int, [_c.POINTER(PlanDesc2D), _c.POINTER(_c.c_void_p)]),
+    "scat_plan2d_destroy": (None, [_c.c_void_p]),
+    "scat_plan2d_info": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_int32)] * 5),
+    "scat_plan2d_const_bytes": (_c.c_size_t, [_c.c_void_p]),
+    "scat_plan2d_bind": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_int32,
+                                    _c.POINTER(_c.c_void_p), _c.c_int32, _c.c_void_p]),
+    "scat_plan2d_workspace_bytes": (_c.c_size_t, [_c.c_void_p, _c.c_int64]),
+    "scat_plan2d_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t,
+                                       _c.c_int64, _c.c_void_p]),
+}
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise ScatB200Error("building libscat_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (once) and attach the C signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScatB200Error(
+            f"{LIB_PATH} not found: the torch_b200 backend has no CPU or eager fallback. "
+            "Build it with `make -C kymatio_b200/csrc` (needs nvcc).")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().scat_last_error()
+        raise ScatB200Error(msg.decode() if msg else f"libscat_b200 error {code}")
+
+
+def launch_count():
+    return int(load().scat_launch_count())

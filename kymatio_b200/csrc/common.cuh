@@ -1,0 +1,77 @@
+// common.cuh - host-side helpers: error reporting, launch accounting, slab configuration.
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include "fft_core.cuh"
+
+namespace sb {
+
+inline std::string& last_error() { static thread_local std::string e; return e; }
+inline std::atomic<uint64_t>& launch_counter() { static std::atomic<uint64_t> c{0}; return c; }
+
+#define SB_CUDA(expr)                                                                           \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+inline void check_launch(const char* what) {
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + what + ": " + cudaGetErrorString(e));
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+// opt in to large dynamic shared memory once per kernel instantiation
+template <typename K> inline void enable_big_smem(K kernel) {
+    SB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Slab launch configuration for a batched 1-D transform of length P.n over `total_lines`.
+struct SlabCfg {
+    int lines;   // lines per CTA
+    int LP;      // shared-memory pitch between consecutive elements (odd, >= lines)
+    dim3 block;  // (lanes over lines, butterflies in flight)
+    size_t smem; // dynamic shared memory bytes (slab + twiddle table)
+};
+
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Defaults: 16 lines x up to 18 butterflies in flight (<= 288 threads, two CTAs per SM at
+// <= 112 registers).  SCAT_B200_LINES / SCAT_B200_THREADS override for tuning runs.
+inline SlabCfg slab_cfg(const Plan1& P, int total_lines, size_t elem_bytes, size_t slab_budget = 72 * 1024) {
+    SlabCfg c{};
+    int lines = env_int("SCAT_B200_LINES", 16);
+    const int max_threads = std::min(576, env_int("SCAT_B200_THREADS", 288));
+    if (lines < 1 || lines > 32 || (lines & (lines - 1))) lines = 16;
+    while (lines > 1 && (size_t)(lines | 1) * P.n * elem_bytes > slab_budget) lines /= 2;
+    while (lines > 1 && lines / 2 >= total_lines) lines /= 2;
+    c.lines = lines;
+    c.LP = lines | 1;
+    int max_bf = 1;
+    for (int p = 0; p < P.npass; ++p) max_bf = std::max(max_bf, P.n / P.radix[p]);
+    int bx = lines;
+    int by = std::max(1, std::min(max_bf, max_threads / bx));
+    // keep at least 64 threads for the staging loops
+    while (bx * by < 64 && by < 64) ++by;
+    c.block = dim3(bx, by, 1);
+    c.smem = ((size_t)c.LP * P.n + P.n) * elem_bytes;
+    if (c.smem > kMaxDynSmem)
+        throw std::runtime_error("FFT line of length " + std::to_string(P.n) + " does not fit in shared memory");
+    return c;
+}
+
+}  // namespace sb

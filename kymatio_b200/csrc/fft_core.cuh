@@ -1,0 +1,270 @@
+// fft_core.cuh - register-level mixed-radix FFT building blocks (host+device).
+//
+// Data-flow conventions used by every kernel in this library:
+//   * forward transform  = decimation-in-frequency (DIF), sign -, natural order in,
+//     "canonical scrambled" order out;
+//   * inverse transform  = decimation-in-time (DIT), sign +, canonical scrambled order
+//     in, natural order out (the exact transpose of the DIF flow graph).
+// Spatial-domain data is therefore always in natural order and Fourier-domain data
+// always in canonical scrambled order, so no permutation pass is ever needed on the
+// hot path; filters are permuted once when they are bound to a plan.
+//
+// Canonical scrambled order for n = (odd primes r1 >= r2 >= ...) * 2^a: the DIF passes
+// run odd radices first, then the power-of-two part; a frequency f lands at
+//   pos(f) = (((f mod r1) * r2 + (f/r1 mod r2)) * ... ) * 2^a + bitrev_a(f / odd)
+// Property used everywhere: the 2^b aliases {u + c*n/2^b} of the Fourier-domain
+// periodisation (kymatio/scattering2d/backend/torch_backend.py:93-129) are ADJACENT in
+// this order, and summing them yields the child spectrum already in the child's own
+// canonical order.
+#pragma once
+#include <type_traits>
+#include <utility>
+
+#if defined(__CUDACC__)
+#define SB_HD __host__ __device__ __forceinline__
+#else
+#define SB_HD inline
+#endif
+
+namespace sb {
+
+template <typename T> struct cx { T x, y; };
+
+template <typename T> SB_HD cx<T> mk(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
+template <typename T> SB_HD cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <typename T> SB_HD cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <typename T> SB_HD cx<T> cmul(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+template <typename T> SB_HD cx<T> cmulc(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+template <typename T> SB_HD cx<T> scal(cx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+
+// ---------------------------------------------------------------------------
+// compile-time trigonometry (Taylor series in double; |x| <= pi)
+// ---------------------------------------------------------------------------
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+constexpr double ct_sin_series(double x) {
+    double term = x, sum = x;
+    for (int k = 1; k < 20; ++k) { term *= -x * x / double((2 * k) * (2 * k + 1)); sum += term; }
+    return sum;
+}
+constexpr double ct_cos_series(double x) {
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 20; ++k) { term *= -x * x / double((2 * k - 1) * (2 * k)); sum += term; }
+    return sum;
+}
+// cos / sin of 2*pi*k/n with exact octant reduction on the integer ratio
+constexpr double ct_cos2pi(int k, int n) {
+    k %= n; if (k < 0) k += n;
+    if (2 * k > n) k = n - k;                 // cos(2pi - t) = cos t   -> t in [0, pi]
+    if (4 * k > n) return -ct_cos2pi(n - 2 * k, 2 * n);  // cos(t) = -cos(pi - t); pi - t = 2pi (n-2k)/(2n)
+    if (8 * k > n) return ct_sin_series(2.0 * kPi * double(n - 4 * k) / double(4 * n)); // cos t = sin(pi/2 - t)
+    return ct_cos_series(2.0 * kPi * double(k) / double(n));
+}
+constexpr double ct_sin2pi(int k, int n) {
+    k %= n; if (k < 0) k += n;
+    if (2 * k > n) return -ct_sin2pi(n - k, n);
+    if (4 * k > n) return ct_sin2pi(n - 2 * k, 2 * n);      // sin(t) = sin(pi - t)
+    if (8 * k > n) return ct_cos_series(2.0 * kPi * double(n - 4 * k) / double(4 * n)); // sin t = cos(pi/2 - t)
+    return ct_sin_series(2.0 * kPi * double(k) / double(n));
+}
+template <int K, int N> struct Root {            // exp(+2*pi*i*K/N)
+    static constexpr double c = ct_cos2pi(K, N);
+    static constexpr double s = ct_sin2pi(K, N);
+};
+
+template <int B, int E, typename F> SB_HD void static_for(F&& f) {
+    if constexpr (B < E) { f(std::integral_constant<int, B>{}); static_for<B + 1, E>(f); }
+}
+
+constexpr int ct_log2(int r) { return r <= 1 ? 0 : 1 + ct_log2(r / 2); }
+constexpr int ct_bitrev(int v, int bits) { int r = 0; for (int i = 0; i < bits; ++i) { r = (r << 1) | ((v >> i) & 1); } return r; }
+SB_HD int rt_bitrev(int v, int bits) { int r = 0; for (int i = 0; i < bits; ++i) { r = (r << 1) | ((v >> i) & 1); } return r; }
+
+// d * exp(SIGN * 2*pi*i * J / N) with the trivial cases folded at compile time
+template <int J, int N, int SIGN, typename T> SB_HD cx<T> mul_root(cx<T> d) {
+    constexpr int j = ((J % N) + N) % N;
+    if constexpr (j == 0) return d;
+    else if constexpr (2 * j == N) return mk<T>(-d.x, -d.y);
+    else if constexpr (4 * j == N) return SIGN > 0 ? mk<T>(-d.y, d.x) : mk<T>(d.y, -d.x);       // * (+-i)
+    else if constexpr (4 * j == 3 * N) return SIGN > 0 ? mk<T>(d.y, -d.x) : mk<T>(-d.y, d.x);   // * (-+i)
+    else {
+        constexpr T c = T(Root<j, N>::c);
+        constexpr T s = T(SIGN > 0 ? Root<j, N>::s : -Root<j, N>::s);
+        return mk<T>(d.x * c - d.y * s, d.x * s + d.y * c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// in-register power-of-two transforms.
+//   dif_pow2: natural v[c] in  -> v[k] = y_{bitrev(k)} out
+//   dit_pow2: v[k] = y_{bitrev(k)} in -> natural x[c] out   (transpose network)
+// y_f = sum_c x_c exp(SIGN*2*pi*i*f*c/R)
+// ---------------------------------------------------------------------------
+template <int R, int SIGN, typename T> SB_HD void dif_pow2(cx<T>* v) {
+    constexpr int LG = ct_log2(R);
+    static_for<0, LG>([&](auto s_) {
+        constexpr int s = decltype(s_)::value;
+        constexpr int half = R >> (s + 1);
+        static_for<0, R / (2 * half)>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            static_for<0, half>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
+                constexpr int i0 = b * 2 * half + j, i1 = i0 + half;
+                cx<T> a = v[i0], c = v[i1];
+                v[i0] = a + c;
+                v[i1] = mul_root<j, 2 * half, SIGN, T>(a - c);
+            });
+        });
+    });
+}
+template <int R, int SIGN, typename T> SB_HD void dit_pow2(cx<T>* v) {
+    constexpr int LG = ct_log2(R);
+    static_for<0, LG>([&](auto s_) {
+        constexpr int s = LG - 1 - decltype(s_)::value;
+        constexpr int half = R >> (s + 1);
+        static_for<0, R / (2 * half)>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            static_for<0, half>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
+                constexpr int i0 = b * 2 * half + j, i1 = i0 + half;
+                cx<T> a = v[i0], c = mul_root<j, 2 * half, SIGN, T>(v[i1]);
+                v[i0] = a + c;
+                v[i1] = a - c;
+            });
+        });
+    });
+}
+
+// ---------------------------------------------------------------------------
+// in-register odd-prime DFT (natural in, natural out; the matrix is symmetric so the
+// same routine serves DIF and DIT).  Uses the x_n +- x_{R-n} pairing: (R-1)^2/2 real
+// FMAs with compile-time constants.
+// ---------------------------------------------------------------------------
+template <int R, int SIGN, typename T> SB_HD void dft_prime(cx<T>* v) {
+    constexpr int H = (R - 1) / 2;
+    cx<T> a[H], b[H];
+    static_for<0, H>([&](auto n_) {
+        constexpr int n = decltype(n_)::value;
+        a[n] = v[n + 1] + v[R - 1 - n];
+        b[n] = v[n + 1] - v[R - 1 - n];
+    });
+    cx<T> x0 = v[0];
+    cx<T> s0 = x0;
+    static_for<0, H>([&](auto n_) { s0 = s0 + a[decltype(n_)::value]; });
+    v[0] = s0;
+    static_for<1, H + 1>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        cx<T> p = x0, q = mk<T>(T(0), T(0));
+        static_for<0, H>([&](auto n_) {
+            constexpr int n = decltype(n_)::value;
+            constexpr int idx = ((n + 1) * k) % R;
+            constexpr T c = T(Root<idx, R>::c);
+            constexpr T s = T(Root<idx, R>::s);
+            p.x += a[n].x * c; p.y += a[n].y * c;
+            q.x += b[n].x * s; q.y += b[n].y * s;
+        });
+        // y_k = p + SIGN*i*q ; y_{R-k} = p - SIGN*i*q ; i*q = (-q.y, q.x)
+        if (SIGN > 0) { v[k] = mk<T>(p.x - q.y, p.y + q.x); v[R - k] = mk<T>(p.x + q.y, p.y - q.x); }
+        else          { v[k] = mk<T>(p.x + q.y, p.y - q.x); v[R - k] = mk<T>(p.x - q.y, p.y + q.x); }
+    });
+}
+
+// ---------------------------------------------------------------------------
+// 1-D plan: radices in DIF order (odd primes descending, then powers of two),
+// blen[p] = block length the p-th DIF pass works on (n, n/r0, n/(r0 r1), ...).
+// ---------------------------------------------------------------------------
+constexpr int kMaxPass = 12;
+constexpr int kMaxGenericRadix = 128;
+struct Plan1 {
+    int n;
+    int npass;
+    int radix[kMaxPass];
+    int blen[kMaxPass];
+};
+
+constexpr bool ct_is_pow2(int r) { return (r & (r - 1)) == 0; }
+
+// One radix-R butterfly of pass (block length m = R*q) on one line.
+//   INV=false : DIF forward  (load natural group, DFT, twiddle, store to slots)
+//   INV=true  : DIT inverse  (load slots, conj twiddle, DFT(+), store natural group)
+// `line` addresses element e at line[e*estride]; base = blk*m + i; twstep = i*(n/m).
+template <int R, bool INV, typename T>
+SB_HD void butterfly(cx<T>* line, int estride, int base, int q, int twstep, const cx<T>* tw, bool do_tw) {
+    constexpr int SIGN = INV ? +1 : -1;
+    constexpr bool P2 = ct_is_pow2(R);
+    constexpr int LG = ct_log2(R);
+    cx<T> v[R];
+    static_for<0, R>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        v[k] = line[(base + k * q) * estride];
+    });
+    if (!INV) {
+        if constexpr (P2) dif_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
+        if (do_tw) {
+            static_for<1, R>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                constexpr int f = P2 ? ct_bitrev(k, LG) : k;
+                v[k] = cmul(v[k], tw[f * twstep]);
+            });
+        }
+    } else {
+        if (do_tw) {
+            static_for<1, R>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                constexpr int f = P2 ? ct_bitrev(k, LG) : k;
+                v[k] = cmulc(v[k], tw[f * twstep]);
+            });
+        }
+        if constexpr (P2) dit_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
+    }
+    static_for<0, R>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        line[(base + k * q) * estride] = v[k];
+    });
+}
+
+// Runtime odd radix (primes not in the compiled list); O(R^2), local-memory array.
+template <bool INV, typename T>
+SB_HD void butterfly_generic(cx<T>* line, int estride, int base, int q, int twstep, const cx<T>* tw,
+                             bool do_tw, int n, int R) {
+    cx<T> v[kMaxGenericRadix];
+    const int rstep = n / R;
+    for (int k = 0; k < R; ++k) {
+        cx<T> t = line[(base + k * q) * estride];
+        if (INV && do_tw && k) t = cmulc(t, tw[k * twstep]);
+        v[k] = t;
+    }
+    for (int f = 0; f < R; ++f) {
+        cx<T> acc = v[0];
+        int idx = 0;
+        for (int c = 1; c < R; ++c) {
+            idx += f; if (idx >= R) idx -= R;
+            cx<T> w = tw[idx * rstep];
+            acc = acc + (INV ? cmulc(v[c], w) : cmul(v[c], w));
+        }
+        if (!INV && do_tw && f) acc = cmul(acc, tw[f * twstep]);
+        line[(base + f * q) * estride] = acc;     // safe: inputs are all in v[]
+    }
+}
+
+// Dispatch one butterfly of plan pass p (work item bf in [0, n/r)) on one line.
+template <bool INV, typename T>
+SB_HD void butterfly_dispatch(int r, cx<T>* line, int estride, int base, int q, int twstep,
+                              const cx<T>* tw, bool do_tw, int n) {
+    switch (r) {
+        case 2:  butterfly<2, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 3:  butterfly<3, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 4:  butterfly<4, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 5:  butterfly<5, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 7:  butterfly<7, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 8:  butterfly<8, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 11: butterfly<11, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 13: butterfly<13, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 16: butterfly<16, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        case 17: butterfly<17, INV, T>(line, estride, base, q, twstep, tw, do_tw); break;
+        default: butterfly_generic<INV, T>(line, estride, base, q, twstep, tw, do_tw, n, r); break;
+    }
+}
+
+}  // namespace sb

@@ -1,0 +1,51 @@
+// slab.cuh - block-level batched 1-D transforms on a slab of lines held in shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include "fft_core.cuh"
+
+namespace sb {
+
+// upper bound on threads per CTA for every slab kernel (caps registers at 65536/576 = 113)
+constexpr int kMaxThreads = 576;
+
+// Transform `lines` lines of length P.n in shared memory, in place.
+//   element e of line l lives at s[l*lstride + e*estride]
+//   INV=false: DIF forward (natural -> scrambled); INV=true: DIT inverse, unnormalised
+// Thread mapping: threadIdx.x strides over lines (consecutive lanes -> consecutive
+// lines, which every caller lays out conflict-free), threadIdx.y strides over the
+// n/r butterflies of a pass.  One __syncthreads per pass; ends synchronised.
+template <bool INV, typename T>
+__device__ __noinline__ void slab_fft(cx<T>* s, int lines, int lstride, int estride, const Plan1& P,
+                                      const cx<T>* tw) {
+    for (int pp = 0; pp < P.npass; ++pp) {
+        const int p = INV ? P.npass - 1 - pp : pp;
+        const int r = P.radix[p], m = P.blen[p];
+        const int q = m / r, nbf = P.n / r, tws = P.n / m;
+        for (int bf = threadIdx.y; bf < nbf; bf += blockDim.y) {
+            const int blk = bf / q, i = bf - blk * q;
+            for (int line = threadIdx.x; line < lines; line += blockDim.x)
+                butterfly_dispatch<INV, T>(r, s + line * lstride, estride, blk * m + i, q, i * tws, tw, q > 1, P.n);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int flat_tid() { return threadIdx.y * blockDim.x + threadIdx.x; }
+__device__ __forceinline__ int flat_nt() { return blockDim.x * blockDim.y; }
+
+template <typename T>
+__device__ __forceinline__ void copy_tw(cx<T>* dst, const cx<T>* __restrict__ src, int n) {
+    for (int i = flat_tid(); i < n; i += flat_nt()) dst[i] = src[i];
+}
+
+// periodic reflection index (numpy 'reflect' / torch ReflectionPad2d semantics extended
+// to pad == size, kymatio/scattering2d/backend/torch_backend.py:49-54,80-83)
+__device__ __forceinline__ int reflect_idx(int t, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    t %= period;
+    if (t < 0) t += period;
+    return t < n ? t : period - t;
+}
+
+}  // namespace sb

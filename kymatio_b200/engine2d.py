@@ -1,0 +1,92 @@
+"""Host-side handle on the fused 2D engine (``scat_plan2d_*`` in include/scat_b200.h).
+
+One ``Engine2D`` per (geometry, dtype, device); it owns the plan, the constant buffer
+(twiddles, scramble tables, scrambled filter copies - a torch tensor, the library never
+allocates) and re-binds the filters whenever the frontend's buffers change
+(kymatio/scattering2d/frontend/torch_frontend.py:48-70 re-reads them on every call).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: 0, torch.float64: 1}
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class Engine2D:
+    def __init__(self, M, N, J, L, max_order, pre_pad, dtype, device):
+        if dtype not in _DTYPES:
+            raise TypeError("torch_b200 supports float32 and float64 inputs, got %s" % dtype)
+        self.lib = _lib.load()
+        self.dtype, self.device = dtype, torch.device(device)
+        desc = _lib.PlanDesc2D(int(M), int(N), int(J), int(L), int(max_order), int(bool(pre_pad)),
+                               _DTYPES[dtype], 0)
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.scat_plan2d_create(ctypes.byref(desc), ctypes.byref(handle)))
+        self._plan = handle
+        vals = [ctypes.c_int32() for _ in range(5)]
+        _lib.check(self.lib.scat_plan2d_info(self._plan, *[ctypes.byref(v) for v in vals]))
+        self.Mp, self.Np, self.out_h, self.out_w, self.K = [v.value for v in vals]
+        with torch.cuda.device(self.device):
+            self._const = torch.empty(self.lib.scat_plan2d_const_bytes(self._plan), dtype=torch.uint8,
+                                      device=self.device)
+        self._bound_key = None
+
+    def __del__(self):
+        plan, self._plan = getattr(self, "_plan", None), None
+        if plan:
+            try:
+                self.lib.scat_plan2d_destroy(plan)
+            except Exception:
+                pass
+
+    # -- filters ---------------------------------------------------------------------
+    def bind(self, phi_levels, psi_levels):
+        """phi_levels: J tensors; psi_levels: flattened levels in registration order."""
+        tensors = list(phi_levels) + list(psi_levels)
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key == self._bound_key:
+            return
+        for t in tensors:
+            if t.dtype != self.dtype:
+                raise TypeError("Input and filter must be of the same dtype.")
+            if t.device != self.device:
+                raise TypeError("Input and filter must be on the same GPU.")
+            if not t.is_contiguous():
+                raise RuntimeError("Tensors must be contiguous.")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_bind(
+                self._plan, self._const.data_ptr(), _ptr_array(phi_levels), len(phi_levels),
+                _ptr_array(psi_levels), len(psi_levels), ctypes.c_void_p(stream)))
+        self._bound_key = key
+
+    # -- forward ---------------------------------------------------------------------
+    def workspace(self, batch):
+        # a fresh tensor per call: torch's caching allocator makes this cheap and keeps the
+        # buffer's lifetime stream-ordered (safe with several streams / DataParallel replicas)
+        need = self.lib.scat_plan2d_workspace_bytes(self._plan, int(batch))
+        with torch.cuda.device(self.device):
+            return torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def forward(self, x):
+        """x: (B, M, N) contiguous on self.device -> (B, K, out_h, out_w)."""
+        B = x.shape[0]
+        out = torch.empty((B, self.K, self.out_h, self.out_w), dtype=self.dtype, device=self.device)
+        if B == 0:
+            return out
+        ws = self.workspace(B)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_forward(
+                self._plan, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), B,
+                ctypes.c_void_p(stream)))
+        return out

@@ -1,0 +1,14 @@
+"""Host emulation of the register-level FFT building blocks (no GPU needed)."""
+import os
+import subprocess
+import sys
+
+
+def test_fft_core_on_cpu(tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fft_core_test")
+    src = os.path.join(root, "tests", "cpu", "fft_core_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, src], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    sys.stdout.write(res.stdout[-2000:])
+    assert res.returncode == 0 and "ALL OK" in res.stdout
