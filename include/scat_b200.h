@@ -42,6 +42,12 @@ const char* scat_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 uint64_t scat_launch_count(void);
 
+/* per-launch timing with CUDA events on the launching stream (bench.py's live roofline):
+ * enable, run, then report -> "label\tcount\ttotal_ms\ttotal_algorithmic_bytes\n" per kernel label.
+ * scat_timing_report synchronises on the recorded events; returns the bytes needed. */
+void scat_timing_enable(int on);
+size_t scat_timing_report(char* buf, size_t buflen);
+
 /* 2-D plan ----------------------------------------------------------------------- */
 int  scat_plan2d_create(const scat_plan2d_desc* desc, scat_plan2d** out_plan);
 void scat_plan2d_destroy(scat_plan2d* plan);

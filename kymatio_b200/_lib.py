@@ -32,6 +32,8 @@ SIGNATURES = {
     "scat_version": (_c.c_int, []),
     "scat_last_error": (_c.c_char_p, []),
     "scat_launch_count": (_c.c_uint64, []),
+    "scat_timing_enable": (None, [_c.c_int]),
+    "scat_timing_report": (_c.c_size_t, [_c.c_char_p, _c.c_size_t]),
     "scat_plan2d_create": (_c.c_int, [_c.POINTER(PlanDesc2D), _c.POINTER(_c.c_void_p)]),
     "scat_plan2d_destroy": (None, [_c.c_void_p]),
     "scat_plan2d_info": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_int32)] * 5),
@@ -82,3 +84,19 @@ def check(code):
 
 def launch_count():
     return int(load().scat_launch_count())
+
+
+def timing_enable(on=True):
+    load().scat_timing_enable(1 if on else 0)
+
+
+def timing_report():
+    """-> list of dicts {label, count, ms, bytes} aggregated per kernel label (synchronises)."""
+    lib = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.scat_timing_report(buf, len(buf))
+    rows = []
+    for line in buf.value.decode().splitlines():
+        label, cnt, ms, nbytes = line.split("\t")
+        rows.append({"label": label, "count": int(cnt), "ms": float(ms), "bytes": float(nbytes)})
+    return rows

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include "fft_core.cuh"
 
 namespace sb {
@@ -21,10 +22,31 @@ inline std::atomic<uint64_t>& launch_counter() { static std::atomic<uint64_t> c{
             throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));       \
     } while (0)
 
+// Optional per-launch timing (CUDA events on the launching stream), switched on by
+// scat_timing_enable(1); bench.py uses it for the live per-kernel roofline figures.
+struct TimingRec { std::string label; cudaEvent_t e0, e1; double bytes; };
+inline bool& timing_on() { static bool on = false; return on; }
+inline std::vector<TimingRec>& timing_recs() { static std::vector<TimingRec> r; return r; }
+
 inline void check_launch(const char* what) {
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + what + ": " + cudaGetErrorString(e));
+}
+
+// Run one kernel launch `f` on stream `st`; `bytes` = algorithmic bytes (reads + writes) of the launch.
+template <typename F> inline void launch(const std::string& label, double bytes, cudaStream_t st, F&& f) {
+    if (timing_on()) {
+        TimingRec r; r.label = label; r.bytes = bytes;
+        SB_CUDA(cudaEventCreate(&r.e0)); SB_CUDA(cudaEventCreate(&r.e1));
+        SB_CUDA(cudaEventRecord(r.e0, st));
+        f();
+        SB_CUDA(cudaEventRecord(r.e1, st));
+        timing_recs().push_back(r);
+    } else {
+        f();
+    }
+    check_launch(label.c_str());
 }
 
 constexpr size_t kMaxDynSmem = 227 * 1024;

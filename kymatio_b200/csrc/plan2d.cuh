@@ -136,9 +136,10 @@ public:
         auto scramble = [&](const void* src, size_t dst_off, int res) {
             const int n0 = lev_[res].a0.n, n1 = lev_[res].a1.n;
             dim3 grid(ceil_div(n1, 128), n0);
-            k2d_scramble<T><<<grid, 128, 0, st>>>(static_cast<const T*>(src), reinterpret_cast<T*>(cbuf_ + dst_off),
-                                                   pos(lev_[res].a0), pos(lev_[res].a1), n0, n1);
-            check_launch("scramble");
+            launch("scramble", 2.0 * n0 * n1 * sizeof(T), st, [&] {
+                k2d_scramble<T><<<grid, 128, 0, st>>>(static_cast<const T*>(src), reinterpret_cast<T*>(cbuf_ + dst_off),
+                                                       pos(lev_[res].a0), pos(lev_[res].a1), n0, n1);
+            });
         };
         for (int j = 0; j < d_.J; ++j) scramble(phi[j], phi_off_[j], j);
         int n = 0;
@@ -189,8 +190,11 @@ private:
         const SlabCfg& c = row_cfg_[out_res];
         a.lines = c.lines; a.LP = c.LP; a.plan = lev_[out_res].a1.plan; a.tw = tw(lev_[out_res].a1);
         dim3 grid((unsigned)(Bp * NF), ceil_div(a.n0, c.lines));
-        k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a);
-        check_launch("rowpass_prod");
+        const double G = (double)Bp * NF;
+        const double bytes = G * a.P0 * a.P1 * sizeof(cx<T>) + (double)NF * a.P0 * a.P1 * sizeof(T) +
+                             G * a.n0 * a.n1 * sizeof(cx<T>);
+        launch("rowpass_prod:L" + std::to_string(parent_res) + ">L" + std::to_string(out_res), bytes, st,
+               [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
     }
     template <int MODE> void col_pass(cx<T>* data, int res, int G, cudaStream_t st) {
         ColArgs<T> a{};
@@ -198,8 +202,10 @@ private:
         const SlabCfg& c = col_cfg_[res];
         a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a0.plan; a.tw = tw(lev_[res].a0);
         dim3 grid((unsigned)G, ceil_div(a.n1, c.lines));
-        k2d_colpass<T, MODE><<<grid, c.block, c.smem, st>>>(a);
-        check_launch("colpass");
+        launch(std::string(MODE == COL_FWD ? "colpass_fwd" : MODE == COL_INV ? "colpass_inv" : "colpass_inv_mod_fwd") +
+                   ":L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
+               2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
+               [&] { k2d_colpass<T, MODE><<<grid, c.block, c.smem, st>>>(a); });
     }
     template <bool INV> void row_pass(cx<T>* data, int res, int G, cudaStream_t st) {
         RowArgs<T> a{};
@@ -207,8 +213,10 @@ private:
         const SlabCfg& c = row_cfg_[res];
         a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a1.plan; a.tw = tw(lev_[res].a1);
         dim3 grid((unsigned)G, ceil_div(a.n0, c.lines));
-        k2d_rowpass<T, INV><<<grid, c.block, c.smem, st>>>(a);
-        check_launch("rowpass");
+        launch(std::string(INV ? "rowpass_inv" : "rowpass_fwd") + ":L" + std::to_string(res) + ":G" +
+                   std::to_string(G / std::max(1, last_B_)),
+               2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
+               [&] { k2d_rowpass<T, INV><<<grid, c.block, c.smem, st>>>(a); });
     }
     // S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra at resolution res
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
@@ -222,8 +230,10 @@ private:
             a.PP = PP; a.NF = NF; a.ch0 = ch0; a.chs = chs; a.K = K_; a.scale = scale;
             a.plan0 = lev_[d_.J].a0.plan; a.plan1 = lev_[d_.J].a1.plan;
             a.tw0 = tw(lev_[d_.J].a0); a.tw1 = tw(lev_[d_.J].a1);
-            k2d_lowpass<T><<<(unsigned)(B * PP), dim3(32, 8), low_smem_, st>>>(a);
-            check_launch("lowpass");
+            const double G = (double)B * PP;
+            launch("lowpass:L" + std::to_string(res) + ":G" + std::to_string(PP),
+                   G * a.P0 * a.P1 * sizeof(cx<T>) + (double)a.P0 * a.P1 * sizeof(T) + G * o0_ * o1_ * sizeof(T), st,
+                   [&] { k2d_lowpass<T><<<(unsigned)(B * PP), dim3(32, 8), low_smem_, st>>>(a); });
         } else {
             // streaming fallback for outputs too large for one CTA
             const int G = B * PP;
@@ -234,20 +244,22 @@ private:
             const SlabCfg& c = row_cfg_[d_.J];
             a.lines = c.lines; a.LP = c.LP; a.plan = lev_[d_.J].a1.plan; a.tw = tw(lev_[d_.J].a1);
             dim3 grid((unsigned)G, ceil_div(m0_, c.lines));
-            k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a);
-            check_launch("rowpass_prod(low)");
+            launch("rowpass_prod(low):L" + std::to_string(res),
+                   (double)G * (a.P0 * a.P1 + m0_ * m1_) * sizeof(cx<T>), st,
+                   [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
             col_pass<COL_INV>(tmp, d_.J, G, st);
             CropArgs<T> ca{};
             ca.in = tmp; ca.out = out; ca.m0 = m0_; ca.m1 = m1_; ca.PP = PP; ca.NF = NF; ca.ch0 = ch0; ca.chs = chs;
             ca.K = K_;
             dim3 g2((unsigned)G, ceil_div(o0_ * o1_, 256));
-            k2d_crop_real<T><<<g2, 256, 0, st>>>(ca);
-            check_launch("crop_real");
+            launch("crop_real", (double)G * (m0_ * m1_ * sizeof(cx<T>) + o0_ * o1_ * sizeof(T)), st,
+                   [&] { k2d_crop_real<T><<<g2, 256, 0, st>>>(ca); });
         }
     }
 
     void forward_chunk(const T* x, T* out, cx<T>* ws, int B, cudaStream_t st) {
         const int J = d_.J, L = d_.L;
+        last_B_ = B;
         cx<T>* U0 = ws;
         cx<T>* U1 = U0 + (size_t)B * ws_u0_;
         cx<T>* U2 = U1 + (size_t)B * ws_u1_;
@@ -260,8 +272,8 @@ private:
             const SlabCfg& c = row_cfg_[0];
             a.lines = c.lines; a.LP = c.LP; a.plan = lev_[0].a1.plan; a.tw = tw(lev_[0].a1);
             dim3 grid((unsigned)B, ceil_div(P0_, c.lines));
-            k2d_pad_rowfft<T><<<grid, c.block, c.smem, st>>>(a);
-            check_launch("pad_rowfft");
+            launch("pad_rowfft", (double)B * (a.M * a.N * sizeof(T) + (double)P0_ * P1_ * sizeof(cx<T>)), st,
+                   [&] { k2d_pad_rowfft<T><<<grid, c.block, c.smem, st>>>(a); });
             col_pass<COL_FWD>(U0, 0, B, st);
         }
         // S0 (core/scattering2d.py:18-28); J == 0 has no filters: handled by the caller
@@ -303,6 +315,7 @@ private:
     size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, per_img_ = 0;
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;
+    int last_B_ = 1;
 };
 
 }  // namespace sb

@@ -1,4 +1,6 @@
 // scat_b200.cu - extern "C" entry points of libscat_b200.so (see include/scat_b200.h).
+#include <cstdio>
+#include <cstring>
 #include "plan2d.cuh"
 
 using namespace sb;
@@ -16,6 +18,42 @@ extern "C" {
 int scat_version(void) { return 100; }
 const char* scat_last_error(void) { return last_error().c_str(); }
 uint64_t scat_launch_count(void) { return launch_counter().load(); }
+
+void scat_timing_enable(int on) {
+    timing_on() = on != 0;
+    if (!on) {
+        for (auto& r : timing_recs()) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        timing_recs().clear();
+    }
+}
+
+// Synchronises the recorded events and writes "label\tcount\ttotal_ms\ttotal_bytes\n" lines
+// (aggregated per label) into buf; returns the number of bytes needed (excluding the NUL).
+size_t scat_timing_report(char* buf, size_t buflen) {
+    std::vector<std::string> labels; std::vector<double> ms, bytes; std::vector<long> cnt;
+    for (auto& r : timing_recs()) {
+        float t = 0.f;
+        cudaEventSynchronize(r.e1);
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        size_t i = 0;
+        for (; i < labels.size(); ++i) if (labels[i] == r.label) break;
+        if (i == labels.size()) { labels.push_back(r.label); ms.push_back(0); bytes.push_back(0); cnt.push_back(0); }
+        ms[i] += t; bytes[i] += r.bytes; cnt[i] += 1;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    timing_recs().clear();
+    std::string out;
+    for (size_t i = 0; i < labels.size(); ++i) {
+        char line[512];
+        snprintf(line, sizeof line, "%s\t%ld\t%.6f\t%.0f\n", labels[i].c_str(), cnt[i], ms[i], bytes[i]);
+        out += line;
+    }
+    if (buf && buflen) {
+        size_t n = std::min(buflen - 1, out.size());
+        memcpy(buf, out.data(), n); buf[n] = 0;
+    }
+    return out.size();
+}
 
 int scat_plan2d_create(const scat_plan2d_desc* desc, scat_plan2d** out_plan) {
     return guarded([&] {
