@@ -74,7 +74,8 @@ inline int env_int(const char* name, int dflt) {
 
 // Defaults: 16 lines x up to 18 butterflies in flight (<= 288 threads, two CTAs per SM at
 // <= 112 registers).  SCAT_B200_LINES / SCAT_B200_THREADS override for tuning runs.
-inline SlabCfg slab_cfg(const Plan1& P, int total_lines, size_t elem_bytes, size_t slab_budget = 72 * 1024) {
+inline SlabCfg slab_cfg(const Plan1& P, int total_lines, size_t elem_bytes, size_t table_bytes_per_elem = 0,
+                        size_t slab_budget = 72 * 1024) {
     SlabCfg c{};
     int lines = env_int("SCAT_B200_LINES", 16);
     const int max_threads = std::min(576, env_int("SCAT_B200_THREADS", 288));
@@ -90,7 +91,7 @@ inline SlabCfg slab_cfg(const Plan1& P, int total_lines, size_t elem_bytes, size
     // keep at least 64 threads for the staging loops
     while (bx * by < 64 && by < 64) ++by;
     c.block = dim3(bx, by, 1);
-    c.smem = ((size_t)c.LP * P.n + P.n) * elem_bytes;
+    c.smem = ((size_t)c.LP * P.n + P.n) * elem_bytes + (size_t)P.n * table_bytes_per_elem;
     if (c.smem > kMaxDynSmem)
         throw std::runtime_error("FFT line of length " + std::to_string(P.n) + " does not fit in shared memory");
     return c;

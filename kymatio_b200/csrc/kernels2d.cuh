@@ -1,4 +1,4 @@
-// kernels2d.cuh - fused 2-D scattering kernels (streaming row / column passes + low-pass tile).
+// kernels2d.cuh - fused 2-D scattering kernels.
 //
 // Reference semantics being fused (paths relative to the kymatio tree):
 //   pad            kymatio/scattering2d/backend/torch_backend.py:36-86
@@ -9,10 +9,23 @@
 //   irfft + unpad  kymatio/scattering2d/backend/torch_backend.py:144-176
 //   cascade        kymatio/scattering2d/core/scattering2d.py:14-86
 //
-// Layout: spatial data natural order, Fourier data canonical scrambled order per axis
-// (fft_core.cuh).  A "slab" is `lines` adjacent lines staged in shared memory as
-// s[e*LP + l] (element-major, LP odd) so that both the coalesced global side and the
-// butterfly side are bank-conflict free.
+// Conventions
+//   * global memory: spatial AND Fourier data in natural order (filters are read in place
+//     from the frontend's buffers);
+//   * shared memory: spatial data natural, Fourier data in the plan's scrambled order
+//     (fft_core.cuh).  Inverse transforms are DIT (scatter through pos[] while staging in),
+//     forward transforms are DIF (gather through pos[] while staging out).
+//   * filter sparsity: every filter row R carries a circular column interval
+//     (start, len) outside which the filter is negligible (|f| <= 1e-7 max|f|); the
+//     product/periodise prologues skip loads outside it.
+//
+// Two execution shapes:
+//   tile kernel       one CTA holds a whole n0 x n1 field: product+periodise, 2-D inverse FFT,
+//                     modulus, separable spatial low-pass + decimation + unpad, and (for
+//                     parents of second-order paths) the forward 2-D FFT - one pass over HBM/L2;
+//   streaming passes  row-slab and column-slab kernels for fields that do not fit one CTA
+//                     (the full-resolution first-order band) and the generic Fourier
+//                     low-pass (any, also non-separable, phi).
 #pragma once
 #include "slab.cuh"
 
@@ -23,20 +36,56 @@ template <typename T> __device__ __forceinline__ T* dyn_smem() {
     return reinterpret_cast<T*>(sb_dyn_smem);
 }
 
+template <typename U> __device__ __forceinline__ void stage(U* dst, const U* __restrict__ src, int n) {
+    for (int i = flat_tid(); i < n; i += flat_nt()) dst[i] = src[i];
+}
+
+// sum over the k x k aliases of (parent * filter) for output bin (r, e), skipping aliases outside
+// the filter's per-row support interval.  supp may live in shared or global memory.
+template <typename T>
+__device__ __forceinline__ cx<T> prod_fold(const cx<T>* __restrict__ pb, const T* __restrict__ fb, const int2* supp,
+                                           int r, int e, int k, int n0, int n1, int P1) {
+    T ax = T(0), ay = T(0);
+    for (int c = 0; c < k; ++c) {
+        const int R = r + c * n0;
+        const int2 sp = supp[R];
+        if (sp.y == 0) continue;
+        const size_t rowoff = (size_t)R * P1;
+        for (int d = 0; d < k; ++d) {
+            const int C = e + d * n1;
+            int rel = C - sp.x;
+            if (rel < 0) rel += P1;
+            if (rel < sp.y) {
+                const cx<T> v = pb[rowoff + C];
+                const T f = fb[rowoff + C];
+                ax += v.x * f; ay += v.y * f;
+            }
+        }
+    }
+    return mk<T>(ax, ay);
+}
+
+__device__ __forceinline__ int wrap(int t, int n) {   // t in (-n, 2n)
+    if (t < 0) t += n; else if (t >= n) t -= n;
+    return t;
+}
+
 // ------------------------------------------------------------------ pad + row FFT
 template <typename T> struct PadRowArgs {
     const T* x; cx<T>* out;
     int M, N, top, left, P0, P1;
     int lines, LP;
-    Plan1 plan; const cx<T>* tw;
+    Plan1 plan; const cx<T>* tw; const int* pos;
 };
-// grid (B, ceil(P0/lines)); reflect-pad rows on the fly, forward DIF along rows.
+// grid (B, ceil(P0/lines)); reflect-pad rows on the fly, forward DIF along rows, natural-order store.
 template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_pad_rowfft(PadRowArgs<T> a) {
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)a.P1 * a.LP;
+    int* pos = reinterpret_cast<int*>(tw + a.P1);
     const int b = blockIdx.x, r0 = blockIdx.y * a.lines;
     const int nl = min(a.lines, a.P0 - r0);
-    copy_tw(tw, a.tw, a.P1);
+    stage(tw, a.tw, a.P1);
+    stage(pos, a.pos, a.P1);
     const T* xb = a.x + (size_t)b * a.M * a.N;
     for (int idx = flat_tid(); idx < nl * a.P1; idx += flat_nt()) {
         const int l = idx / a.P1, e = idx - l * a.P1;
@@ -48,7 +97,7 @@ template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_pad_row
     cx<T>* ob = a.out + ((size_t)b * a.P0 + r0) * a.P1;
     for (int idx = flat_tid(); idx < nl * a.P1; idx += flat_nt()) {
         const int l = idx / a.P1, e = idx - l * a.P1;
-        ob[(size_t)l * a.P1 + e] = s[e * a.LP + l];
+        ob[(size_t)l * a.P1 + e] = s[pos[e] * a.LP + l];
     }
 }
 
@@ -58,22 +107,27 @@ template <typename T> struct ColArgs {
     const cx<T>* in; cx<T>* out;
     int n0, n1;
     int lines, LP;
-    Plan1 plan; const cx<T>* tw;
+    Plan1 plan; const cx<T>* tw; const int* pos;
 };
 // grid (G, ceil(n1/lines)); slab = `lines` adjacent columns, all n0 rows.
-//   COL_FWD          forward DIF along columns
-//   COL_INV          inverse DIT along columns
-//   COL_INV_MOD_FWD  inverse DIT, complex modulus, forward DIF (imag = 0)
+//   COL_FWD          spatial rows in  -> forward DIF along columns -> Fourier rows out
+//   COL_INV          Fourier rows in  -> inverse DIT along columns -> spatial rows out
+//   COL_INV_MOD_FWD  Fourier rows in  -> inverse DIT, modulus, forward DIF -> Fourier rows out
 template <typename T, int MODE> __global__ void __launch_bounds__(kMaxThreads) k2d_colpass(ColArgs<T> a) {
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)a.n0 * a.LP;
+    int* pos = reinterpret_cast<int*>(tw + a.n0);
     const int g = blockIdx.x, c0 = blockIdx.y * a.lines;
     const int nl = min(a.lines, a.n1 - c0);
-    copy_tw(tw, a.tw, a.n0);
+    stage(tw, a.tw, a.n0);
+    stage(pos, a.pos, a.n0);
+    if (MODE != COL_FWD) __syncthreads();
     const cx<T>* ib = a.in + (size_t)g * a.n0 * a.n1 + c0;
-    for (int e = threadIdx.y; e < a.n0; e += blockDim.y)
+    for (int e = threadIdx.y; e < a.n0; e += blockDim.y) {
+        const int se = (MODE == COL_FWD) ? e : pos[e];
         for (int l = threadIdx.x; l < nl; l += blockDim.x)
-            s[e * a.LP + l] = ib[(size_t)e * a.n1 + l];
+            s[se * a.LP + l] = ib[(size_t)e * a.n1 + l];
+    }
     __syncthreads();
     if (MODE == COL_FWD) {
         slab_fft<false, T>(s, nl, 1, a.LP, a.plan, tw);
@@ -90,46 +144,43 @@ template <typename T, int MODE> __global__ void __launch_bounds__(kMaxThreads) k
         }
     }
     cx<T>* ob = a.out + (size_t)g * a.n0 * a.n1 + c0;
-    for (int e = threadIdx.y; e < a.n0; e += blockDim.y)
+    for (int e = threadIdx.y; e < a.n0; e += blockDim.y) {
+        const int se = (MODE == COL_INV) ? e : pos[e];
         for (int l = threadIdx.x; l < nl; l += blockDim.x)
-            ob[(size_t)e * a.n1 + l] = s[e * a.LP + l];
+            ob[(size_t)e * a.n1 + l] = s[se * a.LP + l];
+    }
 }
 
 // ------------------------------------------------------------------ row pass, product + periodise prologue
 template <typename T> struct RowProdArgs {
-    const cx<T>* parent;   // [B*NP][P0][P1] scrambled spectra
-    const T* filt;         // [NF][P0][P1] real scrambled filters
-    cx<T>* out;            // [B*NP*NF][n0][n1]
-    int P0, P1, k, n0, n1, NP, NF;
+    const cx<T>* parent;      // [Bp][P0][P1] natural-order spectra
+    const T* const* filt;     // [NF] pointers to real (P0, P1) filters, natural order
+    const int2* supp;         // [NF][P0] per-row circular support (start, len)
+    cx<T>* out;               // [Bp*NF][n0][n1]: Fourier rows (natural), spatial columns
+    int P0, P1, k, n0, n1, NF;
     T scale;
     int lines, LP;
-    Plan1 plan; const cx<T>* tw;   // length n1
+    Plan1 plan; const cx<T>* tw; const int* pos;   // length n1
 };
-// grid (G = B*NP*NF, ceil(n0/lines)).  out rows = inverse DIT along rows of
-//   V[r][e] = scale * sum_{c,d<k} parent[r*k+c][e*k+d] * filt[r*k+c][e*k+d]
-// (the k x k aliases of the Fourier periodisation are adjacent in scrambled order).
+// grid (G = Bp*NF, ceil(n0/lines)).  rows of out = inverse DIT along the row of
+//   V[r][e] = scale * sum_{c,d<k} parent[r+c*n0][e+d*n1] * filt[r+c*n0][e+d*n1]
 template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass_prod(RowProdArgs<T> a) {
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)a.n1 * a.LP;
+    int* pos = reinterpret_cast<int*>(tw + a.n1);
     const int g = blockIdx.x, r0 = blockIdx.y * a.lines;
     const int nl = min(a.lines, a.n0 - r0);
     const int fi = g % a.NF, pg = g / a.NF;
-    copy_tw(tw, a.tw, a.n1);
+    stage(tw, a.tw, a.n1);
+    stage(pos, a.pos, a.n1);
+    __syncthreads();
     const cx<T>* pb = a.parent + (size_t)pg * a.P0 * a.P1;
-    const T* fb = a.filt + (size_t)fi * a.P0 * a.P1;
-    const int k = a.k;
+    const T* fb = a.filt[fi];
+    const int2* sp = a.supp + (size_t)fi * a.P0;
     for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
         const int l = idx / a.n1, e = idx - l * a.n1;
-        T ax = T(0), ay = T(0);
-        for (int c = 0; c < k; ++c) {
-            const size_t off = (size_t)((r0 + l) * k + c) * a.P1 + (size_t)e * k;
-            for (int d = 0; d < k; ++d) {
-                const cx<T> v = pb[off + d];
-                const T f = fb[off + d];
-                ax += v.x * f; ay += v.y * f;
-            }
-        }
-        s[e * a.LP + l] = mk<T>(ax * a.scale, ay * a.scale);
+        const cx<T> v = prod_fold<T>(pb, fb, sp, r0 + l, e, a.k, a.n0, a.n1, a.P1);
+        s[pos[e] * a.LP + l] = scal(v, a.scale);
     }
     __syncthreads();
     slab_fft<true, T>(s, nl, 1, a.LP, a.plan, tw);
@@ -145,37 +196,42 @@ template <typename T> struct RowArgs {
     const cx<T>* in; cx<T>* out;
     int n0, n1;
     int lines, LP;
-    Plan1 plan; const cx<T>* tw;
+    Plan1 plan; const cx<T>* tw; const int* pos;
 };
+// INV=false: spatial row in -> DIF -> Fourier row out; INV=true: Fourier row in -> DIT -> spatial row out
 template <typename T, bool INV> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass(RowArgs<T> a) {
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)a.n1 * a.LP;
+    int* pos = reinterpret_cast<int*>(tw + a.n1);
     const int g = blockIdx.x, r0 = blockIdx.y * a.lines;
     const int nl = min(a.lines, a.n0 - r0);
-    copy_tw(tw, a.tw, a.n1);
+    stage(tw, a.tw, a.n1);
+    stage(pos, a.pos, a.n1);
+    if (INV) __syncthreads();
     const cx<T>* ib = a.in + ((size_t)g * a.n0 + r0) * a.n1;
     for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
         const int l = idx / a.n1, e = idx - l * a.n1;
-        s[e * a.LP + l] = ib[(size_t)l * a.n1 + e];
+        s[(INV ? pos[e] : e) * a.LP + l] = ib[(size_t)l * a.n1 + e];
     }
     __syncthreads();
     slab_fft<INV, T>(s, nl, 1, a.LP, a.plan, tw);
     cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * a.n1;
     for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
         const int l = idx / a.n1, e = idx - l * a.n1;
-        ob[(size_t)l * a.n1 + e] = s[e * a.LP + l];
+        ob[(size_t)l * a.n1 + e] = s[(INV ? e : pos[e]) * a.LP + l];
     }
 }
 
-// ------------------------------------------------------------------ low-pass tile
+// ------------------------------------------------------------------ Fourier low-pass tile (generic phi)
 template <typename T> struct LowArgs {
-    const cx<T>* in;      // [G][P0][P1] scrambled spectra
-    const T* filt;        // [P0][P1] real scrambled low-pass at this resolution
+    const cx<T>* in;      // [G][P0][P1] natural-order spectra
+    const T* filt;        // [P0][P1] real low-pass at this resolution
+    const int2* supp;     // [P0]
     T* out;               // [B][K][m0-2][m1-2]
     int P0, P1, k, m0, m1, W;
     int PP, NF, ch0, chs, K;
     T scale;
-    Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1;
+    Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
 };
 // grid (G).  One CTA: periodise (in*filt) to m0 x m1, inverse 2-D DIT in shared memory,
 // keep the real part, crop one sample per side (unpad) and write the channel plane.
@@ -183,25 +239,19 @@ template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_lowpass
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw0 = s + (size_t)a.m0 * a.W;
     cx<T>* tw1 = tw0 + a.m0;
+    int* pos0 = reinterpret_cast<int*>(tw1 + a.m1);
+    int* pos1 = pos0 + a.m0;
     const int g = blockIdx.x;
     const int b = g / a.PP, path = g - b * a.PP;
     const int ch = a.ch0 + (path / a.NF) * a.chs + (path % a.NF);
-    copy_tw(tw0, a.tw0, a.m0);
-    copy_tw(tw1, a.tw1, a.m1);
+    stage(tw0, a.tw0, a.m0); stage(tw1, a.tw1, a.m1);
+    stage(pos0, a.pos0, a.m0); stage(pos1, a.pos1, a.m1);
+    __syncthreads();
     const cx<T>* pb = a.in + (size_t)g * a.P0 * a.P1;
-    const int k = a.k;
     for (int idx = flat_tid(); idx < a.m0 * a.m1; idx += flat_nt()) {
         const int r = idx / a.m1, e = idx - r * a.m1;
-        T ax = T(0), ay = T(0);
-        for (int c = 0; c < k; ++c) {
-            const size_t off = (size_t)(r * k + c) * a.P1 + (size_t)e * k;
-            for (int d = 0; d < k; ++d) {
-                const cx<T> v = pb[off + d];
-                const T f = a.filt[off + d];
-                ax += v.x * f; ay += v.y * f;
-            }
-        }
-        s[r * a.W + e] = mk<T>(ax * a.scale, ay * a.scale);
+        const cx<T> v = prod_fold<T>(pb, a.filt, a.supp, r, e, a.k, a.m0, a.m1, a.P1);
+        s[pos0[r] * a.W + pos1[e]] = scal(v, a.scale);
     }
     __syncthreads();
     slab_fft<true, T>(s, a.m0, a.W, 1, a.plan1, tw1);   // along rows (length m1)
@@ -231,13 +281,130 @@ template <typename T> __global__ void k2d_crop_real(CropArgs<T> a) {
     a.out[((size_t)b * a.K + ch) * o0 * o1 + idx] = a.in[((size_t)g * a.m0 + y + 1) * a.m1 + x + 1].x;
 }
 
-// ------------------------------------------------------------------ filter scramble
-// dst[pos0[r]][pos1[c]] = src[r][c]  (natural -> canonical scrambled, per axis)
-template <typename T>
-__global__ void k2d_scramble(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ pos0,
-                             const int* __restrict__ pos1, int n0, int n1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c < n1) dst[(size_t)pos0[r] * n1 + pos1[c]] = src[(size_t)r * n1 + c];
+// ------------------------------------------------------------------ fused tile kernel
+// One CTA = one scattering path (image b, parent, filter):
+//   Z      = periodise_k(parent * filt) * scale                       (n0 x n1, Fourier)
+//   u      = ifft2(Z)                                                 (shared memory)
+//   U      = |u|
+//   S      = unpad( (U conv g)[::kl, ::kl] ),  g = taps0 (x) taps1   -> out[b][ch]
+//   spec   = fft2(U)   (only when spec_out != nullptr)                -> spec_out[g]
+// The separable spatial low-pass equals the reference's Fourier-domain
+// cdgmm(phi) -> subsample_fourier -> irfft -> unpad chain (core/scattering2d.py:42-47)
+// whenever phi_hat = a_hat (x) b_hat / phi_hat[0][0]; the plan verifies this when binding.
+template <typename T> struct TileArgs {
+    const cx<T>* parent; const T* const* filt; const int2* supp;
+    cx<T>* spec_out; T* out;
+    int P0, P1, k, n0, n1, W, NF;
+    T scale;
+    Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
+    const T* taps0; const T* taps1;        // taps[i] multiplies input index kl*(o+1) - (tlo + i)
+    int t0lo, t0cnt, t1lo, t1cnt, kl;
+    int o0, o1, o1p;
+    int PP, NFch, ch0, chs, K;
+};
+
+template <typename T> struct TileSmem {
+    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* taps0; T* taps1; int* pos0; int* pos1;
+};
+template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return o; };
+    const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
+    const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
+    const size_t o_supp = take(sizeof(int2) * a.P0);
+    const size_t o_w1 = take(sizeof(T) * (size_t)a.n0 * a.o1p);
+    const size_t o_t0 = take(sizeof(T) * a.t0cnt), o_t1 = take(sizeof(T) * a.t1cnt);
+    const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
+    if (L) {
+#ifdef __CUDA_ARCH__
+        unsigned char* base = dyn_smem<unsigned char>();
+        L->tile = reinterpret_cast<cx<T>*>(base + o_tile);
+        L->tw0 = reinterpret_cast<cx<T>*>(base + o_tw0); L->tw1 = reinterpret_cast<cx<T>*>(base + o_tw1);
+        L->supp = reinterpret_cast<int2*>(base + o_supp);
+        L->w1 = reinterpret_cast<T*>(base + o_w1);
+        L->taps0 = reinterpret_cast<T*>(base + o_t0); L->taps1 = reinterpret_cast<T*>(base + o_t1);
+        L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
+#endif
+    }
+    return off;
+}
+
+template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_tile(TileArgs<T> a) {
+    TileSmem<T> m;
+    tile_smem_layout(a, &m);
+    cx<T>* s = m.tile;
+    const int g = blockIdx.x;
+    const int fi = g % a.NF, pg = g / a.NF;
+    const int b = g / a.PP, path = g - b * a.PP;
+    const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
+    stage(m.tw0, a.tw0, a.n0); stage(m.tw1, a.tw1, a.n1);
+    stage(m.pos0, a.pos0, a.n0); stage(m.pos1, a.pos1, a.n1);
+    stage(m.taps0, a.taps0, a.t0cnt); stage(m.taps1, a.taps1, a.t1cnt);
+    stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
+    __syncthreads();
+    // 1. product + periodise, scattered into scrambled (DIT-input) order
+    {
+        const cx<T>* pb = a.parent + (size_t)pg * a.P0 * a.P1;
+        const T* fb = a.filt[fi];
+        for (int idx = flat_tid(); idx < a.n0 * a.n1; idx += flat_nt()) {
+            const int r = idx / a.n1, e = idx - r * a.n1;
+            const cx<T> v = prod_fold<T>(pb, fb, m.supp, r, e, a.k, a.n0, a.n1, a.P1);
+            s[m.pos0[r] * a.W + m.pos1[e]] = scal(v, a.scale);
+        }
+    }
+    __syncthreads();
+    // 2. inverse 2-D FFT -> natural-order spatial field
+    slab_fft<true, T>(s, a.n0, a.W, 1, a.plan1, m.tw1);
+    slab_fft<true, T>(s, a.n1, 1, a.W, a.plan0, m.tw0);
+    // 3. modulus (kept in .x; .y zeroed for the optional forward transform)
+    for (int y = threadIdx.y; y < a.n0; y += blockDim.y)
+        for (int x = threadIdx.x; x < a.n1; x += blockDim.x) {
+            const cx<T> v = s[y * a.W + x];
+            s[y * a.W + x] = mk<T>(sqrt(v.x * v.x + v.y * v.y), T(0));
+        }
+    __syncthreads();
+    // 4a. horizontal low-pass + decimation: w1[y][xo] = sum_i taps1[i] * U[y][kl*(xo+1) - (t1lo+i)]
+    for (int xo = threadIdx.y; xo < a.o1; xo += blockDim.y) {
+        const int c = a.kl * (xo + 1) - a.t1lo;
+        for (int y = threadIdx.x; y < a.n0; y += blockDim.x) {
+            const cx<T>* row = s + y * a.W;
+            T acc = T(0);
+            int x = c % a.n1; if (x < 0) x += a.n1;
+            for (int i = 0; i < a.t1cnt; ++i) {
+                acc += m.taps1[i] * row[x].x;
+                x = (x == 0) ? a.n1 - 1 : x - 1;
+            }
+            m.w1[y * a.o1p + xo] = acc;
+        }
+    }
+    __syncthreads();
+    // 4b. vertical low-pass + decimation + unpad, straight to the output plane
+    {
+        T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+        for (int yo = threadIdx.y; yo < a.o0; yo += blockDim.y) {
+            const int c = a.kl * (yo + 1) - a.t0lo;
+            int y0 = c % a.n0; if (y0 < 0) y0 += a.n0;
+            for (int xo = threadIdx.x; xo < a.o1; xo += blockDim.x) {
+                T acc = T(0);
+                int y = y0;
+                for (int i = 0; i < a.t0cnt; ++i) {
+                    acc += m.taps0[i] * m.w1[y * a.o1p + xo];
+                    y = (y == 0) ? a.n0 - 1 : y - 1;
+                }
+                ob[yo * a.o1 + xo] = acc;
+            }
+        }
+    }
+    // 5. forward 2-D FFT of U for the children of this path
+    if (a.spec_out) {
+        slab_fft<false, T>(s, a.n0, a.W, 1, a.plan1, m.tw1);
+        slab_fft<false, T>(s, a.n1, 1, a.W, a.plan0, m.tw0);
+        cx<T>* ob = a.spec_out + (size_t)g * a.n0 * a.n1;
+        for (int idx = flat_tid(); idx < a.n0 * a.n1; idx += flat_nt()) {
+            const int r = idx / a.n1, e = idx - r * a.n1;
+            ob[idx] = s[m.pos0[r] * a.W + m.pos1[e]];
+        }
+    }
 }
 
 }  // namespace sb

@@ -1,10 +1,16 @@
 // plan2d.cuh - host orchestration of the fused 2-D scattering forward.
 //
 // Mirrors the loop of kymatio/scattering2d/core/scattering2d.py:14-86, restructured into
-// grouped launches: one (row-pass, column-pass, row-pass, low-pass) quartet per first-order
-// scale j1 and per (j1, j2) second-order pair, each launch covering batch x angles.
+// grouped launches (each covering batch x angles):
+//   * U0 = fft2(pad(x))                       pad+row pass, column pass
+//   * S0                                      Fourier low-pass tile
+//   * per first-order scale j1                ONE tile kernel (product, ifft2, modulus, spatial
+//                                             low-pass -> S1, optional fft2 -> U1) when the field
+//                                             fits one CTA, else three streaming passes + low-pass
+//   * per (j1 < j2) second-order pair         ONE tile kernel -> S2 (same fallback)
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "../../include/scat_b200.h"
@@ -31,10 +37,40 @@ struct Axis {
 };
 struct Level2D { Axis a0, a1; };
 
+// separable spatial low-pass derived from phi_hat at one resolution
+struct FirLevel {
+    bool ok = false;
+    int t0lo = 0, t0cnt = 0, t1lo = 0, t1cnt = 0;
+    size_t taps0_off = 0, taps1_off = 0;
+};
+
+// per-row circular support interval of a real filter (natural order)
+template <typename T>
+inline void row_supports(const T* f, int n0, int n1, double rel_thr, int2* out) {
+    double mx = 0;
+    for (size_t i = 0; i < (size_t)n0 * n1; ++i) mx = std::max(mx, (double)std::fabs(f[i]));
+    const double thr = rel_thr * mx;
+    for (int r = 0; r < n0; ++r) {
+        const T* row = f + (size_t)r * n1;
+        int first = -1, last = -1, prev = -1, best_gap = -1, best_end = -1;
+        for (int c = 0; c < n1; ++c) {
+            if (std::fabs((double)row[c]) > thr) {
+                if (first < 0) first = c;
+                if (prev >= 0 && c - prev - 1 > best_gap) { best_gap = c - prev - 1; best_end = c; }
+                prev = c; last = c;
+            }
+        }
+        if (first < 0) { out[r] = make_int2(0, 0); continue; }
+        const int wrap_gap = first + n1 - last - 1;           // zeros between last and first, circularly
+        if (wrap_gap >= best_gap) out[r] = make_int2(first, last - first + 1);
+        else out[r] = make_int2(best_end, n1 - best_gap);     // support starts after the largest gap
+    }
+}
+
 template <typename T> class Plan2D final : public scat_plan2d {
 public:
     explicit Plan2D(const scat_plan2d_desc& d) : d_(d) {
-        if (d.J < 0 || d.L < 1) throw std::runtime_error("invalid J or L");
+        if (d.J < 1 || d.L < 1) throw std::runtime_error("J and L must be >= 1");
         if (d.max_order != 1 && d.max_order != 2) throw std::runtime_error("max_order must be 1 or 2");
         const int s = 1 << d.J;
         if (d.pre_pad) {
@@ -52,8 +88,9 @@ public:
         if (o0_ < 1 || o1_ < 1) throw std::runtime_error("padded size too small for unpad");
         K_ = 1 + d.L * d.J + (d.max_order == 2 ? d.L * d.L * d.J * (d.J - 1) / 2 : 0);
 
-        // levels 0..J, tables
         size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+        // levels 0..J: twiddles and scramble tables per axis
         lev_.resize(d.J + 1);
         for (int j = 0; j <= d.J; ++j) {
             Axis* ax[2] = {&lev_[j].a0, &lev_[j].a1};
@@ -61,55 +98,55 @@ public:
             for (int a = 0; a < 2; ++a) {
                 ax[a]->n = nn[a];
                 ax[a]->plan = make_plan1(nn[a]);
-                ax[a]->tw_off = off; off = align_up(off + (size_t)nn[a] * sizeof(cx<T>), 256);
-                ax[a]->pos_off = off; off = align_up(off + (size_t)nn[a] * sizeof(int), 256);
+                ax[a]->tw_off = take((size_t)nn[a] * sizeof(cx<T>));
+                ax[a]->pos_off = take((size_t)nn[a] * sizeof(int));
             }
         }
         tables_bytes_ = off;
-        host_tables_.assign(tables_bytes_, 0);
+        host_const_.assign(tables_bytes_, 0);
         for (int j = 0; j <= d.J; ++j) {
             const Axis* ax[2] = {&lev_[j].a0, &lev_[j].a1};
             for (int a = 0; a < 2; ++a) {
                 auto tw = twiddle_table<T>(ax[a]->n);
                 auto pos = scramble_table(ax[a]->plan);
-                std::memcpy(host_tables_.data() + ax[a]->tw_off, tw.data(), (size_t)ax[a]->n * sizeof(cx<T>));
-                std::memcpy(host_tables_.data() + ax[a]->pos_off, pos.data(), (size_t)ax[a]->n * sizeof(int));
+                std::memcpy(host_const_.data() + ax[a]->tw_off, tw.data(), (size_t)ax[a]->n * sizeof(cx<T>));
+                std::memcpy(host_const_.data() + ax[a]->pos_off, pos.data(), (size_t)ax[a]->n * sizeof(int));
             }
         }
-        // scrambled filter bank
-        phi_off_.resize(d.J);
-        for (int j = 0; j < d.J; ++j) { phi_off_[j] = off; off = align_up(off + fsize(j) * sizeof(T), 256); }
-        psi_off_.resize(d.J);
+        // filter-derived tables (filled by bind): pointer arrays, supports, FIR taps
+        phi_supp_off_.resize(d.J); fir_.resize(d.J);
+        phi_ptrslot_off_ = take((size_t)d.J * sizeof(void*));
+        for (int j = 0; j < d.J; ++j) {
+            phi_supp_off_[j] = take((size_t)lev_[j].a0.n * sizeof(int2));
+            fir_[j].taps0_off = take((size_t)lev_[j].a0.n * sizeof(T));
+            fir_[j].taps1_off = take((size_t)lev_[j].a1.n * sizeof(T));
+        }
+        psi_ptr_off_.resize(d.J); psi_supp_off_.resize(d.J);
         n_psi_expected_ = 0;
         for (int j = 0; j < d.J; ++j) {
             const int nres = std::min(j + 1, std::max(d.J - 1, 1));   // filter_bank.py:40
-            psi_off_[j].resize(nres);
+            psi_ptr_off_[j].resize(nres); psi_supp_off_[j].resize(nres);
             for (int r = 0; r < nres; ++r) {
-                psi_off_[j][r] = off;
-                off = align_up(off + (size_t)d.L * fsize(r) * sizeof(T), 256);
+                psi_ptr_off_[j][r] = take((size_t)d.L * sizeof(void*));
+                psi_supp_off_[j][r] = take((size_t)d.L * lev_[r].a0.n * sizeof(int2));
             }
             n_psi_expected_ += d.L * nres;
         }
         const_bytes_ = off;
+        host_const_.resize(const_bytes_, 0);
 
         // slab configurations per level
         row_cfg_.resize(d.J + 1); col_cfg_.resize(d.J + 1);
         for (int j = 0; j <= d.J; ++j) {
-            row_cfg_[j] = slab_cfg(lev_[j].a1.plan, lev_[j].a0.n, sizeof(cx<T>));
-            col_cfg_[j] = slab_cfg(lev_[j].a0.plan, lev_[j].a1.n, sizeof(cx<T>));
+            row_cfg_[j] = slab_cfg(lev_[j].a1.plan, lev_[j].a0.n, sizeof(cx<T>), sizeof(int));
+            col_cfg_[j] = slab_cfg(lev_[j].a0.plan, lev_[j].a1.n, sizeof(cx<T>), sizeof(int));
         }
         lowW_ = m1_ | 1;
-        low_smem_ = ((size_t)m0_ * lowW_ + m0_ + m1_) * sizeof(cx<T>);
+        low_smem_ = ((size_t)m0_ * lowW_ + m0_ + m1_) * sizeof(cx<T>) + (size_t)(m0_ + m1_) * sizeof(int);
         low_tile_ = low_smem_ <= 96 * 1024;
-
-        // workspace per image, in cx<T> elements
-        const size_t lvl0 = (size_t)P0_ * P1_;
-        ws_u0_ = lvl0;
-        ws_u1_ = d.J >= 1 ? (size_t)d.L * lvl0 : 0;
-        ws_u2_ = (d.max_order == 2 && d.J >= 2) ? (size_t)d.L * d.L * lev_[1].a0.n * lev_[1].a1.n : 0;
-        ws_low_ = 0;
-        if (!low_tile_) ws_low_ = (size_t)std::max(1, (d.max_order == 2 && d.J >= 2) ? d.L * d.L : d.L) * m0_ * m1_;
-        per_img_ = (ws_u0_ + ws_u1_ + ws_u2_ + ws_low_) * sizeof(cx<T>);
+        tile_ok_.assign(d.J, false);
+        tile_smem_.assign(d.J, 0);
+        force_stream_ = env_int("SCAT_B200_NO_TILE", 0) != 0;
 
         enable_big_smem(k2d_pad_rowfft<T>);
         enable_big_smem(k2d_colpass<T, COL_FWD>);
@@ -119,35 +156,62 @@ public:
         enable_big_smem(k2d_rowpass<T, false>);
         enable_big_smem(k2d_rowpass<T, true>);
         enable_big_smem(k2d_lowpass<T>);
+        enable_big_smem(k2d_tile<T>);
+        compute_workspace();
     }
 
     void info(int32_t* Mp, int32_t* Np, int32_t* oh, int32_t* ow, int32_t* K) const override {
-        if (Mp) *Mp = P0_; if (Np) *Np = P1_; if (oh) *oh = o0_; if (ow) *ow = o1_; if (K) *K = K_;
+        if (Mp) *Mp = P0_;
+        if (Np) *Np = P1_;
+        if (oh) *oh = o0_;
+        if (ow) *ow = o1_;
+        if (K) *K = K_;
     }
     size_t const_bytes() const override { return const_bytes_; }
 
+    // Analyse the filter bank on the host (supports, separable low-pass taps) and upload the tables.
     void bind(void* const_dev, const void* const* phi, int n_phi, const void* const* psi, int n_psi,
               cudaStream_t st) override {
         if (!const_dev) throw std::runtime_error("const buffer is null");
         if (n_phi != d_.J) throw std::runtime_error("expected J low-pass levels");
         if (n_psi != n_psi_expected_) throw std::runtime_error("unexpected number of band-pass levels");
         cbuf_ = static_cast<unsigned char*>(const_dev);
-        SB_CUDA(cudaMemcpyAsync(cbuf_, host_tables_.data(), tables_bytes_, cudaMemcpyHostToDevice, st));
-        auto scramble = [&](const void* src, size_t dst_off, int res) {
-            const int n0 = lev_[res].a0.n, n1 = lev_[res].a1.n;
-            dim3 grid(ceil_div(n1, 128), n0);
-            launch("scramble", 2.0 * n0 * n1 * sizeof(T), st, [&] {
-                k2d_scramble<T><<<grid, 128, 0, st>>>(static_cast<const T*>(src), reinterpret_cast<T*>(cbuf_ + dst_off),
-                                                       pos(lev_[res].a0), pos(lev_[res].a1), n0, n1);
-            });
+        const double supp_thr = 1e-7;
+        std::vector<T> host;
+        auto fetch = [&](const void* dev, int res) {
+            host.resize(fsize(res));
+            SB_CUDA(cudaMemcpyAsync(host.data(), dev, fsize(res) * sizeof(T), cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
         };
-        for (int j = 0; j < d_.J; ++j) scramble(phi[j], phi_off_[j], j);
+        phi_ptr_.assign(phi, phi + n_phi);
+        for (int j = 0; j < d_.J; ++j) {
+            reinterpret_cast<const void**>(host_const_.data() + phi_ptrslot_off_)[j] = phi[j];
+            fetch(phi[j], j);
+            const int n0 = lev_[j].a0.n, n1 = lev_[j].a1.n;
+            row_supports<T>(host.data(), n0, n1, supp_thr, reinterpret_cast<int2*>(host_const_.data() + phi_supp_off_[j]));
+            analyse_lowpass(host.data(), j);
+        }
         int n = 0;
         for (int j = 0; j < d_.J; ++j)
             for (int th = 0; th < d_.L; ++th)
-                for (size_t r = 0; r < psi_off_[j].size(); ++r)
-                    scramble(psi[n++], psi_off_[j][r] + (size_t)th * fsize((int)r) * sizeof(T), (int)r);
+                for (size_t r = 0; r < psi_ptr_off_[j].size(); ++r) {
+                    const void* p = psi[n++];
+                    reinterpret_cast<const void**>(host_const_.data() + psi_ptr_off_[j][r])[th] = p;
+                    fetch(p, (int)r);
+                    row_supports<T>(host.data(), lev_[r].a0.n, lev_[r].a1.n, supp_thr,
+                                    reinterpret_cast<int2*>(host_const_.data() + psi_supp_off_[j][r]) +
+                                        (size_t)th * lev_[r].a0.n);
+                }
+        SB_CUDA(cudaMemcpyAsync(cbuf_, host_const_.data(), const_bytes_, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st));   // host_const_ may be rewritten by the next bind
+        // which levels can run as one-CTA tiles
+        for (int j = 0; j < d_.J; ++j) {
+            TileArgs<T> a = tile_args_geometry(j);
+            tile_smem_[j] = tile_smem_layout<T>(a, nullptr);
+            tile_ok_[j] = !force_stream_ && fir_[j].ok && tile_smem_[j] <= kMaxDynSmem;
+        }
         bound_ = true;
+        compute_workspace();
     }
 
     size_t workspace_bytes(int64_t batch) const override {
@@ -175,32 +239,98 @@ private:
     size_t fsize(int res) const { return (size_t)lev_[res].a0.n * lev_[res].a1.n; }
     const cx<T>* tw(const Axis& a) const { return reinterpret_cast<const cx<T>*>(cbuf_ + a.tw_off); }
     const int* pos(const Axis& a) const { return reinterpret_cast<const int*>(cbuf_ + a.pos_off); }
-    const T* phi(int j) const { return reinterpret_cast<const T*>(cbuf_ + phi_off_[j]); }
-    const T* psi(int j, int res) const { return reinterpret_cast<const T*>(cbuf_ + psi_off_[j][res]); }
+    const T* phi(int j) const { return static_cast<const T*>(phi_ptr_[j]); }
+    const int2* phi_supp(int j) const { return reinterpret_cast<const int2*>(cbuf_ + phi_supp_off_[j]); }
+    const T* const* psi_ptrs(int j, int res) const {
+        return reinterpret_cast<const T* const*>(cbuf_ + psi_ptr_off_[j][res]);
+    }
+    const int2* psi_supp(int j, int res) const { return reinterpret_cast<const int2*>(cbuf_ + psi_supp_off_[j][res]); }
 
-    // out[G][n0][n1] = rows-inverse-DIT( periodise_k( parent * filt ) ), G = Bp * NF
-    void row_prod(const cx<T>* parent, const T* filt, cx<T>* out, int parent_res, int out_res, int Bp, int NF,
-                  T scale, cudaStream_t st) {
+    // phi_hat[u][v] ~ a[u] b[v] / phi_hat[0][0]  ->  spatial taps (SURVEY Appendix A identity:
+    // ifft(periodise_k(X)) = ifft(X)[::k], so the Fourier low-pass is a decimated circular convolution)
+    void analyse_lowpass(const T* f, int j) {
+        FirLevel& F = fir_[j];
+        F.ok = false;
+        const int n0 = lev_[j].a0.n, n1 = lev_[j].a1.n;
+        const double c = (double)f[0];
+        if (!(std::fabs(c) > 0)) return;
+        double resid = 0;
+        for (int u = 0; u < n0; ++u)
+            for (int v = 0; v < n1; ++v)
+                resid = std::max(resid, std::fabs((double)f[(size_t)u * n1 + v] * c -
+                                                  (double)f[(size_t)u * n1] * (double)f[v]));
+        if (resid > 4e-6 * c * c) return;   // not separable to float32 rounding: keep the Fourier low-pass
+        const double tau = 6.283185307179586476925286766559;
+        auto taps = [&](int n, int stride, double norm, int& tlo, int& tcnt, size_t off) {
+            std::vector<double> a(n);
+            double mx = 0;
+            for (int y = 0; y < n; ++y) {
+                double acc = 0;
+                for (int u = 0; u < n; ++u) acc += (double)f[(size_t)u * stride] * std::cos(tau * (double)((long long)u * y % n) / n);
+                a[y] = acc / n / norm;
+                mx = std::max(mx, std::fabs(a[y]));
+            }
+            int R = 0;
+            for (int y = 0; y < n; ++y)
+                if (std::fabs(a[y]) > 1e-6 * mx) R = std::max(R, std::min(y, n - y));
+            if (2 * R + 1 >= n) { tlo = 0; tcnt = n; } else { tlo = -R; tcnt = 2 * R + 1; }
+            T* dst = reinterpret_cast<T*>(host_const_.data() + off);
+            for (int i = 0; i < tcnt; ++i) dst[i] = (T)a[((tlo + i) % n + n) % n];
+        };
+        taps(n0, n1, 1.0, F.t0lo, F.t0cnt, F.taps0_off);   // column 0 of phi_hat: f[u*n1]
+        taps(n1, 1, c, F.t1lo, F.t1cnt, F.taps1_off);      // row 0 of phi_hat:    f[v]
+        F.ok = true;
+    }
+
+    TileArgs<T> tile_args_geometry(int res) const {
+        TileArgs<T> a{};
+        a.P0 = lev_[0].a0.n;   // worst case for the staged support rows
+        a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n; a.W = a.n1 | 1;
+        a.o0 = o0_; a.o1 = o1_; a.o1p = o1_ | 1;
+        a.t0cnt = fir_[res].t0cnt; a.t1cnt = fir_[res].t1cnt;
+        return a;
+    }
+
+    void compute_workspace() {
+        const int J = d_.J, L = d_.L;
+        const size_t lvl0 = (size_t)P0_ * P1_;
+        ws_u0_ = lvl0;
+        ws_u1_ = (size_t)L * lvl0;
+        // U2 is only materialised when a second-order scale has to stream
+        ws_u2_ = 0;
+        if (d_.max_order == 2)
+            for (int j2 = 1; j2 < J; ++j2)
+                if (!bound_ || !tile_ok_[j2]) ws_u2_ = std::max(ws_u2_, (size_t)L * L * fsize(j2));
+        ws_low_ = low_tile_ ? 0 : (size_t)std::max(1, d_.max_order == 2 && J >= 2 ? L * L : L) * m0_ * m1_;
+        per_img_ = (ws_u0_ + ws_u1_ + ws_u2_ + ws_low_) * sizeof(cx<T>);
+    }
+
+    // ---------------------------------------------------------------- launch wrappers
+    // out[G][n0][n1] = rows-inverse( periodise_k( parent * filt ) ), G = Bp * NF
+    void row_prod(const cx<T>* parent, const T* const* filt, const int2* supp, cx<T>* out, int parent_res,
+                  int out_res, int Bp, int NF, T scale, cudaStream_t st) {
         RowProdArgs<T> a{};
-        a.parent = parent; a.filt = filt; a.out = out;
+        a.parent = parent; a.filt = filt; a.supp = supp; a.out = out;
         a.P0 = lev_[parent_res].a0.n; a.P1 = lev_[parent_res].a1.n;
         a.k = 1 << (out_res - parent_res);
         a.n0 = lev_[out_res].a0.n; a.n1 = lev_[out_res].a1.n;
-        a.NP = 1; a.NF = NF; a.scale = scale;
+        a.NF = NF; a.scale = scale;
         const SlabCfg& c = row_cfg_[out_res];
-        a.lines = c.lines; a.LP = c.LP; a.plan = lev_[out_res].a1.plan; a.tw = tw(lev_[out_res].a1);
+        a.lines = c.lines; a.LP = c.LP; a.plan = lev_[out_res].a1.plan;
+        a.tw = tw(lev_[out_res].a1); a.pos = pos(lev_[out_res].a1);
         dim3 grid((unsigned)(Bp * NF), ceil_div(a.n0, c.lines));
         const double G = (double)Bp * NF;
         const double bytes = G * a.P0 * a.P1 * sizeof(cx<T>) + (double)NF * a.P0 * a.P1 * sizeof(T) +
                              G * a.n0 * a.n1 * sizeof(cx<T>);
-        launch("rowpass_prod:L" + std::to_string(parent_res) + ">L" + std::to_string(out_res), bytes, st,
-               [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
+        launch("rowpass_prod:L" + std::to_string(parent_res) + ">L" + std::to_string(out_res) + ":G" +
+                   std::to_string((int)G / std::max(1, last_B_)),
+               bytes, st, [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
     }
     template <int MODE> void col_pass(cx<T>* data, int res, int G, cudaStream_t st) {
         ColArgs<T> a{};
         a.in = data; a.out = data; a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n;
         const SlabCfg& c = col_cfg_[res];
-        a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a0.plan; a.tw = tw(lev_[res].a0);
+        a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a0.plan; a.tw = tw(lev_[res].a0); a.pos = pos(lev_[res].a0);
         dim3 grid((unsigned)G, ceil_div(a.n1, c.lines));
         launch(std::string(MODE == COL_FWD ? "colpass_fwd" : MODE == COL_INV ? "colpass_inv" : "colpass_inv_mod_fwd") +
                    ":L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
@@ -211,25 +341,26 @@ private:
         RowArgs<T> a{};
         a.in = data; a.out = data; a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n;
         const SlabCfg& c = row_cfg_[res];
-        a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a1.plan; a.tw = tw(lev_[res].a1);
+        a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a1.plan; a.tw = tw(lev_[res].a1); a.pos = pos(lev_[res].a1);
         dim3 grid((unsigned)G, ceil_div(a.n0, c.lines));
         launch(std::string(INV ? "rowpass_inv" : "rowpass_fwd") + ":L" + std::to_string(res) + ":G" +
                    std::to_string(G / std::max(1, last_B_)),
                2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
                [&] { k2d_rowpass<T, INV><<<grid, c.block, c.smem, st>>>(a); });
     }
-    // S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra at resolution res
+    // Fourier low-pass: S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
                   cudaStream_t st) {
         const int k = 1 << (d_.J - res);
         const T scale = T(1) / (T(k) * T(k) * T(m0_) * T(m1_));
+        const int J = d_.J;
         if (low_tile_) {
             LowArgs<T> a{};
-            a.in = spec; a.filt = phi(res); a.out = out;
+            a.in = spec; a.filt = phi(res); a.supp = phi_supp(res); a.out = out;
             a.P0 = lev_[res].a0.n; a.P1 = lev_[res].a1.n; a.k = k; a.m0 = m0_; a.m1 = m1_; a.W = lowW_;
             a.PP = PP; a.NF = NF; a.ch0 = ch0; a.chs = chs; a.K = K_; a.scale = scale;
-            a.plan0 = lev_[d_.J].a0.plan; a.plan1 = lev_[d_.J].a1.plan;
-            a.tw0 = tw(lev_[d_.J].a0); a.tw1 = tw(lev_[d_.J].a1);
+            a.plan0 = lev_[J].a0.plan; a.plan1 = lev_[J].a1.plan;
+            a.tw0 = tw(lev_[J].a0); a.tw1 = tw(lev_[J].a1); a.pos0 = pos(lev_[J].a0); a.pos1 = pos(lev_[J].a1);
             const double G = (double)B * PP;
             launch("lowpass:L" + std::to_string(res) + ":G" + std::to_string(PP),
                    G * a.P0 * a.P1 * sizeof(cx<T>) + (double)a.P0 * a.P1 * sizeof(T) + G * o0_ * o1_ * sizeof(T), st,
@@ -238,16 +369,16 @@ private:
             // streaming fallback for outputs too large for one CTA
             const int G = B * PP;
             RowProdArgs<T> a{};
-            a.parent = spec; a.filt = phi(res); a.out = tmp;
+            a.parent = spec; a.filt = phi_ptr_dev(res); a.supp = phi_supp(res); a.out = tmp;
             a.P0 = lev_[res].a0.n; a.P1 = lev_[res].a1.n; a.k = k; a.n0 = m0_; a.n1 = m1_;
-            a.NP = 1; a.NF = 1; a.scale = scale;
-            const SlabCfg& c = row_cfg_[d_.J];
-            a.lines = c.lines; a.LP = c.LP; a.plan = lev_[d_.J].a1.plan; a.tw = tw(lev_[d_.J].a1);
+            a.NF = 1; a.scale = scale;
+            const SlabCfg& c = row_cfg_[J];
+            a.lines = c.lines; a.LP = c.LP; a.plan = lev_[J].a1.plan; a.tw = tw(lev_[J].a1); a.pos = pos(lev_[J].a1);
             dim3 grid((unsigned)G, ceil_div(m0_, c.lines));
             launch("rowpass_prod(low):L" + std::to_string(res),
                    (double)G * (a.P0 * a.P1 + m0_ * m1_) * sizeof(cx<T>), st,
                    [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
-            col_pass<COL_INV>(tmp, d_.J, G, st);
+            col_pass<COL_INV>(tmp, J, G, st);
             CropArgs<T> ca{};
             ca.in = tmp; ca.out = out; ca.m0 = m0_; ca.m1 = m1_; ca.PP = PP; ca.NF = NF; ca.ch0 = ch0; ca.chs = chs;
             ca.K = K_;
@@ -255,6 +386,47 @@ private:
             launch("crop_real", (double)G * (m0_ * m1_ * sizeof(cx<T>) + o0_ * o1_ * sizeof(T)), st,
                    [&] { k2d_crop_real<T><<<g2, 256, 0, st>>>(ca); });
         }
+    }
+    // device-side one-entry pointer table for phi[res]
+    const T* const* phi_ptr_dev(int res) const {
+        return reinterpret_cast<const T* const*>(cbuf_ + phi_ptrslot_off_ + (size_t)res * sizeof(void*));
+    }
+
+    // fused tile: product/periodise from `parent` (resolution parent_res) with NF filters, ifft2,
+    // modulus, spatial low-pass to `out`, optional fft2 to `spec_out`
+    void tile(const cx<T>* parent, const T* const* filt, const int2* supp, int parent_res, int res, int Bp, int NF,
+              T* out, int PP, int NFch, int ch0, int chs, cx<T>* spec_out, const char* what, cudaStream_t st) {
+        TileArgs<T> a{};
+        a.parent = parent; a.filt = filt; a.supp = supp; a.spec_out = spec_out; a.out = out;
+        a.P0 = lev_[parent_res].a0.n; a.P1 = lev_[parent_res].a1.n;
+        a.k = 1 << (res - parent_res);
+        a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n; a.W = a.n1 | 1; a.NF = NF;
+        a.scale = T(1) / (T(a.k) * T(a.k) * T(a.n0) * T(a.n1));
+        a.plan0 = lev_[res].a0.plan; a.plan1 = lev_[res].a1.plan;
+        a.tw0 = tw(lev_[res].a0); a.tw1 = tw(lev_[res].a1); a.pos0 = pos(lev_[res].a0); a.pos1 = pos(lev_[res].a1);
+        const FirLevel& F = fir_[res];
+        a.taps0 = reinterpret_cast<const T*>(cbuf_ + F.taps0_off);
+        a.taps1 = reinterpret_cast<const T*>(cbuf_ + F.taps1_off);
+        a.t0lo = F.t0lo; a.t0cnt = F.t0cnt; a.t1lo = F.t1lo; a.t1cnt = F.t1cnt;
+        a.kl = 1 << (d_.J - res);
+        a.o0 = o0_; a.o1 = o1_; a.o1p = o1_ | 1;
+        a.PP = PP; a.NFch = NFch; a.ch0 = ch0; a.chs = chs; a.K = K_;
+        const size_t smem = tile_smem_layout<T>(a, nullptr);
+        const int G = Bp * NF;
+        // threads: enough to cover the larger pass (lines x butterflies) in about two rounds
+        int maxbf = 1;
+        for (int p = 0; p < a.plan1.npass; ++p) maxbf = std::max(maxbf, a.n1 / a.plan1.radix[p]);
+        const int items = a.n0 * maxbf;
+        // a tile that fills more than half the SM's shared memory runs alone: give it every thread
+        // the register budget allows; smaller tiles share the SM (3-4 CTAs) with ~items/8 threads each
+        int threads = (2 * smem > kMaxDynSmem) ? tile_threads_cap_
+                                               : std::min(tile_threads_cap_, std::max(96, (items / 8 + 31) / 32 * 32));
+        dim3 block(32, threads / 32);
+        const double bytes = (double)G * a.P0 * a.P1 * sizeof(cx<T>) + (double)NF * a.P0 * a.P1 * sizeof(T) +
+                             (double)G * o0_ * o1_ * sizeof(T) + (spec_out ? (double)G * a.n0 * a.n1 * sizeof(cx<T>) : 0.0);
+        launch(std::string("tile_") + what + ":L" + std::to_string(parent_res) + ">L" + std::to_string(res) + ":G" +
+                   std::to_string(G / std::max(1, last_B_)),
+               bytes, st, [&] { k2d_tile<T><<<(unsigned)G, block, smem, st>>>(a); });
     }
 
     void forward_chunk(const T* x, T* out, cx<T>* ws, int B, cudaStream_t st) {
@@ -270,33 +442,44 @@ private:
             a.x = x; a.out = U0; a.M = d_.pre_pad ? P0_ : d_.M; a.N = d_.pre_pad ? P1_ : d_.N;
             a.top = top_; a.left = left_; a.P0 = P0_; a.P1 = P1_;
             const SlabCfg& c = row_cfg_[0];
-            a.lines = c.lines; a.LP = c.LP; a.plan = lev_[0].a1.plan; a.tw = tw(lev_[0].a1);
+            a.lines = c.lines; a.LP = c.LP; a.plan = lev_[0].a1.plan; a.tw = tw(lev_[0].a1); a.pos = pos(lev_[0].a1);
             dim3 grid((unsigned)B, ceil_div(P0_, c.lines));
             launch("pad_rowfft", (double)B * (a.M * a.N * sizeof(T) + (double)P0_ * P1_ * sizeof(cx<T>)), st,
                    [&] { k2d_pad_rowfft<T><<<grid, c.block, c.smem, st>>>(a); });
             col_pass<COL_FWD>(U0, 0, B, st);
         }
-        // S0 (core/scattering2d.py:18-28); J == 0 has no filters: handled by the caller
-        if (J == 0) throw std::runtime_error("J = 0 is not supported");
+        // S0 (core/scattering2d.py:18-28)
         low_pass(U0, 0, out, B, 1, 1, 0, 0, TL, st);
         int ch2 = 1 + L * J;   // first second-order channel
         for (int j1 = 0; j1 < J; ++j1) {
-            // U1 = fft2(|ifft2(periodise(U0 * psi_j1))|)   (core:30-40)
-            const T sc1 = T(1) / (T(1 << j1) * T(1 << j1) * T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
-            row_prod(U0, psi(j1, 0), U1, 0, j1, B, L, sc1, st);
-            col_pass<COL_INV_MOD_FWD>(U1, j1, B * L, st);
-            row_pass<false>(U1, j1, B * L, st);
-            low_pass(U1, j1, out, B, L, L, 1 + j1 * L, 0, TL, st);   // core:42-51
+            const bool need_spec = d_.max_order == 2 && j1 < J - 1;
+            // U1 = fft2(|ifft2(periodise(U0 * psi_j1))|), S1 = low(U1)   (core:30-51)
+            if (tile_ok_[j1]) {
+                tile(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), 0, j1, B, L, out, L, L, 1 + j1 * L, 0,
+                     need_spec ? U1 : nullptr, need_spec ? "o1p" : "o1", st);
+            } else {
+                const T sc1 = T(1) / (T(1 << j1) * T(1 << j1) * T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
+                row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), U1, 0, j1, B, L, sc1, st);
+                col_pass<COL_INV_MOD_FWD>(U1, j1, B * L, st);
+                row_pass<false>(U1, j1, B * L, st);
+                low_pass(U1, j1, out, B, L, L, 1 + j1 * L, 0, TL, st);
+            }
             if (d_.max_order < 2) continue;
             const int nchild = (J - 1 - j1) * L;
             for (int j2 = j1 + 1; j2 < J; ++j2) {
-                // U2 = fft2(|ifft2(periodise(U1 * psi_j2[level j1]))|)   (core:55-68)
-                const int kk = 1 << (j2 - j1);
-                const T sc2 = T(1) / (T(kk) * T(kk) * T(lev_[j2].a0.n) * T(lev_[j2].a1.n));
-                row_prod(U1, psi(j2, j1), U2, j1, j2, B * L, L, sc2, st);
-                col_pass<COL_INV_MOD_FWD>(U2, j2, B * L * L, st);
-                row_pass<false>(U2, j2, B * L * L, st);
-                low_pass(U2, j2, out, B, L * L, L, ch2 + (j2 - j1 - 1) * L, nchild, TL, st);   // core:70-83
+                // U2 = fft2(|ifft2(periodise(U1 * psi_j2[level j1]))|), S2 = low(U2)   (core:55-83)
+                const int c0 = ch2 + (j2 - j1 - 1) * L;
+                if (tile_ok_[j2]) {
+                    tile(U1, psi_ptrs(j2, j1), psi_supp(j2, j1), j1, j2, B * L, L, out, L * L, L, c0, nchild,
+                         nullptr, "o2", st);
+                } else {
+                    const int kk = 1 << (j2 - j1);
+                    const T sc2 = T(1) / (T(kk) * T(kk) * T(lev_[j2].a0.n) * T(lev_[j2].a1.n));
+                    row_prod(U1, psi_ptrs(j2, j1), psi_supp(j2, j1), U2, j1, j2, B * L, L, sc2, st);
+                    col_pass<COL_INV_MOD_FWD>(U2, j2, B * L * L, st);
+                    row_pass<false>(U2, j2, B * L * L, st);
+                    low_pass(U2, j2, out, B, L * L, L, c0, nchild, TL, st);
+                }
             }
             ch2 += L * nchild;
         }
@@ -307,11 +490,18 @@ private:
     std::vector<Level2D> lev_;
     std::vector<SlabCfg> row_cfg_, col_cfg_;
     size_t tables_bytes_ = 0, const_bytes_ = 0;
-    std::vector<unsigned char> host_tables_;
-    std::vector<size_t> phi_off_;
-    std::vector<std::vector<size_t>> psi_off_;
+    std::vector<unsigned char> host_const_;
+    std::vector<const void*> phi_ptr_;
+    std::vector<size_t> phi_supp_off_;
+    std::vector<FirLevel> fir_;
+    std::vector<std::vector<size_t>> psi_ptr_off_, psi_supp_off_;
+    size_t phi_ptrslot_off_ = 0;
     int n_psi_expected_ = 0;
     int lowW_ = 0; size_t low_smem_ = 0; bool low_tile_ = true;
+    std::vector<bool> tile_ok_;
+    std::vector<size_t> tile_smem_;
+    bool force_stream_ = false;
+    int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 544);
     size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, per_img_ = 0;
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;

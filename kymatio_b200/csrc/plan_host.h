@@ -13,9 +13,12 @@ inline bool radix_compiled(int r) {
     return false;
 }
 
-// Factor n into DIF pass radices: odd primes (descending) first, then the power-of-two
-// part split into radices <= max_pow2 (largest first).  Throws for unsupported sizes.
-inline Plan1 make_plan1(int n, int max_pow2 = 16) {
+// Factor n into DIF pass radices: the power-of-two part split into radices <= max_pow2 and
+// the odd primes (descending).  pow2_first = true puts the power-of-two passes first, which
+// makes the natural -> scrambled scatter of consecutive frequencies hit distinct shared-memory
+// banks (pos jumps by odd multiples); false gives the "odd first" order whose scrambled
+// layout nests across resolutions.  Throws for unsupported sizes.
+inline Plan1 make_plan1(int n, int max_pow2 = 16, bool pow2_first = true) {
     if (n < 1) throw std::runtime_error("FFT length must be >= 1");
     Plan1 P{};
     P.n = n;
@@ -29,7 +32,7 @@ inline Plan1 make_plan1(int n, int max_pow2 = 16) {
     for (size_t i = 0; i < odd.size(); ++i)
         for (size_t j = i + 1; j < odd.size(); ++j)
             if (odd[j] > odd[i]) std::swap(odd[i], odd[j]);
-    std::vector<int> rad;
+    std::vector<int> rad, rad2;
     for (int p : odd) {
         if (!radix_compiled(p) && p > kMaxGenericRadix)
             throw std::runtime_error("FFT length " + std::to_string(n) + " has prime factor " +
@@ -42,8 +45,10 @@ inline Plan1 make_plan1(int n, int max_pow2 = 16) {
     if (two > 0) {
         int np = (two + lgmax - 1) / lgmax;
         int base = two / np, extra = two % np;
-        for (int i = 0; i < np; ++i) rad.push_back(1 << (base + (i < extra ? 1 : 0)));
+        for (int i = 0; i < np; ++i) rad2.push_back(1 << (base + (i < extra ? 1 : 0)));
     }
+    if (pow2_first) rad.insert(rad.begin(), rad2.begin(), rad2.end());
+    else rad.insert(rad.end(), rad2.begin(), rad2.end());
     if (rad.empty()) rad.push_back(1);  // n == 1: degenerate
     if ((int)rad.size() > kMaxPass) throw std::runtime_error("too many FFT passes");
     if (n == 1) { P.npass = 0; return P; }

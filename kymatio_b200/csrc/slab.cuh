@@ -8,30 +8,33 @@ namespace sb {
 // upper bound on threads per CTA for every slab kernel (caps registers at 65536/576 = 113)
 constexpr int kMaxThreads = 576;
 
+__device__ __forceinline__ int flat_tid() { return threadIdx.y * blockDim.x + threadIdx.x; }
+__device__ __forceinline__ int flat_nt() { return blockDim.x * blockDim.y; }
+
 // Transform `lines` lines of length P.n in shared memory, in place.
 //   element e of line l lives at s[l*lstride + e*estride]
 //   INV=false: DIF forward (natural -> scrambled); INV=true: DIT inverse, unnormalised
-// Thread mapping: threadIdx.x strides over lines (consecutive lanes -> consecutive
-// lines, which every caller lays out conflict-free), threadIdx.y strides over the
-// n/r butterflies of a pass.  One __syncthreads per pass; ends synchronised.
+// Work items (butterfly, line) are flattened over the whole CTA with the line index
+// fastest, so consecutive lanes touch consecutive lines (which every caller lays out
+// conflict-free) and any lines x butterflies shape keeps all threads busy.
+// One __syncthreads per pass; ends synchronised.
 template <bool INV, typename T>
 __device__ __noinline__ void slab_fft(cx<T>* s, int lines, int lstride, int estride, const Plan1& P,
                                       const cx<T>* tw) {
+    const int tid = flat_tid(), nt = flat_nt();
     for (int pp = 0; pp < P.npass; ++pp) {
         const int p = INV ? P.npass - 1 - pp : pp;
         const int r = P.radix[p], m = P.blen[p];
         const int q = m / r, nbf = P.n / r, tws = P.n / m;
-        for (int bf = threadIdx.y; bf < nbf; bf += blockDim.y) {
+        const int items = nbf * lines;
+        for (int it = tid; it < items; it += nt) {
+            const int bf = it / lines, line = it - bf * lines;
             const int blk = bf / q, i = bf - blk * q;
-            for (int line = threadIdx.x; line < lines; line += blockDim.x)
-                butterfly_dispatch<INV, T>(r, s + line * lstride, estride, blk * m + i, q, i * tws, tw, q > 1, P.n);
+            butterfly_dispatch<INV, T>(r, s + line * lstride, estride, blk * m + i, q, i * tws, tw, q > 1, P.n);
         }
         __syncthreads();
     }
 }
-
-__device__ __forceinline__ int flat_tid() { return threadIdx.y * blockDim.x + threadIdx.x; }
-__device__ __forceinline__ int flat_nt() { return blockDim.x * blockDim.y; }
 
 template <typename T>
 __device__ __forceinline__ void copy_tw(cx<T>* dst, const cx<T>* __restrict__ src, int n) {

@@ -24,8 +24,8 @@ static void run_passes(std::vector<cx<T>>& line, const Plan1& P, const std::vect
     }
 }
 
-template <typename T> static double check(int n, int max_pow2, double tol) {
-    Plan1 P = make_plan1(n, max_pow2);
+template <typename T> static double check(int n, int max_pow2, double tol, bool pow2_first) {
+    Plan1 P = make_plan1(n, max_pow2, pow2_first);
     auto tw = twiddle_table<T>(n);
     auto pos = scramble_table(P);
     const int estride = 3;
@@ -54,10 +54,10 @@ template <typename T> static double check(int n, int max_pow2, double tol) {
     }
     double e1 = err / nrm;
     // periodisation adjacency: for k = 2, 4 (if they divide the 2-part) aliases f + c*n/k are adjacent
-    for (int k = 2; k <= 8; k *= 2) {
+    for (int k = 2; k <= 8 && !pow2_first; k *= 2) {
         if (n % k) break;
         bool pow2part_ok = ((n / k) * k == n);
-        Plan1 Pc = make_plan1(n / k, max_pow2);
+        Plan1 Pc = make_plan1(n / k, max_pow2, false);
         auto posc = scramble_table(Pc);
         for (int u = 0; u < n / k && pow2part_ok; ++u)
             for (int c = 0; c < k; ++c) {
@@ -85,9 +85,10 @@ int main() {
     for (int n : sizes) {
         for (int mp : {16, 8, 4, 2}) {
             if (n > 300 && mp < 16) continue;
-            if (check<float>(n, mp, 2e-5) > 2e-5) ++bad;
+            if (check<float>(n, mp, 2e-5, false) > 2e-5) ++bad;
+            if (check<float>(n, mp, 2e-5, true) > 2e-5) ++bad;
         }
-        if (check<double>(n, 16, 1e-12) > 1e-12) ++bad;
+        if (check<double>(n, 16, 1e-12, true) > 1e-12) ++bad;
     }
     printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);
     return bad ? 1 : 0;
