@@ -185,6 +185,40 @@ struct Plan1 {
 
 constexpr bool ct_is_pow2(int r) { return (r & (r - 1)) == 0; }
 
+// Factor n into DIF pass radices (usable at compile time and on the host):
+//   power-of-two part split into balanced radices <= max_pow2, odd primes descending;
+//   pow2_first selects which group runs first in the DIF order.
+constexpr Plan1 ct_plan1(int n, int max_pow2 = 16, bool pow2_first = true) {
+    Plan1 P{};
+    P.n = n;
+    if (n <= 1) { P.npass = 0; return P; }
+    int two = 0, m = n;
+    while (m % 2 == 0) { m /= 2; ++two; }
+    int odd[kMaxPass] = {}; int nodd = 0;
+    for (int p = 3; (long long)p * p <= m; p += 2)
+        while (m % p == 0) { if (nodd < kMaxPass) odd[nodd] = p; ++nodd; m /= p; }
+    if (m > 1) { if (nodd < kMaxPass) odd[nodd] = m; ++nodd; }
+    for (int i = 0; i < nodd && i < kMaxPass; ++i)
+        for (int j = i + 1; j < nodd && j < kMaxPass; ++j)
+            if (odd[j] > odd[i]) { int t = odd[i]; odd[i] = odd[j]; odd[j] = t; }
+    int lgmax = 0; while ((1 << (lgmax + 1)) <= max_pow2) ++lgmax;
+    int p2[kMaxPass] = {}; int np2 = 0;
+    if (two > 0) {
+        np2 = (two + lgmax - 1) / lgmax;
+        const int base = two / np2, extra = two % np2;
+        for (int i = 0; i < np2 && i < kMaxPass; ++i) p2[i] = 1 << (base + (i < extra ? 1 : 0));
+    }
+    if (nodd + np2 > kMaxPass) { P.npass = -1; return P; }   // too many passes (reported by the host wrapper)
+    int k = 0;
+    if (pow2_first) { for (int i = 0; i < np2; ++i) P.radix[k++] = p2[i]; for (int i = 0; i < nodd; ++i) P.radix[k++] = odd[i]; }
+    else            { for (int i = 0; i < nodd; ++i) P.radix[k++] = odd[i]; for (int i = 0; i < np2; ++i) P.radix[k++] = p2[i]; }
+    P.npass = k;
+    int bl = n;
+    for (int p = 0; p < k; ++p) { P.blen[p] = bl; bl /= P.radix[p]; }
+    return P;
+}
+template <int N> struct SPlan { static constexpr Plan1 p = ct_plan1(N); };
+
 // One radix-R butterfly of pass (block length m = R*q) on one line.
 //   INV=false : DIF forward  (load natural group, DFT, twiddle, store to slots)
 //   INV=true  : DIT inverse  (load slots, conj twiddle, DFT(+), store natural group)
@@ -222,6 +256,52 @@ SB_HD void butterfly(cx<T>* line, int estride, int base, int q, int twstep, cons
         constexpr int k = decltype(k_)::value;
         line[(base + k * q) * estride] = v[k];
     });
+}
+
+// Same butterfly with the group stride Q (in elements) and the element stride ES known at compile
+// time: every shared-memory access becomes base + immediate offset.
+template <int R, bool INV, int Q, int ES, typename T>
+SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
+    constexpr int SIGN = INV ? +1 : -1;
+    constexpr bool P2 = ct_is_pow2(R);
+    constexpr int LG = ct_log2(R);
+    cx<T> v[R];
+    static_for<0, R>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        v[k] = p0[k * Q * ES];
+    });
+    if (!INV) {
+        if constexpr (P2) dif_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
+        if constexpr (Q > 1) {
+            static_for<1, R>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                constexpr int f = P2 ? ct_bitrev(k, LG) : k;
+                v[k] = cmul(v[k], tw[f * twstep]);
+            });
+        }
+    } else {
+        if constexpr (Q > 1) {
+            static_for<1, R>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                constexpr int f = P2 ? ct_bitrev(k, LG) : k;
+                v[k] = cmulc(v[k], tw[f * twstep]);
+            });
+        }
+        if constexpr (P2) dit_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
+    }
+    static_for<0, R>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        p0[k * Q * ES] = v[k];
+    });
+}
+
+constexpr bool ct_radix_compiled(int r) {
+    return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 11 || r == 13 || r == 16 || r == 17;
+}
+constexpr bool ct_plan_static_ok(const Plan1& P) {
+    if (P.npass <= 0) return false;
+    for (int p = 0; p < P.npass; ++p) if (!ct_radix_compiled(P.radix[p])) return false;
+    return true;
 }
 
 // Runtime odd radix (primes not in the compiled list); O(R^2), local-memory array.

@@ -281,130 +281,4 @@ template <typename T> __global__ void k2d_crop_real(CropArgs<T> a) {
     a.out[((size_t)b * a.K + ch) * o0 * o1 + idx] = a.in[((size_t)g * a.m0 + y + 1) * a.m1 + x + 1].x;
 }
 
-// ------------------------------------------------------------------ fused tile kernel
-// One CTA = one scattering path (image b, parent, filter):
-//   Z      = periodise_k(parent * filt) * scale                       (n0 x n1, Fourier)
-//   u      = ifft2(Z)                                                 (shared memory)
-//   U      = |u|
-//   S      = unpad( (U conv g)[::kl, ::kl] ),  g = taps0 (x) taps1   -> out[b][ch]
-//   spec   = fft2(U)   (only when spec_out != nullptr)                -> spec_out[g]
-// The separable spatial low-pass equals the reference's Fourier-domain
-// cdgmm(phi) -> subsample_fourier -> irfft -> unpad chain (core/scattering2d.py:42-47)
-// whenever phi_hat = a_hat (x) b_hat / phi_hat[0][0]; the plan verifies this when binding.
-template <typename T> struct TileArgs {
-    const cx<T>* parent; const T* const* filt; const int2* supp;
-    cx<T>* spec_out; T* out;
-    int P0, P1, k, n0, n1, W, NF;
-    T scale;
-    Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
-    const T* taps0; const T* taps1;        // taps[i] multiplies input index kl*(o+1) - (tlo + i)
-    int t0lo, t0cnt, t1lo, t1cnt, kl;
-    int o0, o1, o1p;
-    int PP, NFch, ch0, chs, K;
-};
-
-template <typename T> struct TileSmem {
-    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* taps0; T* taps1; int* pos0; int* pos1;
-};
-template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return o; };
-    const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
-    const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
-    const size_t o_supp = take(sizeof(int2) * a.P0);
-    const size_t o_w1 = take(sizeof(T) * (size_t)a.n0 * a.o1p);
-    const size_t o_t0 = take(sizeof(T) * a.t0cnt), o_t1 = take(sizeof(T) * a.t1cnt);
-    const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
-    if (L) {
-#ifdef __CUDA_ARCH__
-        unsigned char* base = dyn_smem<unsigned char>();
-        L->tile = reinterpret_cast<cx<T>*>(base + o_tile);
-        L->tw0 = reinterpret_cast<cx<T>*>(base + o_tw0); L->tw1 = reinterpret_cast<cx<T>*>(base + o_tw1);
-        L->supp = reinterpret_cast<int2*>(base + o_supp);
-        L->w1 = reinterpret_cast<T*>(base + o_w1);
-        L->taps0 = reinterpret_cast<T*>(base + o_t0); L->taps1 = reinterpret_cast<T*>(base + o_t1);
-        L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
-#endif
-    }
-    return off;
-}
-
-template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_tile(TileArgs<T> a) {
-    TileSmem<T> m;
-    tile_smem_layout(a, &m);
-    cx<T>* s = m.tile;
-    const int g = blockIdx.x;
-    const int fi = g % a.NF, pg = g / a.NF;
-    const int b = g / a.PP, path = g - b * a.PP;
-    const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
-    stage(m.tw0, a.tw0, a.n0); stage(m.tw1, a.tw1, a.n1);
-    stage(m.pos0, a.pos0, a.n0); stage(m.pos1, a.pos1, a.n1);
-    stage(m.taps0, a.taps0, a.t0cnt); stage(m.taps1, a.taps1, a.t1cnt);
-    stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
-    __syncthreads();
-    // 1. product + periodise, scattered into scrambled (DIT-input) order
-    {
-        const cx<T>* pb = a.parent + (size_t)pg * a.P0 * a.P1;
-        const T* fb = a.filt[fi];
-        for (int idx = flat_tid(); idx < a.n0 * a.n1; idx += flat_nt()) {
-            const int r = idx / a.n1, e = idx - r * a.n1;
-            const cx<T> v = prod_fold<T>(pb, fb, m.supp, r, e, a.k, a.n0, a.n1, a.P1);
-            s[m.pos0[r] * a.W + m.pos1[e]] = scal(v, a.scale);
-        }
-    }
-    __syncthreads();
-    // 2. inverse 2-D FFT -> natural-order spatial field
-    slab_fft<true, T>(s, a.n0, a.W, 1, a.plan1, m.tw1);
-    slab_fft<true, T>(s, a.n1, 1, a.W, a.plan0, m.tw0);
-    // 3. modulus (kept in .x; .y zeroed for the optional forward transform)
-    for (int y = threadIdx.y; y < a.n0; y += blockDim.y)
-        for (int x = threadIdx.x; x < a.n1; x += blockDim.x) {
-            const cx<T> v = s[y * a.W + x];
-            s[y * a.W + x] = mk<T>(sqrt(v.x * v.x + v.y * v.y), T(0));
-        }
-    __syncthreads();
-    // 4a. horizontal low-pass + decimation: w1[y][xo] = sum_i taps1[i] * U[y][kl*(xo+1) - (t1lo+i)]
-    for (int xo = threadIdx.y; xo < a.o1; xo += blockDim.y) {
-        const int c = a.kl * (xo + 1) - a.t1lo;
-        for (int y = threadIdx.x; y < a.n0; y += blockDim.x) {
-            const cx<T>* row = s + y * a.W;
-            T acc = T(0);
-            int x = c % a.n1; if (x < 0) x += a.n1;
-            for (int i = 0; i < a.t1cnt; ++i) {
-                acc += m.taps1[i] * row[x].x;
-                x = (x == 0) ? a.n1 - 1 : x - 1;
-            }
-            m.w1[y * a.o1p + xo] = acc;
-        }
-    }
-    __syncthreads();
-    // 4b. vertical low-pass + decimation + unpad, straight to the output plane
-    {
-        T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
-        for (int yo = threadIdx.y; yo < a.o0; yo += blockDim.y) {
-            const int c = a.kl * (yo + 1) - a.t0lo;
-            int y0 = c % a.n0; if (y0 < 0) y0 += a.n0;
-            for (int xo = threadIdx.x; xo < a.o1; xo += blockDim.x) {
-                T acc = T(0);
-                int y = y0;
-                for (int i = 0; i < a.t0cnt; ++i) {
-                    acc += m.taps0[i] * m.w1[y * a.o1p + xo];
-                    y = (y == 0) ? a.n0 - 1 : y - 1;
-                }
-                ob[yo * a.o1 + xo] = acc;
-            }
-        }
-    }
-    // 5. forward 2-D FFT of U for the children of this path
-    if (a.spec_out) {
-        slab_fft<false, T>(s, a.n0, a.W, 1, a.plan1, m.tw1);
-        slab_fft<false, T>(s, a.n1, 1, a.W, a.plan0, m.tw0);
-        cx<T>* ob = a.spec_out + (size_t)g * a.n0 * a.n1;
-        for (int idx = flat_tid(); idx < a.n0 * a.n1; idx += flat_nt()) {
-            const int r = idx / a.n1, e = idx - r * a.n1;
-            ob[idx] = s[m.pos0[r] * a.W + m.pos1[e]];
-        }
-    }
-}
-
 }  // namespace sb

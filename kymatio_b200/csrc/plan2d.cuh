@@ -16,6 +16,7 @@
 #include "../../include/scat_b200.h"
 #include "common.cuh"
 #include "kernels2d.cuh"
+#include "tile2d.cuh"
 #include "plan_host.h"
 
 struct scat_plan2d {
@@ -40,8 +41,8 @@ struct Level2D { Axis a0, a1; };
 // separable spatial low-pass derived from phi_hat at one resolution
 struct FirLevel {
     bool ok = false;
-    int t0lo = 0, t0cnt = 0, t1lo = 0, t1cnt = 0;
-    size_t taps0_off = 0, taps1_off = 0;
+    int y0lo = 0, y0cnt = 0, x1lo = 0, x1cnt = 0;   // input window per group of 4 outputs (tile2d.cuh)
+    size_t G0_off = 0, G1_off = 0;                  // dense [n][o?p] decimation matrices
 };
 
 // per-row circular support interval of a real filter (natural order)
@@ -118,8 +119,8 @@ public:
         phi_ptrslot_off_ = take((size_t)d.J * sizeof(void*));
         for (int j = 0; j < d.J; ++j) {
             phi_supp_off_[j] = take((size_t)lev_[j].a0.n * sizeof(int2));
-            fir_[j].taps0_off = take((size_t)lev_[j].a0.n * sizeof(T));
-            fir_[j].taps1_off = take((size_t)lev_[j].a1.n * sizeof(T));
+            fir_[j].G0_off = take((size_t)lev_[j].a0.n * o0p() * sizeof(T));
+            fir_[j].G1_off = take((size_t)lev_[j].a1.n * o1p() * sizeof(T));
         }
         psi_ptr_off_.resize(d.J); psi_supp_off_.resize(d.J);
         n_psi_expected_ = 0;
@@ -156,7 +157,7 @@ public:
         enable_big_smem(k2d_rowpass<T, false>);
         enable_big_smem(k2d_rowpass<T, true>);
         enable_big_smem(k2d_lowpass<T>);
-        enable_big_smem(k2d_tile<T>);
+        tile_kernels_enable_smem<T>();
         compute_workspace();
     }
 
@@ -208,7 +209,7 @@ public:
         for (int j = 0; j < d_.J; ++j) {
             TileArgs<T> a = tile_args_geometry(j);
             tile_smem_[j] = tile_smem_layout<T>(a, nullptr);
-            tile_ok_[j] = !force_stream_ && fir_[j].ok && tile_smem_[j] <= kMaxDynSmem;
+            tile_ok_[j] = !force_stream_ && fir_[j].ok && tile_smem_[j] <= kMaxDynSmem && a.n1 % 2 == 0;
         }
         bound_ = true;
         compute_workspace();
@@ -236,6 +237,8 @@ public:
 private:
     static constexpr size_t kWsCap = (size_t)12 << 30;
 
+    int o0p() const { return (o0_ + 3) & ~3; }
+    int o1p() const { return (o1_ + 3) & ~3; }
     size_t fsize(int res) const { return (size_t)lev_[res].a0.n * lev_[res].a1.n; }
     const cx<T>* tw(const Axis& a) const { return reinterpret_cast<const cx<T>*>(cbuf_ + a.tw_off); }
     const int* pos(const Axis& a) const { return reinterpret_cast<const int*>(cbuf_ + a.pos_off); }
@@ -261,7 +264,10 @@ private:
                                                   (double)f[(size_t)u * n1] * (double)f[v]));
         if (resid > 4e-6 * c * c) return;   // not separable to float32 rounding: keep the Fourier low-pass
         const double tau = 6.283185307179586476925286766559;
-        auto taps = [&](int n, int stride, double norm, int& tlo, int& tcnt, size_t off) {
+        // spatial taps a[t] (circular), truncated where |a| <= 1e-6 max|a|, expanded into the dense
+        // matrix G[x][o] = a[(kl*(o+1) - x) mod n] (zero outside the kept radius / for padded columns)
+        const int kl = 1 << (d_.J - j);
+        auto build = [&](int n, int stride, double norm, int nout, int noutp, int& lo, int& cnt, size_t off) {
             std::vector<double> a(n);
             double mx = 0;
             for (int y = 0; y < n; ++y) {
@@ -273,12 +279,24 @@ private:
             int R = 0;
             for (int y = 0; y < n; ++y)
                 if (std::fabs(a[y]) > 1e-6 * mx) R = std::max(R, std::min(y, n - y));
-            if (2 * R + 1 >= n) { tlo = 0; tcnt = n; } else { tlo = -R; tcnt = 2 * R + 1; }
-            T* dst = reinterpret_cast<T*>(host_const_.data() + off);
-            for (int i = 0; i < tcnt; ++i) dst[i] = (T)a[((tlo + i) % n + n) % n];
+            const bool full = 2 * R + 1 >= n;
+            const int tcnt = full ? n : 2 * R + 1, tlo = full ? 0 : -R;
+            // group of outputs 4g..4g+3 reads inputs kl*(4g+1) - tlo - tcnt + 1 ... kl*(4g+4) - tlo
+            lo = -tlo - tcnt + 1;
+            cnt = std::min(n, tcnt + 3 * kl);
+            T* G = reinterpret_cast<T*>(host_const_.data() + off);
+            for (int x = 0; x < n; ++x)
+                for (int o = 0; o < noutp; ++o) {
+                    double v = 0;
+                    if (o < nout) {
+                        const int t = (((kl * (o + 1) - x) % n) + n) % n;
+                        if (full || std::min(t, n - t) <= R) v = a[t];
+                    }
+                    G[(size_t)x * noutp + o] = (T)v;
+                }
         };
-        taps(n0, n1, 1.0, F.t0lo, F.t0cnt, F.taps0_off);   // column 0 of phi_hat: f[u*n1]
-        taps(n1, 1, c, F.t1lo, F.t1cnt, F.taps1_off);      // row 0 of phi_hat:    f[v]
+        build(n0, n1, 1.0, o0_, o0p(), F.y0lo, F.y0cnt, F.G0_off);   // column 0 of phi_hat: f[u*n1]
+        build(n1, 1, c, o1_, o1p(), F.x1lo, F.x1cnt, F.G1_off);      // row 0 of phi_hat:    f[v]
         F.ok = true;
     }
 
@@ -286,8 +304,7 @@ private:
         TileArgs<T> a{};
         a.P0 = lev_[0].a0.n;   // worst case for the staged support rows
         a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n; a.W = a.n1 | 1;
-        a.o0 = o0_; a.o1 = o1_; a.o1p = o1_ | 1;
-        a.t0cnt = fir_[res].t0cnt; a.t1cnt = fir_[res].t1cnt;
+        a.o0 = o0_; a.o1 = o1_; a.o0p = o0p(); a.o1p = o1p();
         return a;
     }
 
@@ -405,11 +422,11 @@ private:
         a.plan0 = lev_[res].a0.plan; a.plan1 = lev_[res].a1.plan;
         a.tw0 = tw(lev_[res].a0); a.tw1 = tw(lev_[res].a1); a.pos0 = pos(lev_[res].a0); a.pos1 = pos(lev_[res].a1);
         const FirLevel& F = fir_[res];
-        a.taps0 = reinterpret_cast<const T*>(cbuf_ + F.taps0_off);
-        a.taps1 = reinterpret_cast<const T*>(cbuf_ + F.taps1_off);
-        a.t0lo = F.t0lo; a.t0cnt = F.t0cnt; a.t1lo = F.t1lo; a.t1cnt = F.t1cnt;
+        a.G0 = reinterpret_cast<const T*>(cbuf_ + F.G0_off);
+        a.G1 = reinterpret_cast<const T*>(cbuf_ + F.G1_off);
+        a.y0lo = F.y0lo; a.y0cnt = F.y0cnt; a.x1lo = F.x1lo; a.x1cnt = F.x1cnt;
         a.kl = 1 << (d_.J - res);
-        a.o0 = o0_; a.o1 = o1_; a.o1p = o1_ | 1;
+        a.o0 = o0_; a.o1 = o1_; a.o0p = o0p(); a.o1p = o1p();
         a.PP = PP; a.NFch = NFch; a.ch0 = ch0; a.chs = chs; a.K = K_;
         const size_t smem = tile_smem_layout<T>(a, nullptr);
         const int G = Bp * NF;
@@ -426,7 +443,7 @@ private:
                              (double)G * o0_ * o1_ * sizeof(T) + (spec_out ? (double)G * a.n0 * a.n1 * sizeof(cx<T>) : 0.0);
         launch(std::string("tile_") + what + ":L" + std::to_string(parent_res) + ">L" + std::to_string(res) + ":G" +
                    std::to_string(G / std::max(1, last_B_)),
-               bytes, st, [&] { k2d_tile<T><<<(unsigned)G, block, smem, st>>>(a); });
+               bytes, st, [&] { tile_kernel_lookup<T>(a.n0, a.n1, a.k, nullptr)<<<(unsigned)G, block, smem, st>>>(a); });
     }
 
     void forward_chunk(const T* x, T* out, cx<T>* ws, int B, cudaStream_t st) {

@@ -13,48 +13,16 @@ inline bool radix_compiled(int r) {
     return false;
 }
 
-// Factor n into DIF pass radices: the power-of-two part split into radices <= max_pow2 and
-// the odd primes (descending).  pow2_first = true puts the power-of-two passes first, which
-// makes the natural -> scrambled scatter of consecutive frequencies hit distinct shared-memory
-// banks (pos jumps by odd multiples); false gives the "odd first" order whose scrambled
-// layout nests across resolutions.  Throws for unsupported sizes.
+// Host wrapper around ct_plan1 (fft_core.cuh) with validation.  Throws for unsupported sizes.
 inline Plan1 make_plan1(int n, int max_pow2 = 16, bool pow2_first = true) {
     if (n < 1) throw std::runtime_error("FFT length must be >= 1");
-    Plan1 P{};
-    P.n = n;
-    int two = 0, m = n;
-    while (m % 2 == 0) { m /= 2; ++two; }
-    std::vector<int> odd;
-    for (int p = 3; (long long)p * p <= m; p += 2)
-        while (m % p == 0) { odd.push_back(p); m /= p; }
-    if (m > 1) odd.push_back(m);
-    // descending
-    for (size_t i = 0; i < odd.size(); ++i)
-        for (size_t j = i + 1; j < odd.size(); ++j)
-            if (odd[j] > odd[i]) std::swap(odd[i], odd[j]);
-    std::vector<int> rad, rad2;
-    for (int p : odd) {
-        if (!radix_compiled(p) && p > kMaxGenericRadix)
+    Plan1 P = ct_plan1(n, max_pow2, pow2_first);
+    if (P.npass < 0) throw std::runtime_error("too many FFT passes for length " + std::to_string(n));
+    for (int p = 0; p < P.npass; ++p)
+        if (!radix_compiled(P.radix[p]) && P.radix[p] > kMaxGenericRadix)
             throw std::runtime_error("FFT length " + std::to_string(n) + " has prime factor " +
-                                     std::to_string(p) + " > " + std::to_string(kMaxGenericRadix) +
+                                     std::to_string(P.radix[p]) + " > " + std::to_string(kMaxGenericRadix) +
                                      " (unsupported)");
-        rad.push_back(p);
-    }
-    int lgmax = 0; while ((1 << (lgmax + 1)) <= max_pow2) ++lgmax;
-    // balanced split of the 2-part into ceil(two/lgmax) passes
-    if (two > 0) {
-        int np = (two + lgmax - 1) / lgmax;
-        int base = two / np, extra = two % np;
-        for (int i = 0; i < np; ++i) rad2.push_back(1 << (base + (i < extra ? 1 : 0)));
-    }
-    if (pow2_first) rad.insert(rad.begin(), rad2.begin(), rad2.end());
-    else rad.insert(rad.end(), rad2.begin(), rad2.end());
-    if (rad.empty()) rad.push_back(1);  // n == 1: degenerate
-    if ((int)rad.size() > kMaxPass) throw std::runtime_error("too many FFT passes");
-    if (n == 1) { P.npass = 0; return P; }
-    P.npass = (int)rad.size();
-    int bl = n;
-    for (int p = 0; p < P.npass; ++p) { P.radix[p] = rad[p]; P.blen[p] = bl; bl /= rad[p]; }
     return P;
 }
 

@@ -1,0 +1,231 @@
+// tile2d.cuh - the fused one-CTA-per-path tile kernel.
+//
+// One CTA = one scattering path (image b, parent spectrum, band-pass filter):
+//   Z      = periodise_k(parent * filt) * scale                       (n0 x n1, Fourier)
+//   u      = ifft2(Z)                                                 (shared memory)
+//   U      = |u|
+//   S      = unpad( (U conv g)[::kl, ::kl] ),  g = a (x) b           -> out[b][ch]
+//   spec   = fft2(U)   (only when spec_out != nullptr)                -> spec_out[g]
+// i.e. cdgmm -> subsample_fourier -> ifft -> modulus -> rfft -> cdgmm(phi) -> subsample_fourier ->
+// irfft -> unpad of kymatio/scattering2d/core/scattering2d.py:33-47 (and :59-75) in one pass.
+// The separable spatial low-pass equals the reference's Fourier-domain low-pass whenever
+// phi_hat = a_hat (x) b_hat / phi_hat[0][0] (checked when the filters are bound); it is applied as
+// two small dense products with the decimation matrices G1[x][xo], G0[y][yo] built at bind time.
+//
+// Template parameters N0, N1 (field size) and K (periodisation factor) select a fully
+// specialised instance (static FFT plans, immediate-offset shared-memory accesses, unrolled alias
+// loops); N0 = 0 is the generic runtime-size fallback.
+#pragma once
+#include "kernels2d.cuh"
+
+namespace sb {
+
+template <typename T> struct TileArgs {
+    const cx<T>* parent; const T* const* filt; const int2* supp;
+    cx<T>* spec_out; T* out;
+    int P0, P1, k, n0, n1, W, NF;
+    T scale;
+    Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
+    const T* G0; const T* G1;              // [n0][o0p], [n1][o1p] dense low-pass + decimation + unpad matrices
+    int y0lo, y0cnt, x1lo, x1cnt;          // input window (start offset rel. to kl*(4*group+1), length) per 4-output group
+    int kl, o0, o1, o0p, o1p;              // o?p = o? rounded up to a multiple of 4
+    int PP, NFch, ch0, chs, K;
+};
+
+template <typename T> struct TileSmem {
+    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1;
+};
+template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return o; };
+    const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
+    const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
+    const size_t o_supp = take(sizeof(int2) * a.P0);
+    const size_t o_w1 = take(sizeof(T) * (size_t)a.n0 * a.o1p);
+    const size_t o_g0 = take(sizeof(T) * (size_t)a.n0 * a.o0p), o_g1 = take(sizeof(T) * (size_t)a.n1 * a.o1p);
+    const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
+    if (L) {
+#ifdef __CUDA_ARCH__
+        unsigned char* base = dyn_smem<unsigned char>();
+        L->tile = reinterpret_cast<cx<T>*>(base + o_tile);
+        L->tw0 = reinterpret_cast<cx<T>*>(base + o_tw0); L->tw1 = reinterpret_cast<cx<T>*>(base + o_tw1);
+        L->supp = reinterpret_cast<int2*>(base + o_supp);
+        L->w1 = reinterpret_cast<T*>(base + o_w1);
+        L->G0 = reinterpret_cast<T*>(base + o_g0); L->G1 = reinterpret_cast<T*>(base + o_g1);
+        L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
+#endif
+    }
+    return off;
+}
+
+template <typename T> struct alignas(2 * sizeof(cx<T>)) cx2 { cx<T> a, b; };
+template <typename T> struct alignas(2 * sizeof(T)) re2 { T a, b; };
+template <typename T> struct alignas(4 * sizeof(T)) re4 { T a, b, c, d; };
+
+__device__ __forceinline__ float fast_abs(float x, float y) {
+    const float m2 = x * x + y * y;
+    return m2 > 0.f ? m2 * rsqrtf(m2) : 0.f;      // <= 2 ulp; the reference computes sqrt(x^2+y^2)
+}
+__device__ __forceinline__ double fast_abs(double x, double y) { return sqrt(x * x + y * y); }
+
+template <typename T, int N0, int N1, int KT>
+__device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
+    constexpr bool ST = N0 > 0;
+    const int n0 = ST ? N0 : a.n0, n1 = ST ? N1 : a.n1;
+    const int W = ST ? (N1 | 1) : a.W;
+    const int k = KT > 0 ? KT : a.k;
+    TileSmem<T> m;
+    tile_smem_layout(a, &m);
+    cx<T>* s = m.tile;
+    const int g = blockIdx.x;
+    const int fi = g % a.NF, pg = g / a.NF;
+    const int b = g / a.PP, path = g - b * a.PP;
+    const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
+    const int tid = flat_tid(), nt = flat_nt();
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+
+    stage(m.tw0, a.tw0, n0); stage(m.tw1, a.tw1, n1);
+    stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
+    stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
+    stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
+    stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
+    __syncthreads();
+
+    // 1. product + periodise: one output row per warp, two adjacent columns per lane (128-bit parent
+    //    loads); aliases outside the filter's support interval are skipped
+    {
+        const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
+        const T* __restrict__ fb = a.filt[fi];
+        const int P1 = a.P1, half = n1 >> 1;
+        for (int r = warp; r < n0; r += nwarps) {
+            const int prow = m.pos0[r] * W;
+            for (int e2 = lane; e2 < half; e2 += 32) {
+                const int e = 2 * e2;
+                T ax0 = T(0), ay0 = T(0), ax1 = T(0), ay1 = T(0);
+#pragma unroll
+                for (int c = 0; c < k; ++c) {
+                    const int R = r + c * n0;
+                    const int2 sp = m.supp[R];
+                    const size_t rowoff = (size_t)R * P1;
+#pragma unroll
+                    for (int d = 0; d < k; ++d) {
+                        const int C = e + d * n1;
+                        int rel = C - sp.x;
+                        if (rel < 0) rel += P1;
+                        if ((rel < sp.y) | ((rel == P1 - 1) & (sp.y > 0))) {
+                            const cx2<T> v = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
+                            const re2<T> f = *reinterpret_cast<const re2<T>*>(fb + rowoff + C);
+                            ax0 += v.a.x * f.a; ay0 += v.a.y * f.a;
+                            ax1 += v.b.x * f.b; ay1 += v.b.y * f.b;
+                        }
+                    }
+                }
+                s[prow + m.pos1[e]] = mk<T>(ax0 * a.scale, ay0 * a.scale);
+                s[prow + m.pos1[e + 1]] = mk<T>(ax1 * a.scale, ay1 * a.scale);
+            }
+        }
+    }
+    __syncthreads();
+    // 2. inverse 2-D FFT -> natural-order spatial field
+    if constexpr (ST) {
+        slab_fft_s<N1, true, (N1 | 1), 1, T>(s, N0, m.tw1);
+        slab_fft_s<N0, true, 1, (N1 | 1), T>(s, N1, m.tw0);
+    } else {
+        slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
+        slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
+    }
+    // 3. modulus (kept in .x; .y zeroed for the optional forward transform)
+    for (int y = warp; y < n0; y += nwarps)
+        for (int x = lane; x < n1; x += 32) {
+            const cx<T> v = s[y * W + x];
+            s[y * W + x] = mk<T>(fast_abs(v.x, v.y), T(0));
+        }
+    __syncthreads();
+    // 4a. horizontal low-pass + decimation + unpad: w1[y][xo] = sum_x U[y][x] * G1[x][xo]
+    //     register tile: 4 rows x 4 outputs per thread, x restricted to the group's input window
+    {
+        const int rgroups = (n0 + 3) >> 2, xgroups = a.o1p >> 2;
+        for (int it = tid; it < rgroups * xgroups; it += nt) {
+            const int xg = it / rgroups, rg = it - xg * rgroups;
+            int yy[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yy[j] = min(rg + j * rgroups, n0 - 1) * W;
+            T acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+            int x = (a.kl * (4 * xg + 1) + a.x1lo) % n1;
+            if (x < 0) x += n1;
+            for (int st = 0; st < a.x1cnt; ++st) {
+                const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G1 + x * a.o1p + 4 * xg);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const T u = s[yy[j] + x].x;
+                    acc[j][0] += u * gq.a; acc[j][1] += u * gq.b; acc[j][2] += u * gq.c; acc[j][3] += u * gq.d;
+                }
+                x = (x + 1 == n1) ? 0 : x + 1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int y = rg + j * rgroups;
+                if (y < n0) {
+                    re4<T> o; o.a = acc[j][0]; o.b = acc[j][1]; o.c = acc[j][2]; o.d = acc[j][3];
+                    *reinterpret_cast<re4<T>*>(m.w1 + y * a.o1p + 4 * xg) = o;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
+    //     S[yo][xo] = sum_y G0[y][yo] * w1[y][xo]; 4 output rows per thread, lanes along xo
+    {
+        T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+        const int ygroups = a.o0p >> 2;
+        for (int it = tid; it < ygroups * a.o1p; it += nt) {
+            const int yg = it / a.o1p, xo = it - yg * a.o1p;
+            T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+            int y = (a.kl * (4 * yg + 1) + a.y0lo) % n0;
+            if (y < 0) y += n0;
+            for (int st = 0; st < a.y0cnt; ++st) {
+                const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G0 + y * a.o0p + 4 * yg);
+                const T w = m.w1[y * a.o1p + xo];
+                acc0 += w * gq.a; acc1 += w * gq.b; acc2 += w * gq.c; acc3 += w * gq.d;
+                y = (y + 1 == n0) ? 0 : y + 1;
+            }
+            if (xo < a.o1) {
+                const int yo = 4 * yg;
+                if (yo + 0 < a.o0) ob[(yo + 0) * a.o1 + xo] = acc0;
+                if (yo + 1 < a.o0) ob[(yo + 1) * a.o1 + xo] = acc1;
+                if (yo + 2 < a.o0) ob[(yo + 2) * a.o1 + xo] = acc2;
+                if (yo + 3 < a.o0) ob[(yo + 3) * a.o1 + xo] = acc3;
+            }
+        }
+    }
+    // 5. forward 2-D FFT of U for the children of this path (natural-order store)
+    if (a.spec_out) {
+        if constexpr (ST) {
+            slab_fft_s<N1, false, (N1 | 1), 1, T>(s, N0, m.tw1);
+            slab_fft_s<N0, false, 1, (N1 | 1), T>(s, N1, m.tw0);
+        } else {
+            slab_fft<false, T>(s, n0, W, 1, a.plan1, m.tw1);
+            slab_fft<false, T>(s, n1, 1, W, a.plan0, m.tw0);
+        }
+        cx<T>* ob = a.spec_out + (size_t)g * n0 * n1;
+        for (int r = warp; r < n0; r += nwarps) {
+            const int prow = m.pos0[r] * W;
+            for (int e = lane; e < n1; e += 32) ob[(size_t)r * n1 + e] = s[prow + m.pos1[e]];
+        }
+    }
+}
+
+template <typename T, int N0, int N1, int KT>
+__global__ void __launch_bounds__(kMaxThreads) k2d_tile(TileArgs<T> a) { tile_body<T, N0, N1, KT>(a); }
+
+// specialised instances are compiled in tile_inst_*.cu; returns the kernel for (n0, n1, k) or the
+// generic one
+template <typename T> using TileKernel = void (*)(TileArgs<T>);
+template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bool* is_static);
+template <typename T> void tile_kernels_enable_smem();
+
+}  // namespace sb

@@ -1,0 +1,40 @@
+// tile_inst.cu - explicit instances of the fused tile kernel for the field sizes of the
+// BASELINE.json configurations, plus the generic runtime-size fallback.
+//   272-padded (256^2, J=3): 136, 68        256-padded (224^2, J=4): 128, 64, 32
+#include "tile2d.cuh"
+#include "common.cuh"
+
+namespace sb {
+
+#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32)
+
+template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bool* is_static) {
+    if (is_static) *is_static = true;
+    if (n0 == n1) {
+#define SB_CASE(N)                                           \
+        if (n0 == N) {                                       \
+            if (k == 2) return k2d_tile<T, N, N, 2>;         \
+            if (k == 4) return k2d_tile<T, N, N, 4>;         \
+            return k2d_tile<T, N, N, 0>;                     \
+        }
+        SB_TILE_SIZES(SB_CASE)
+#undef SB_CASE
+    }
+    if (is_static) *is_static = false;
+    return k2d_tile<T, 0, 0, 0>;
+}
+
+template <typename T> void tile_kernels_enable_smem() {
+#define SB_EN(N) enable_big_smem(k2d_tile<T, N, N, 2>); enable_big_smem(k2d_tile<T, N, N, 4>); \
+                 enable_big_smem(k2d_tile<T, N, N, 0>);
+    SB_TILE_SIZES(SB_EN)
+#undef SB_EN
+    enable_big_smem(k2d_tile<T, 0, 0, 0>);
+}
+
+template TileKernel<float> tile_kernel_lookup<float>(int, int, int, bool*);
+template TileKernel<double> tile_kernel_lookup<double>(int, int, int, bool*);
+template void tile_kernels_enable_smem<float>();
+template void tile_kernels_enable_smem<double>();
+
+}  // namespace sb
