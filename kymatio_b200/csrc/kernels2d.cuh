@@ -70,6 +70,23 @@ __device__ __forceinline__ int wrap(int t, int n) {   // t in (-n, 2n)
     return t;
 }
 
+// ===================================================================================
+// Streaming slab kernels.  Template parameter NS > 0 selects a compile-time line length
+// (static FFT plan, 16 lines per CTA, pitch 17): every index computation folds to constants.
+// NS = 0 is the generic runtime-size version.
+// ===================================================================================
+constexpr int kSLines = 16;           // lines per CTA in the static variants
+constexpr int kSLP = kSLines | 1;     // odd shared-memory pitch
+
+template <typename T> struct alignas(2 * sizeof(cx<T>)) cxpair { cx<T> a, b; };
+template <typename T> struct alignas(2 * sizeof(T)) repair { T a, b; };
+
+__device__ __forceinline__ float abs2f(float x, float y) {
+    const float m2 = x * x + y * y;
+    return m2 > 0.f ? m2 * rsqrtf(m2) : 0.f;
+}
+__device__ __forceinline__ double abs2f(double x, double y) { return sqrt(x * x + y * y); }
+
 // ------------------------------------------------------------------ pad + row FFT
 template <typename T> struct PadRowArgs {
     const T* x; cx<T>* out;
@@ -78,26 +95,28 @@ template <typename T> struct PadRowArgs {
     Plan1 plan; const cx<T>* tw; const int* pos;
 };
 // grid (B, ceil(P0/lines)); reflect-pad rows on the fly, forward DIF along rows, natural-order store.
-template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_pad_rowfft(PadRowArgs<T> a) {
+template <typename T, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_pad_rowfft(PadRowArgs<T> a) {
+    const int P1 = NS ? NS : a.P1, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
-    cx<T>* tw = s + (size_t)a.P1 * a.LP;
-    int* pos = reinterpret_cast<int*>(tw + a.P1);
-    const int b = blockIdx.x, r0 = blockIdx.y * a.lines;
-    const int nl = min(a.lines, a.P0 - r0);
-    stage(tw, a.tw, a.P1);
-    stage(pos, a.pos, a.P1);
+    cx<T>* tw = s + (size_t)P1 * LP;
+    int* pos = reinterpret_cast<int*>(tw + P1);
+    const int b = blockIdx.x, r0 = blockIdx.y * lines;
+    const int nl = min(lines, a.P0 - r0);
+    stage(tw, a.tw, P1);
+    stage(pos, a.pos, P1);
     const T* xb = a.x + (size_t)b * a.M * a.N;
-    for (int idx = flat_tid(); idx < nl * a.P1; idx += flat_nt()) {
-        const int l = idx / a.P1, e = idx - l * a.P1;
+    for (int idx = flat_tid(); idx < nl * P1; idx += flat_nt()) {
+        const int l = idx / P1, e = idx - l * P1;
         const int sr = reflect_idx(r0 + l - a.top, a.M), sc = reflect_idx(e - a.left, a.N);
-        s[e * a.LP + l] = mk<T>(xb[(size_t)sr * a.N + sc], T(0));
+        s[e * LP + l] = mk<T>(xb[(size_t)sr * a.N + sc], T(0));
     }
     __syncthreads();
-    slab_fft<false, T>(s, nl, 1, a.LP, a.plan, tw);
-    cx<T>* ob = a.out + ((size_t)b * a.P0 + r0) * a.P1;
-    for (int idx = flat_tid(); idx < nl * a.P1; idx += flat_nt()) {
-        const int l = idx / a.P1, e = idx - l * a.P1;
-        ob[(size_t)l * a.P1 + e] = s[pos[e] * a.LP + l];
+    if constexpr (NS > 0) slab_fft_s<NS, false, 1, kSLP, T>(s, nl, tw);
+    else slab_fft<false, T>(s, nl, 1, LP, a.plan, tw);
+    cx<T>* ob = a.out + ((size_t)b * a.P0 + r0) * P1;
+    for (int idx = flat_tid(); idx < nl * P1; idx += flat_nt()) {
+        const int l = idx / P1, e = idx - l * P1;
+        ob[(size_t)l * P1 + e] = s[pos[e] * LP + l];
     }
 }
 
@@ -113,41 +132,63 @@ template <typename T> struct ColArgs {
 //   COL_FWD          spatial rows in  -> forward DIF along columns -> Fourier rows out
 //   COL_INV          Fourier rows in  -> inverse DIT along columns -> spatial rows out
 //   COL_INV_MOD_FWD  Fourier rows in  -> inverse DIT, modulus, forward DIF -> Fourier rows out
-template <typename T, int MODE> __global__ void __launch_bounds__(kMaxThreads) k2d_colpass(ColArgs<T> a) {
+template <typename T, int MODE, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_colpass(ColArgs<T> a) {
+    const int n0 = NS ? NS : a.n0, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
-    cx<T>* tw = s + (size_t)a.n0 * a.LP;
-    int* pos = reinterpret_cast<int*>(tw + a.n0);
-    const int g = blockIdx.x, c0 = blockIdx.y * a.lines;
-    const int nl = min(a.lines, a.n1 - c0);
-    stage(tw, a.tw, a.n0);
-    stage(pos, a.pos, a.n0);
+    cx<T>* tw = s + (size_t)n0 * LP;
+    int* pos = reinterpret_cast<int*>(tw + n0);
+    const int g = blockIdx.x, c0 = blockIdx.y * lines;
+    const int nl = min(lines, a.n1 - c0);
+    stage(tw, a.tw, n0);
+    stage(pos, a.pos, n0);
     if (MODE != COL_FWD) __syncthreads();
-    const cx<T>* ib = a.in + (size_t)g * a.n0 * a.n1 + c0;
-    for (int e = threadIdx.y; e < a.n0; e += blockDim.y) {
-        const int se = (MODE == COL_FWD) ? e : pos[e];
-        for (int l = threadIdx.x; l < nl; l += blockDim.x)
-            s[se * a.LP + l] = ib[(size_t)e * a.n1 + l];
+    const cx<T>* ib = a.in + (size_t)g * n0 * a.n1 + c0;
+    cx<T>* ob = a.out + (size_t)g * n0 * a.n1 + c0;
+    const int tid = flat_tid(), nt = flat_nt();
+    if (NS > 0 && nl == kSLines && (a.n1 & 1) == 0) {
+        // full slab: 8 lanes x 16 bytes per row segment
+        for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+            const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+            const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)e * a.n1 + l);
+            const int se = (MODE == COL_FWD) ? e : pos[e];
+            s[se * LP + l] = v.a; s[se * LP + l + 1] = v.b;
+        }
+    } else {
+        for (int idx = tid; idx < n0 * lines; idx += nt) {
+            const int e = idx / lines, l = idx - e * lines;
+            if (l < nl) s[((MODE == COL_FWD) ? e : pos[e]) * LP + l] = ib[(size_t)e * a.n1 + l];
+        }
     }
     __syncthreads();
     if (MODE == COL_FWD) {
-        slab_fft<false, T>(s, nl, 1, a.LP, a.plan, tw);
+        if constexpr (NS > 0) slab_fft_s<NS, false, 1, kSLP, T>(s, nl, tw);
+        else slab_fft<false, T>(s, nl, 1, LP, a.plan, tw);
     } else {
-        slab_fft<true, T>(s, nl, 1, a.LP, a.plan, tw);
+        if constexpr (NS > 0) slab_fft_s<NS, true, 1, kSLP, T>(s, nl, tw);
+        else slab_fft<true, T>(s, nl, 1, LP, a.plan, tw);
         if (MODE == COL_INV_MOD_FWD) {
-            for (int e = threadIdx.y; e < a.n0; e += blockDim.y)
-                for (int l = threadIdx.x; l < nl; l += blockDim.x) {
-                    const cx<T> v = s[e * a.LP + l];
-                    s[e * a.LP + l] = mk<T>(sqrt(v.x * v.x + v.y * v.y), T(0));
-                }
+            for (int idx = tid; idx < n0 * lines; idx += nt) {
+                const int e = idx / lines, l = idx - e * lines;
+                const cx<T> v = s[e * LP + l];
+                s[e * LP + l] = mk<T>(abs2f(v.x, v.y), T(0));
+            }
             __syncthreads();
-            slab_fft<false, T>(s, nl, 1, a.LP, a.plan, tw);
+            if constexpr (NS > 0) slab_fft_s<NS, false, 1, kSLP, T>(s, nl, tw);
+            else slab_fft<false, T>(s, nl, 1, LP, a.plan, tw);
         }
     }
-    cx<T>* ob = a.out + (size_t)g * a.n0 * a.n1 + c0;
-    for (int e = threadIdx.y; e < a.n0; e += blockDim.y) {
-        const int se = (MODE == COL_INV) ? e : pos[e];
-        for (int l = threadIdx.x; l < nl; l += blockDim.x)
-            ob[(size_t)e * a.n1 + l] = s[se * a.LP + l];
+    if (NS > 0 && nl == kSLines && (a.n1 & 1) == 0) {
+        for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+            const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+            const int se = (MODE == COL_INV) ? e : pos[e];
+            cxpair<T> v; v.a = s[se * LP + l]; v.b = s[se * LP + l + 1];
+            *reinterpret_cast<cxpair<T>*>(ob + (size_t)e * a.n1 + l) = v;
+        }
+    } else {
+        for (int idx = tid; idx < n0 * lines; idx += nt) {
+            const int e = idx / lines, l = idx - e * lines;
+            if (l < nl) ob[(size_t)e * a.n1 + l] = s[((MODE == COL_INV) ? e : pos[e]) * LP + l];
+        }
     }
 }
 
@@ -164,30 +205,69 @@ template <typename T> struct RowProdArgs {
 };
 // grid (G = Bp*NF, ceil(n0/lines)).  rows of out = inverse DIT along the row of
 //   V[r][e] = scale * sum_{c,d<k} parent[r+c*n0][e+d*n1] * filt[r+c*n0][e+d*n1]
-template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass_prod(RowProdArgs<T> a) {
+template <typename T, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass_prod(RowProdArgs<T> a) {
+    const int n1 = NS ? NS : a.n1, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
-    cx<T>* tw = s + (size_t)a.n1 * a.LP;
-    int* pos = reinterpret_cast<int*>(tw + a.n1);
-    const int g = blockIdx.x, r0 = blockIdx.y * a.lines;
-    const int nl = min(a.lines, a.n0 - r0);
+    cx<T>* tw = s + (size_t)n1 * LP;
+    int* pos = reinterpret_cast<int*>(tw + n1);
+    const int g = blockIdx.x, r0 = blockIdx.y * lines;
+    const int nl = min(lines, a.n0 - r0);
     const int fi = g % a.NF, pg = g / a.NF;
-    stage(tw, a.tw, a.n1);
-    stage(pos, a.pos, a.n1);
+    stage(tw, a.tw, n1);
+    stage(pos, a.pos, n1);
     __syncthreads();
-    const cx<T>* pb = a.parent + (size_t)pg * a.P0 * a.P1;
-    const T* fb = a.filt[fi];
+    const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
+    const T* __restrict__ fb = a.filt[fi];
     const int2* sp = a.supp + (size_t)fi * a.P0;
-    for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
-        const int l = idx / a.n1, e = idx - l * a.n1;
-        const cx<T> v = prod_fold<T>(pb, fb, sp, r0 + l, e, a.k, a.n0, a.n1, a.P1);
-        s[pos[e] * a.LP + l] = scal(v, a.scale);
+    const int tid = flat_tid(), nt = flat_nt();
+    if ((n1 & 1) == 0) {
+        // two adjacent columns per thread (128-bit parent loads), support-interval skipping
+        const int half = n1 >> 1, P1 = a.P1, k = a.k;
+        for (int idx = tid; idx < nl * half; idx += nt) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            T ax0 = T(0), ay0 = T(0), ax1 = T(0), ay1 = T(0);
+            for (int c = 0; c < k; ++c) {
+                const int R = r0 + l + c * a.n0;
+                const int2 iv = sp[R];
+                const size_t rowoff = (size_t)R * P1;
+                for (int d = 0; d < k; ++d) {
+                    const int C = e + d * n1;
+                    int rel = C - iv.x;
+                    if (rel < 0) rel += P1;
+                    if ((rel < iv.y) | ((rel == P1 - 1) & (iv.y > 0))) {
+                        const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(pb + rowoff + C);
+                        const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + rowoff + C);
+                        ax0 += v.a.x * f.a; ay0 += v.a.y * f.a;
+                        ax1 += v.b.x * f.b; ay1 += v.b.y * f.b;
+                    }
+                }
+            }
+            s[pos[e] * LP + l] = mk<T>(ax0 * a.scale, ay0 * a.scale);
+            s[pos[e + 1] * LP + l] = mk<T>(ax1 * a.scale, ay1 * a.scale);
+        }
+    } else {
+        for (int idx = tid; idx < nl * n1; idx += nt) {
+            const int l = idx / n1, e = idx - l * n1;
+            const cx<T> v = prod_fold<T>(pb, fb, sp, r0 + l, e, a.k, a.n0, n1, a.P1);
+            s[pos[e] * LP + l] = scal(v, a.scale);
+        }
     }
     __syncthreads();
-    slab_fft<true, T>(s, nl, 1, a.LP, a.plan, tw);
-    cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * a.n1;
-    for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
-        const int l = idx / a.n1, e = idx - l * a.n1;
-        ob[(size_t)l * a.n1 + e] = s[e * a.LP + l];
+    if constexpr (NS > 0) slab_fft_s<NS, true, 1, kSLP, T>(s, nl, tw);
+    else slab_fft<true, T>(s, nl, 1, LP, a.plan, tw);
+    cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * n1;
+    if ((n1 & 1) == 0) {
+        const int half = n1 >> 1;
+        for (int idx = tid; idx < nl * half; idx += nt) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            cxpair<T> v; v.a = s[e * LP + l]; v.b = s[(e + 1) * LP + l];
+            *reinterpret_cast<cxpair<T>*>(ob + (size_t)l * n1 + e) = v;
+        }
+    } else {
+        for (int idx = tid; idx < nl * n1; idx += nt) {
+            const int l = idx / n1, e = idx - l * n1;
+            ob[(size_t)l * n1 + e] = s[e * LP + l];
+        }
     }
 }
 
@@ -199,26 +279,50 @@ template <typename T> struct RowArgs {
     Plan1 plan; const cx<T>* tw; const int* pos;
 };
 // INV=false: spatial row in -> DIF -> Fourier row out; INV=true: Fourier row in -> DIT -> spatial row out
-template <typename T, bool INV> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass(RowArgs<T> a) {
+template <typename T, bool INV, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass(RowArgs<T> a) {
+    const int n1 = NS ? NS : a.n1, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
-    cx<T>* tw = s + (size_t)a.n1 * a.LP;
-    int* pos = reinterpret_cast<int*>(tw + a.n1);
-    const int g = blockIdx.x, r0 = blockIdx.y * a.lines;
-    const int nl = min(a.lines, a.n0 - r0);
-    stage(tw, a.tw, a.n1);
-    stage(pos, a.pos, a.n1);
-    if (INV) __syncthreads();
-    const cx<T>* ib = a.in + ((size_t)g * a.n0 + r0) * a.n1;
-    for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
-        const int l = idx / a.n1, e = idx - l * a.n1;
-        s[(INV ? pos[e] : e) * a.LP + l] = ib[(size_t)l * a.n1 + e];
+    cx<T>* tw = s + (size_t)n1 * LP;
+    int* pos = reinterpret_cast<int*>(tw + n1);
+    const int g = blockIdx.x, r0 = blockIdx.y * lines;
+    const int nl = min(lines, a.n0 - r0);
+    stage(tw, a.tw, n1);
+    stage(pos, a.pos, n1);
+    __syncthreads();
+    const cx<T>* ib = a.in + ((size_t)g * a.n0 + r0) * n1;
+    cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * n1;
+    const int tid = flat_tid(), nt = flat_nt();
+    if ((n1 & 1) == 0) {
+        const int half = n1 >> 1;
+        for (int idx = tid; idx < nl * half; idx += nt) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)l * n1 + e);
+            s[(INV ? pos[e] : e) * LP + l] = v.a;
+            s[(INV ? pos[e + 1] : e + 1) * LP + l] = v.b;
+        }
+    } else {
+        for (int idx = tid; idx < nl * n1; idx += nt) {
+            const int l = idx / n1, e = idx - l * n1;
+            s[(INV ? pos[e] : e) * LP + l] = ib[(size_t)l * n1 + e];
+        }
     }
     __syncthreads();
-    slab_fft<INV, T>(s, nl, 1, a.LP, a.plan, tw);
-    cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * a.n1;
-    for (int idx = flat_tid(); idx < nl * a.n1; idx += flat_nt()) {
-        const int l = idx / a.n1, e = idx - l * a.n1;
-        ob[(size_t)l * a.n1 + e] = s[(INV ? e : pos[e]) * a.LP + l];
+    if constexpr (NS > 0) slab_fft_s<NS, INV, 1, kSLP, T>(s, nl, tw);
+    else slab_fft<INV, T>(s, nl, 1, LP, a.plan, tw);
+    if ((n1 & 1) == 0) {
+        const int half = n1 >> 1;
+        for (int idx = tid; idx < nl * half; idx += nt) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            cxpair<T> v;
+            v.a = s[(INV ? e : pos[e]) * LP + l];
+            v.b = s[(INV ? e + 1 : pos[e + 1]) * LP + l];
+            *reinterpret_cast<cxpair<T>*>(ob + (size_t)l * n1 + e) = v;
+        }
+    } else {
+        for (int idx = tid; idx < nl * n1; idx += nt) {
+            const int l = idx / n1, e = idx - l * n1;
+            ob[(size_t)l * n1 + e] = s[(INV ? e : pos[e]) * LP + l];
+        }
     }
 }
 
@@ -281,4 +385,21 @@ template <typename T> __global__ void k2d_crop_real(CropArgs<T> a) {
     a.out[((size_t)b * a.K + ch) * o0 * o1 + idx] = a.in[((size_t)g * a.m0 + y + 1) * a.m1 + x + 1].x;
 }
 
+}  // namespace sb
+
+namespace sb {
+// Kernel table for one line length (compiled in stream_inst.cu); `is_static` tells whether the
+// entries are compile-time specialised (they then require 16 lines per CTA, pitch 17).
+template <typename T> struct StreamKernels {
+    void (*pad_rowfft)(PadRowArgs<T>);
+    void (*col_fwd)(ColArgs<T>);
+    void (*col_inv)(ColArgs<T>);
+    void (*col_imf)(ColArgs<T>);
+    void (*row_prod)(RowProdArgs<T>);
+    void (*row_fwd)(RowArgs<T>);
+    void (*row_inv)(RowArgs<T>);
+    bool is_static;
+};
+template <typename T> StreamKernels<T> stream_kernels_lookup(int n, bool allow_static);
+template <typename T> void stream_kernels_enable_smem();
 }  // namespace sb

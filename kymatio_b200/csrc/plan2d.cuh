@@ -149,13 +149,7 @@ public:
         tile_smem_.assign(d.J, 0);
         force_stream_ = env_int("SCAT_B200_NO_TILE", 0) != 0;
 
-        enable_big_smem(k2d_pad_rowfft<T>);
-        enable_big_smem(k2d_colpass<T, COL_FWD>);
-        enable_big_smem(k2d_colpass<T, COL_INV>);
-        enable_big_smem(k2d_colpass<T, COL_INV_MOD_FWD>);
-        enable_big_smem(k2d_rowpass_prod<T>);
-        enable_big_smem(k2d_rowpass<T, false>);
-        enable_big_smem(k2d_rowpass<T, true>);
+        stream_kernels_enable_smem<T>();
         enable_big_smem(k2d_lowpass<T>);
         tile_kernels_enable_smem<T>();
         compute_workspace();
@@ -322,6 +316,11 @@ private:
         per_img_ = (ws_u0_ + ws_u1_ + ws_u2_ + ws_low_) * sizeof(cx<T>);
     }
 
+    // kernel table for line length n; the static instances need the default 16-line slab shape
+    StreamKernels<T> skern(int n, const SlabCfg& c) const {
+        return stream_kernels_lookup<T>(n, c.lines == kSLines && c.LP == kSLP);
+    }
+
     // ---------------------------------------------------------------- launch wrappers
     // out[G][n0][n1] = rows-inverse( periodise_k( parent * filt ) ), G = Bp * NF
     void row_prod(const cx<T>* parent, const T* const* filt, const int2* supp, cx<T>* out, int parent_res,
@@ -341,7 +340,7 @@ private:
                              G * a.n0 * a.n1 * sizeof(cx<T>);
         launch("rowpass_prod:L" + std::to_string(parent_res) + ">L" + std::to_string(out_res) + ":G" +
                    std::to_string((int)G / std::max(1, last_B_)),
-               bytes, st, [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
+               bytes, st, [&] { skern(a.n1, c).row_prod<<<grid, c.block, c.smem, st>>>(a); });
     }
     template <int MODE> void col_pass(cx<T>* data, int res, int G, cudaStream_t st) {
         ColArgs<T> a{};
@@ -352,7 +351,10 @@ private:
         launch(std::string(MODE == COL_FWD ? "colpass_fwd" : MODE == COL_INV ? "colpass_inv" : "colpass_inv_mod_fwd") +
                    ":L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
                2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
-               [&] { k2d_colpass<T, MODE><<<grid, c.block, c.smem, st>>>(a); });
+               [&] {
+                   const StreamKernels<T> k = skern(a.n0, c);
+                   (MODE == COL_FWD ? k.col_fwd : MODE == COL_INV ? k.col_inv : k.col_imf)<<<grid, c.block, c.smem, st>>>(a);
+               });
     }
     template <bool INV> void row_pass(cx<T>* data, int res, int G, cudaStream_t st) {
         RowArgs<T> a{};
@@ -363,7 +365,7 @@ private:
         launch(std::string(INV ? "rowpass_inv" : "rowpass_fwd") + ":L" + std::to_string(res) + ":G" +
                    std::to_string(G / std::max(1, last_B_)),
                2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
-               [&] { k2d_rowpass<T, INV><<<grid, c.block, c.smem, st>>>(a); });
+               [&] { (INV ? skern(a.n1, c).row_inv : skern(a.n1, c).row_fwd)<<<grid, c.block, c.smem, st>>>(a); });
     }
     // Fourier low-pass: S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
@@ -394,7 +396,7 @@ private:
             dim3 grid((unsigned)G, ceil_div(m0_, c.lines));
             launch("rowpass_prod(low):L" + std::to_string(res),
                    (double)G * (a.P0 * a.P1 + m0_ * m1_) * sizeof(cx<T>), st,
-                   [&] { k2d_rowpass_prod<T><<<grid, c.block, c.smem, st>>>(a); });
+                   [&] { skern(a.n1, c).row_prod<<<grid, c.block, c.smem, st>>>(a); });
             col_pass<COL_INV>(tmp, J, G, st);
             CropArgs<T> ca{};
             ca.in = tmp; ca.out = out; ca.m0 = m0_; ca.m1 = m1_; ca.PP = PP; ca.NF = NF; ca.ch0 = ch0; ca.chs = chs;
@@ -462,7 +464,7 @@ private:
             a.lines = c.lines; a.LP = c.LP; a.plan = lev_[0].a1.plan; a.tw = tw(lev_[0].a1); a.pos = pos(lev_[0].a1);
             dim3 grid((unsigned)B, ceil_div(P0_, c.lines));
             launch("pad_rowfft", (double)B * (a.M * a.N * sizeof(T) + (double)P0_ * P1_ * sizeof(cx<T>)), st,
-                   [&] { k2d_pad_rowfft<T><<<grid, c.block, c.smem, st>>>(a); });
+                   [&] { skern(P1_, c).pad_rowfft<<<grid, c.block, c.smem, st>>>(a); });
             col_pass<COL_FWD>(U0, 0, B, st);
         }
         // S0 (core/scattering2d.py:18-28)
