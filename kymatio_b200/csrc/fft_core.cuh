@@ -38,6 +38,18 @@ template <typename T> SB_HD cx<T> cmul(cx<T> a, cx<T> b) { return mk<T>(a.x * b.
 template <typename T> SB_HD cx<T> cmulc(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 template <typename T> SB_HD cx<T> scal(cx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
 
+// |v|: the reference computes sqrt(x^2 + y^2) (kymatio/backend/torch_backend.py:57); on the device the
+// float version uses m2 * rsqrt(m2) (<= 2 ulp), exact zero at zero.
+template <typename T> SB_HD T cabs_fast(cx<T> v) {
+    const T m2 = v.x * v.x + v.y * v.y;
+#if defined(__CUDA_ARCH__)
+    if constexpr (std::is_same<T, float>::value) return m2 > 0.f ? m2 * rsqrtf(m2) : 0.f;
+    else return sqrt(m2);
+#else
+    return (T)__builtin_sqrt((double)m2);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // compile-time trigonometry (Taylor series in double; |x| <= pi)
 // ---------------------------------------------------------------------------
@@ -260,7 +272,7 @@ SB_HD void butterfly(cx<T>* line, int estride, int base, int q, int twstep, cons
 
 // Same butterfly with the group stride Q (in elements) and the element stride ES known at compile
 // time: every shared-memory access becomes base + immediate offset.
-template <int R, bool INV, int Q, int ES, typename T>
+template <int R, bool INV, int Q, int ES, bool MODULUS, typename T>
 SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
     constexpr int SIGN = INV ? +1 : -1;
     constexpr bool P2 = ct_is_pow2(R);
@@ -291,7 +303,8 @@ SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
     }
     static_for<0, R>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
-        p0[k * Q * ES] = v[k];
+        if constexpr (MODULUS) p0[k * Q * ES] = mk<T>(cabs_fast<T>(v[k]), T(0));
+        else p0[k * Q * ES] = v[k];
     });
 }
 

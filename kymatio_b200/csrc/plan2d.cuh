@@ -152,6 +152,11 @@ public:
         stream_kernels_enable_smem<T>();
         enable_big_smem(k2d_lowpass<T>);
         tile_kernels_enable_smem<T>();
+        {
+            int dev = 0;
+            SB_CUDA(cudaGetDevice(&dev));
+            SB_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
+        }
         compute_workspace();
     }
 
@@ -432,20 +437,27 @@ private:
         a.PP = PP; a.NFch = NFch; a.ch0 = ch0; a.chs = chs; a.K = K_;
         const size_t smem = tile_smem_layout<T>(a, nullptr);
         const int G = Bp * NF;
-        // threads: enough to cover the larger pass (lines x butterflies) in about two rounds
+        a.G = G;
+        bool is_static = false;
+        TileKernel<T> kern = tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
+        // threads: a field that runs alone on its SM takes every thread its instance allows; smaller
+        // fields use about one thread per 4 butterflies of the widest pass
         int maxbf = 1;
         for (int p = 0; p < a.plan1.npass; ++p) maxbf = std::max(maxbf, a.n1 / a.plan1.radix[p]);
         const int items = a.n0 * maxbf;
-        // a tile that fills more than half the SM's shared memory runs alone: give it every thread
-        // the register budget allows; smaller tiles share the SM (3-4 CTAs) with ~items/8 threads each
-        int threads = (2 * smem > kMaxDynSmem) ? tile_threads_cap_
-                                               : std::min(tile_threads_cap_, std::max(96, (items / 8 + 31) / 32 * 32));
+        const int cap = std::min(tile_threads_cap_, is_static ? tile_max_threads(a.n0, a.n1) : tile_max_threads(0, 0));
+        int threads = (2 * smem > kMaxDynSmem) ? cap : std::min(cap, std::max(96, (items / 4 + 31) / 32 * 32));
+        threads = threads / 32 * 32;
         dim3 block(32, threads / 32);
+        // persistent grid: as many CTAs as fit on the device at once
+        int occ = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        const int grid = std::max(1, std::min(G, std::max(1, occ) * num_sms_));
         const double bytes = (double)G * a.P0 * a.P1 * sizeof(cx<T>) + (double)NF * a.P0 * a.P1 * sizeof(T) +
                              (double)G * o0_ * o1_ * sizeof(T) + (spec_out ? (double)G * a.n0 * a.n1 * sizeof(cx<T>) : 0.0);
         launch(std::string("tile_") + what + ":L" + std::to_string(parent_res) + ">L" + std::to_string(res) + ":G" +
                    std::to_string(G / std::max(1, last_B_)),
-               bytes, st, [&] { tile_kernel_lookup<T>(a.n0, a.n1, a.k, nullptr)<<<(unsigned)G, block, smem, st>>>(a); });
+               bytes, st, [&] { kern<<<(unsigned)grid, block, smem, st>>>(a); });
     }
 
     void forward_chunk(const T* x, T* out, cx<T>* ws, int B, cudaStream_t st) {
@@ -520,7 +532,8 @@ private:
     std::vector<bool> tile_ok_;
     std::vector<size_t> tile_smem_;
     bool force_stream_ = false;
-    int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 544);
+    int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 576);
+    int num_sms_ = 148;
     size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, per_img_ = 0;
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;

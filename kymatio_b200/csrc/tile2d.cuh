@@ -30,6 +30,7 @@ template <typename T> struct TileArgs {
     int y0lo, y0cnt, x1lo, x1cnt;          // input window (start offset rel. to kl*(4*group+1), length) per 4-output group
     int kl, o0, o1, o0p, o1p;              // o?p = o? rounded up to a multiple of 4
     int PP, NFch, ch0, chs, K;
+    int G;                                 // number of paths; CTAs are persistent and stride over them
 };
 
 template <typename T> struct TileSmem {
@@ -68,6 +69,56 @@ __device__ __forceinline__ float fast_abs(float x, float y) {
 }
 __device__ __forceinline__ double fast_abs(double x, double y) { return sqrt(x * x + y * y); }
 
+// threads per CTA / CTAs per SM the instances are compiled for: a field that fills more than half of
+// the SM's shared memory runs alone with up to 576 threads (<= 112 registers); smaller fields share
+// the SM three at a time with up to 288 threads each (<= 75 registers).
+__host__ __device__ constexpr bool tile_is_big(int n0, int n1) { return n0 == 0 || (long long)n0 * n1 > 10000; }
+__host__ __device__ constexpr int tile_max_threads(int n0, int n1) { return tile_is_big(n0, n1) ? 576 : 288; }
+__host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_is_big(n0, n1) ? 1 : 3; }
+
+// product + periodise for VEC adjacent columns starting at column e of output row r
+template <typename T, int VEC, int KT>
+__device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, const cx<T>* __restrict__ pb,
+                                               const T* __restrict__ fb, int r, int e, int k, int n0, int n1, int W,
+                                               int P1, T scale) {
+    T ax[VEC], ay[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { ax[i] = T(0); ay[i] = T(0); }
+#pragma unroll
+    for (int c = 0; c < k; ++c) {
+        const int R = r + c * n0;
+        const int2 sp = m.supp[R];
+        if (sp.y == 0) continue;            // filter row entirely negligible
+        const size_t rowoff = (size_t)R * P1;
+#pragma unroll
+        for (int d = 0; d < k; ++d) {
+            const int C = e + d * n1;
+            int rel = C - sp.x;
+            if (rel < 0) rel += P1;
+            // any of the VEC columns C..C+VEC-1 inside the circular interval [start, start+len)
+            if ((rel < sp.y) | (rel > P1 - VEC)) {
+                if constexpr (VEC == 4) {
+                    const cx2<T> v0 = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
+                    const cx2<T> v1 = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C + 2);
+                    const re4<T> f = *reinterpret_cast<const re4<T>*>(fb + rowoff + C);
+                    ax[0] += v0.a.x * f.a; ay[0] += v0.a.y * f.a;
+                    ax[1] += v0.b.x * f.b; ay[1] += v0.b.y * f.b;
+                    ax[2] += v1.a.x * f.c; ay[2] += v1.a.y * f.c;
+                    ax[3] += v1.b.x * f.d; ay[3] += v1.b.y * f.d;
+                } else {
+                    const cx2<T> v = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
+                    const re2<T> f = *reinterpret_cast<const re2<T>*>(fb + rowoff + C);
+                    ax[0] += v.a.x * f.a; ay[0] += v.a.y * f.a;
+                    ax[1] += v.b.x * f.b; ay[1] += v.b.y * f.b;
+                }
+            }
+        }
+    }
+    const int prow = m.pos0[r] * W;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[prow + m.pos1[e + i]] = mk<T>(ax[i] * scale, ay[i] * scale);
+}
+
 template <typename T, int N0, int N1, int KT>
 __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     constexpr bool ST = N0 > 0;
@@ -77,150 +128,143 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     TileSmem<T> m;
     tile_smem_layout(a, &m);
     cx<T>* s = m.tile;
-    const int g = blockIdx.x;
-    const int fi = g % a.NF, pg = g / a.NF;
-    const int b = g / a.PP, path = g - b * a.PP;
-    const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
     const int tid = flat_tid(), nt = flat_nt();
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
+    // constants shared by every path this (persistent) CTA processes
     stage(m.tw0, a.tw0, n0); stage(m.tw1, a.tw1, n1);
     stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
-    stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
     stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
     stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
-    __syncthreads();
 
-    // 1. product + periodise: one output row per warp, two adjacent columns per lane (128-bit parent
-    //    loads); aliases outside the filter's support interval are skipped
-    {
-        const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
-        const T* __restrict__ fb = a.filt[fi];
-        const int P1 = a.P1, half = n1 >> 1;
-        for (int r = warp; r < n0; r += nwarps) {
-            const int prow = m.pos0[r] * W;
-            for (int e2 = lane; e2 < half; e2 += 32) {
-                const int e = 2 * e2;
-                T ax0 = T(0), ay0 = T(0), ax1 = T(0), ay1 = T(0);
-#pragma unroll
-                for (int c = 0; c < k; ++c) {
-                    const int R = r + c * n0;
-                    const int2 sp = m.supp[R];
-                    const size_t rowoff = (size_t)R * P1;
-#pragma unroll
-                    for (int d = 0; d < k; ++d) {
-                        const int C = e + d * n1;
-                        int rel = C - sp.x;
-                        if (rel < 0) rel += P1;
-                        if ((rel < sp.y) | ((rel == P1 - 1) & (sp.y > 0))) {
-                            const cx2<T> v = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
-                            const re2<T> f = *reinterpret_cast<const re2<T>*>(fb + rowoff + C);
-                            ax0 += v.a.x * f.a; ay0 += v.a.y * f.a;
-                            ax1 += v.b.x * f.b; ay1 += v.b.y * f.b;
-                        }
+    for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
+        const int fi = g % a.NF, pg = g / a.NF;
+        const int b = g / a.PP, path = g - b * a.PP;
+        const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
+        stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
+        __syncthreads();
+
+        // 1. product + periodise into scrambled (DIT-input) order: 4 (or 2) adjacent columns per thread with
+        //    128-bit loads, two independent items per iteration, aliases outside the filter support skipped
+        {
+            const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
+            const T* __restrict__ fb = a.filt[fi];
+            const int P1 = a.P1;
+            if ((n1 & 3) == 0 && (P1 & 3) == 0) {
+                const int per_row = n1 >> 2, items = n0 * per_row;
+                for (int it = tid; it < items; it += 2 * nt) {
+                    const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
+                    tile_load_item<T, 4, KT>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale);
+                    const int it1 = it + nt;
+                    if (it1 < items) {
+                        const int r1 = it1 / per_row, e1 = 4 * (it1 - r1 * per_row);
+                        tile_load_item<T, 4, KT>(s, m, pb, fb, r1, e1, k, n0, n1, W, P1, a.scale);
                     }
                 }
-                s[prow + m.pos1[e]] = mk<T>(ax0 * a.scale, ay0 * a.scale);
-                s[prow + m.pos1[e + 1]] = mk<T>(ax1 * a.scale, ay1 * a.scale);
+            } else {
+                const int per_row = n1 >> 1, items = n0 * per_row;
+                for (int it = tid; it < items; it += nt) {
+                    const int r0 = it / per_row, e0 = 2 * (it - r0 * per_row);
+                    tile_load_item<T, 2, KT>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale);
+                }
             }
         }
-    }
-    __syncthreads();
-    // 2. inverse 2-D FFT -> natural-order spatial field
-    if constexpr (ST) {
-        slab_fft_s<N1, true, (N1 | 1), 1, T>(s, N0, m.tw1);
-        slab_fft_s<N0, true, 1, (N1 | 1), T>(s, N1, m.tw0);
-    } else {
-        slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
-        slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
-    }
-    // 3. modulus (kept in .x; .y zeroed for the optional forward transform)
-    for (int y = warp; y < n0; y += nwarps)
-        for (int x = lane; x < n1; x += 32) {
-            const cx<T> v = s[y * W + x];
-            s[y * W + x] = mk<T>(fast_abs(v.x, v.y), T(0));
+        __syncthreads();
+        // 2+3. inverse 2-D FFT -> natural-order spatial field, modulus applied in the registers of the last pass
+        if constexpr (ST) {
+            slab_fft_s<N1, true, (N1 | 1), 1, T>(s, N0, m.tw1);
+            slab_fft_s<N0, true, 1, (N1 | 1), T, true>(s, N1, m.tw0);
+        } else {
+            slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
+            slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
+            for (int y = warp; y < n0; y += nwarps)
+                for (int x = lane; x < n1; x += 32) s[y * W + x] = mk<T>(cabs_fast<T>(s[y * W + x]), T(0));
+            __syncthreads();
         }
-    __syncthreads();
-    // 4a. horizontal low-pass + decimation + unpad: w1[y][xo] = sum_x U[y][x] * G1[x][xo]
-    //     register tile: 4 rows x 4 outputs per thread, x restricted to the group's input window
-    {
-        const int rgroups = (n0 + 3) >> 2, xgroups = a.o1p >> 2;
-        for (int it = tid; it < rgroups * xgroups; it += nt) {
-            const int xg = it / rgroups, rg = it - xg * rgroups;
-            int yy[4];
+        // 4a. horizontal low-pass + decimation + unpad: w1[y][xo] = sum_x U[y][x] * G1[x][xo]
+        //     register tile: 4 rows x 4 outputs per thread, x restricted to the group's input window
+        {
+            const int rgroups = (n0 + 3) >> 2, xgroups = a.o1p >> 2;
+            for (int it = tid; it < rgroups * xgroups; it += nt) {
+                const int xg = it / rgroups, rg = it - xg * rgroups;
+                int yy[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) yy[j] = min(rg + j * rgroups, n0 - 1) * W;
-            T acc[4][4];
+                for (int j = 0; j < 4; ++j) yy[j] = min(rg + j * rgroups, n0 - 1) * W;
+                T acc[4][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-            int x = (a.kl * (4 * xg + 1) + a.x1lo) % n1;
-            if (x < 0) x += n1;
-            for (int st = 0; st < a.x1cnt; ++st) {
-                const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G1 + x * a.o1p + 4 * xg);
+                    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+                int x = (a.kl * (4 * xg + 1) + a.x1lo) % n1;
+                if (x < 0) x += n1;
+                for (int st = 0; st < a.x1cnt; ++st) {
+                    const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G1 + x * a.o1p + 4 * xg);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const T u = s[yy[j] + x].x;
+                        acc[j][0] += u * gq.a; acc[j][1] += u * gq.b; acc[j][2] += u * gq.c; acc[j][3] += u * gq.d;
+                    }
+                    x = (x + 1 == n1) ? 0 : x + 1;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const T u = s[yy[j] + x].x;
-                    acc[j][0] += u * gq.a; acc[j][1] += u * gq.b; acc[j][2] += u * gq.c; acc[j][3] += u * gq.d;
-                }
-                x = (x + 1 == n1) ? 0 : x + 1;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int y = rg + j * rgroups;
-                if (y < n0) {
-                    re4<T> o; o.a = acc[j][0]; o.b = acc[j][1]; o.c = acc[j][2]; o.d = acc[j][3];
-                    *reinterpret_cast<re4<T>*>(m.w1 + y * a.o1p + 4 * xg) = o;
+                    const int y = rg + j * rgroups;
+                    if (y < n0) {
+                        re4<T> o; o.a = acc[j][0]; o.b = acc[j][1]; o.c = acc[j][2]; o.d = acc[j][3];
+                        *reinterpret_cast<re4<T>*>(m.w1 + y * a.o1p + 4 * xg) = o;
+                    }
                 }
             }
         }
-    }
-    __syncthreads();
-    // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
-    //     S[yo][xo] = sum_y G0[y][yo] * w1[y][xo]; 4 output rows per thread, lanes along xo
-    {
-        T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
-        const int ygroups = a.o0p >> 2;
-        for (int it = tid; it < ygroups * a.o1p; it += nt) {
-            const int yg = it / a.o1p, xo = it - yg * a.o1p;
-            T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
-            int y = (a.kl * (4 * yg + 1) + a.y0lo) % n0;
-            if (y < 0) y += n0;
-            for (int st = 0; st < a.y0cnt; ++st) {
-                const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G0 + y * a.o0p + 4 * yg);
-                const T w = m.w1[y * a.o1p + xo];
-                acc0 += w * gq.a; acc1 += w * gq.b; acc2 += w * gq.c; acc3 += w * gq.d;
-                y = (y + 1 == n0) ? 0 : y + 1;
+        __syncthreads();
+        // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
+        //     S[yo][xo] = sum_y G0[y][yo] * w1[y][xo]; 4 output rows per thread, lanes along xo
+        {
+            T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+            const int ygroups = a.o0p >> 2;
+            for (int it = tid; it < ygroups * a.o1p; it += nt) {
+                const int yg = it / a.o1p, xo = it - yg * a.o1p;
+                T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+                int y = (a.kl * (4 * yg + 1) + a.y0lo) % n0;
+                if (y < 0) y += n0;
+                for (int st = 0; st < a.y0cnt; ++st) {
+                    const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G0 + y * a.o0p + 4 * yg);
+                    const T w = m.w1[y * a.o1p + xo];
+                    acc0 += w * gq.a; acc1 += w * gq.b; acc2 += w * gq.c; acc3 += w * gq.d;
+                    y = (y + 1 == n0) ? 0 : y + 1;
+                }
+                if (xo < a.o1) {
+                    const int yo = 4 * yg;
+                    if (yo + 0 < a.o0) ob[(yo + 0) * a.o1 + xo] = acc0;
+                    if (yo + 1 < a.o0) ob[(yo + 1) * a.o1 + xo] = acc1;
+                    if (yo + 2 < a.o0) ob[(yo + 2) * a.o1 + xo] = acc2;
+                    if (yo + 3 < a.o0) ob[(yo + 3) * a.o1 + xo] = acc3;
+                }
             }
-            if (xo < a.o1) {
-                const int yo = 4 * yg;
-                if (yo + 0 < a.o0) ob[(yo + 0) * a.o1 + xo] = acc0;
-                if (yo + 1 < a.o0) ob[(yo + 1) * a.o1 + xo] = acc1;
-                if (yo + 2 < a.o0) ob[(yo + 2) * a.o1 + xo] = acc2;
-                if (yo + 3 < a.o0) ob[(yo + 3) * a.o1 + xo] = acc3;
+        }
+        // 5. forward 2-D FFT of U for the children of this path (natural-order store)
+        if (a.spec_out) {
+            if constexpr (ST) {
+                slab_fft_s<N1, false, (N1 | 1), 1, T>(s, N0, m.tw1);
+                slab_fft_s<N0, false, 1, (N1 | 1), T>(s, N1, m.tw0);
+            } else {
+                slab_fft<false, T>(s, n0, W, 1, a.plan1, m.tw1);
+                slab_fft<false, T>(s, n1, 1, W, a.plan0, m.tw0);
+            }
+            cx<T>* ob = a.spec_out + (size_t)g * n0 * n1;
+            for (int r = warp; r < n0; r += nwarps) {
+                const int prow = m.pos0[r] * W;
+                for (int e = lane; e < n1; e += 32) ob[(size_t)r * n1 + e] = s[prow + m.pos1[e]];
             }
         }
-    }
-    // 5. forward 2-D FFT of U for the children of this path (natural-order store)
-    if (a.spec_out) {
-        if constexpr (ST) {
-            slab_fft_s<N1, false, (N1 | 1), 1, T>(s, N0, m.tw1);
-            slab_fft_s<N0, false, 1, (N1 | 1), T>(s, N1, m.tw0);
-        } else {
-            slab_fft<false, T>(s, n0, W, 1, a.plan1, m.tw1);
-            slab_fft<false, T>(s, n1, 1, W, a.plan0, m.tw0);
-        }
-        cx<T>* ob = a.spec_out + (size_t)g * n0 * n1;
-        for (int r = warp; r < n0; r += nwarps) {
-            const int prow = m.pos0[r] * W;
-            for (int e = lane; e < n1; e += 32) ob[(size_t)r * n1 + e] = s[prow + m.pos1[e]];
-        }
+        __syncthreads();   // the next path rewrites the tile, the support rows and w1
     }
 }
 
 template <typename T, int N0, int N1, int KT>
-__global__ void __launch_bounds__(kMaxThreads) k2d_tile(TileArgs<T> a) { tile_body<T, N0, N1, KT>(a); }
+__global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, N1)) k2d_tile(TileArgs<T> a) {
+    tile_body<T, N0, N1, KT>(a);
+}
 
 // specialised instances are compiled in tile_inst_*.cu; returns the kernel for (n0, n1, k) or the
 // generic one
