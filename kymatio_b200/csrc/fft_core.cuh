@@ -271,10 +271,12 @@ SB_HD void butterfly(cx<T>* line, int estride, int base, int q, int twstep, cons
 }
 
 // Same butterfly with the group stride Q (in elements) and the element stride ES known at compile
-// time: every shared-memory access becomes base + immediate offset.
-template <int R, bool INV, int Q, int ES, bool MODULUS, typename T>
+// time: every shared-memory access becomes base + immediate offset.  The flow (DIT: twiddle then
+// butterfly, scrambled -> natural; DIF: butterfly then twiddle, natural -> scrambled) and the sign of
+// the exponent are independent, so an inverse transform can run as DIF (natural-order input) and a
+// forward one as DIT (natural-order output).
+template <int R, bool DIT, int SIGN, int Q, int ES, bool MODULUS, typename T>
 SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
-    constexpr int SIGN = INV ? +1 : -1;
     constexpr bool P2 = ct_is_pow2(R);
     constexpr int LG = ct_log2(R);
     cx<T> v[R];
@@ -282,13 +284,13 @@ SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
         constexpr int k = decltype(k_)::value;
         v[k] = p0[k * Q * ES];
     });
-    if (!INV) {
+    if (!DIT) {
         if constexpr (P2) dif_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
         if constexpr (Q > 1) {
             static_for<1, R>([&](auto k_) {
                 constexpr int k = decltype(k_)::value;
                 constexpr int f = P2 ? ct_bitrev(k, LG) : k;
-                v[k] = cmul(v[k], tw[f * twstep]);
+                v[k] = SIGN < 0 ? cmul(v[k], tw[f * twstep]) : cmulc(v[k], tw[f * twstep]);
             });
         }
     } else {
@@ -296,7 +298,7 @@ SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
             static_for<1, R>([&](auto k_) {
                 constexpr int k = decltype(k_)::value;
                 constexpr int f = P2 ? ct_bitrev(k, LG) : k;
-                v[k] = cmulc(v[k], tw[f * twstep]);
+                v[k] = SIGN < 0 ? cmul(v[k], tw[f * twstep]) : cmulc(v[k], tw[f * twstep]);
             });
         }
         if constexpr (P2) dit_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);

@@ -40,6 +40,27 @@ template <typename U> __device__ __forceinline__ void stage(U* dst, const U* __r
     for (int i = flat_tid(); i < n; i += flat_nt()) dst[i] = src[i];
 }
 
+template <typename T> struct alignas(2 * sizeof(cx<T>)) cx2 { cx<T> a, b; };
+template <typename T> struct alignas(2 * sizeof(T)) re2 { T a, b; };
+template <typename T> struct alignas(4 * sizeof(T)) re4 { T a, b, c, d; };
+
+// 16-byte predicated read-only global load (zero when the predicate is false): keeps the alias loads of
+// the product/periodise prologue branch-free so that all of them are in flight together
+__device__ __forceinline__ uint4 ldg16_pred(const void* ptr, bool pred) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
+        : "l"(ptr), "r"((int)pred));
+    return r;
+}
+template <typename V> __device__ __forceinline__ V ld_pred(const void* ptr, bool pred) {
+    static_assert(sizeof(V) % 16 == 0, "ld_pred needs 16-byte multiples");
+    union { V v; uint4 q[sizeof(V) / 16]; } u;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(V) / 16); ++i) u.q[i] = ldg16_pred(static_cast<const char*>(ptr) + 16 * i, pred);
+    return u.v;
+}
+
 // sum over the k x k aliases of (parent * filter) for output bin (r, e), skipping aliases outside
 // the filter's per-row support interval.  supp may live in shared or global memory.
 template <typename T>
@@ -111,7 +132,7 @@ template <typename T, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d
         s[e * LP + l] = mk<T>(xb[(size_t)sr * a.N + sc], T(0));
     }
     __syncthreads();
-    if constexpr (NS > 0) slab_fft_s<NS, false, 1, kSLP, T>(s, nl, tw);
+    if constexpr (NS > 0) slab_fft_s<NS, false, -1, 1, kSLP, T>(s, nl, tw);
     else slab_fft<false, T>(s, nl, 1, LP, a.plan, tw);
     cx<T>* ob = a.out + ((size_t)b * a.P0 + r0) * P1;
     for (int idx = flat_tid(); idx < nl * P1; idx += flat_nt()) {
@@ -145,26 +166,31 @@ template <typename T, int MODE, int NS> __global__ void __launch_bounds__(kMaxTh
     const cx<T>* ib = a.in + (size_t)g * n0 * a.n1 + c0;
     cx<T>* ob = a.out + (size_t)g * n0 * a.n1 + c0;
     const int tid = flat_tid(), nt = flat_nt();
+    // static COL_INV_MOD_FWD runs DIF(+) -> modulus -> DIT(-): natural order on both global sides, no scatter
+    constexpr bool PLAIN = (NS > 0 && MODE == COL_INV_MOD_FWD);
     if (NS > 0 && nl == kSLines && (a.n1 & 1) == 0) {
         // full slab: 8 lanes x 16 bytes per row segment
         for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
             const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
             const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)e * a.n1 + l);
-            const int se = (MODE == COL_FWD) ? e : pos[e];
+            const int se = (MODE == COL_FWD || PLAIN) ? e : pos[e];
             s[se * LP + l] = v.a; s[se * LP + l + 1] = v.b;
         }
     } else {
         for (int idx = tid; idx < n0 * lines; idx += nt) {
             const int e = idx / lines, l = idx - e * lines;
-            if (l < nl) s[((MODE == COL_FWD) ? e : pos[e]) * LP + l] = ib[(size_t)e * a.n1 + l];
+            if (l < nl) s[((MODE == COL_FWD || PLAIN) ? e : pos[e]) * LP + l] = ib[(size_t)e * a.n1 + l];
         }
     }
     __syncthreads();
     if (MODE == COL_FWD) {
-        if constexpr (NS > 0) slab_fft_s<NS, false, 1, kSLP, T>(s, nl, tw);
+        if constexpr (NS > 0) slab_fft_s<NS, false, -1, 1, kSLP, T>(s, nl, tw);
         else slab_fft<false, T>(s, nl, 1, LP, a.plan, tw);
+    } else if constexpr (PLAIN) {
+        slab_fft_s<NS, false, +1, 1, kSLP, T, true>(s, nl, tw);
+        slab_fft_s<NS, true, -1, 1, kSLP, T>(s, nl, tw);
     } else {
-        if constexpr (NS > 0) slab_fft_s<NS, true, 1, kSLP, T>(s, nl, tw);
+        if constexpr (NS > 0) slab_fft_s<NS, true, +1, 1, kSLP, T>(s, nl, tw);
         else slab_fft<true, T>(s, nl, 1, LP, a.plan, tw);
         if (MODE == COL_INV_MOD_FWD) {
             for (int idx = tid; idx < n0 * lines; idx += nt) {
@@ -173,21 +199,21 @@ template <typename T, int MODE, int NS> __global__ void __launch_bounds__(kMaxTh
                 s[e * LP + l] = mk<T>(abs2f(v.x, v.y), T(0));
             }
             __syncthreads();
-            if constexpr (NS > 0) slab_fft_s<NS, false, 1, kSLP, T>(s, nl, tw);
+            if constexpr (NS > 0) slab_fft_s<NS, false, -1, 1, kSLP, T>(s, nl, tw);
             else slab_fft<false, T>(s, nl, 1, LP, a.plan, tw);
         }
     }
     if (NS > 0 && nl == kSLines && (a.n1 & 1) == 0) {
         for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
             const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
-            const int se = (MODE == COL_INV) ? e : pos[e];
+            const int se = (MODE == COL_INV || PLAIN) ? e : pos[e];
             cxpair<T> v; v.a = s[se * LP + l]; v.b = s[se * LP + l + 1];
             *reinterpret_cast<cxpair<T>*>(ob + (size_t)e * a.n1 + l) = v;
         }
     } else {
         for (int idx = tid; idx < n0 * lines; idx += nt) {
             const int e = idx / lines, l = idx - e * lines;
-            if (l < nl) ob[(size_t)e * a.n1 + l] = s[((MODE == COL_INV) ? e : pos[e]) * LP + l];
+            if (l < nl) ob[(size_t)e * a.n1 + l] = s[((MODE == COL_INV || PLAIN) ? e : pos[e]) * LP + l];
         }
     }
 }
@@ -220,40 +246,50 @@ template <typename T, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d
     const T* __restrict__ fb = a.filt[fi];
     const int2* sp = a.supp + (size_t)fi * a.P0;
     const int tid = flat_tid(), nt = flat_nt();
+    // static instances keep natural order in shared memory (the inverse runs as DIF and leaves the row
+    // scrambled, which the following column/row passes of the chain expect); generic ones scatter for DIT
     if ((n1 & 1) == 0) {
-        // two adjacent columns per thread (128-bit parent loads), support-interval skipping
         const int half = n1 >> 1, P1 = a.P1, k = a.k;
         for (int idx = tid; idx < nl * half; idx += nt) {
             const int l = idx / half, e = 2 * (idx - l * half);
             T ax0 = T(0), ay0 = T(0), ax1 = T(0), ay1 = T(0);
-            for (int c = 0; c < k; ++c) {
-                const int R = r0 + l + c * a.n0;
-                const int2 iv = sp[R];
-                const size_t rowoff = (size_t)R * P1;
-                for (int d = 0; d < k; ++d) {
-                    const int C = e + d * n1;
-                    int rel = C - iv.x;
-                    if (rel < 0) rel += P1;
-                    if ((rel < iv.y) | ((rel == P1 - 1) & (iv.y > 0))) {
-                        const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(pb + rowoff + C);
-                        const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + rowoff + C);
-                        ax0 += v.a.x * f.a; ay0 += v.a.y * f.a;
-                        ax1 += v.b.x * f.b; ay1 += v.b.y * f.b;
+            if (k == 1) {
+                // no aliases: plain vector loads (values outside the support interval are the true, tiny ones)
+                const size_t off = (size_t)(r0 + l) * P1 + e;
+                const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(pb + off);
+                const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + off);
+                ax0 = v.a.x * f.a; ay0 = v.a.y * f.a; ax1 = v.b.x * f.b; ay1 = v.b.y * f.b;
+            } else {
+                for (int c = 0; c < k; ++c) {
+                    const int R = r0 + l + c * a.n0;
+                    const int2 iv = sp[R];
+                    if (iv.y == 0) continue;
+                    const size_t rowoff = (size_t)R * P1;
+                    for (int d = 0; d < k; ++d) {
+                        const int C = e + d * n1;
+                        int rel = C - iv.x;
+                        if (rel < 0) rel += P1;
+                        if ((rel < iv.y) | (rel == P1 - 1)) {
+                            const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(pb + rowoff + C);
+                            const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + rowoff + C);
+                            ax0 += v.a.x * f.a; ay0 += v.a.y * f.a;
+                            ax1 += v.b.x * f.b; ay1 += v.b.y * f.b;
+                        }
                     }
                 }
             }
-            s[pos[e] * LP + l] = mk<T>(ax0 * a.scale, ay0 * a.scale);
-            s[pos[e + 1] * LP + l] = mk<T>(ax1 * a.scale, ay1 * a.scale);
+            s[(NS ? e : pos[e]) * LP + l] = mk<T>(ax0 * a.scale, ay0 * a.scale);
+            s[(NS ? e + 1 : pos[e + 1]) * LP + l] = mk<T>(ax1 * a.scale, ay1 * a.scale);
         }
     } else {
         for (int idx = tid; idx < nl * n1; idx += nt) {
             const int l = idx / n1, e = idx - l * n1;
             const cx<T> v = prod_fold<T>(pb, fb, sp, r0 + l, e, a.k, a.n0, n1, a.P1);
-            s[pos[e] * LP + l] = scal(v, a.scale);
+            s[(NS ? e : pos[e]) * LP + l] = scal(v, a.scale);
         }
     }
     __syncthreads();
-    if constexpr (NS > 0) slab_fft_s<NS, true, 1, kSLP, T>(s, nl, tw);
+    if constexpr (NS > 0) slab_fft_s<NS, false, +1, 1, kSLP, T>(s, nl, tw);
     else slab_fft<true, T>(s, nl, 1, LP, a.plan, tw);
     cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * n1;
     if ((n1 & 1) == 0) {
@@ -292,13 +328,16 @@ template <typename T, bool INV, int NS> __global__ void __launch_bounds__(kMaxTh
     const cx<T>* ib = a.in + ((size_t)g * a.n0 + r0) * n1;
     cx<T>* ob = a.out + ((size_t)g * a.n0 + r0) * n1;
     const int tid = flat_tid(), nt = flat_nt();
+    // static forward instance: the row arrives scrambled (left so by the static chain's DIF inverse), DIT(-)
+    // returns natural-order Fourier data - no permutation on either side
+    constexpr bool PLAIN = (NS > 0 && !INV);
     if ((n1 & 1) == 0) {
         const int half = n1 >> 1;
         for (int idx = tid; idx < nl * half; idx += nt) {
             const int l = idx / half, e = 2 * (idx - l * half);
             const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)l * n1 + e);
-            s[(INV ? pos[e] : e) * LP + l] = v.a;
-            s[(INV ? pos[e + 1] : e + 1) * LP + l] = v.b;
+            s[((INV && !PLAIN) ? pos[e] : e) * LP + l] = v.a;
+            s[((INV && !PLAIN) ? pos[e + 1] : e + 1) * LP + l] = v.b;
         }
     } else {
         for (int idx = tid; idx < nl * n1; idx += nt) {
@@ -307,15 +346,16 @@ template <typename T, bool INV, int NS> __global__ void __launch_bounds__(kMaxTh
         }
     }
     __syncthreads();
-    if constexpr (NS > 0) slab_fft_s<NS, INV, 1, kSLP, T>(s, nl, tw);
+    if constexpr (PLAIN) slab_fft_s<NS, true, -1, 1, kSLP, T>(s, nl, tw);
+    else if constexpr (NS > 0) slab_fft_s<NS, true, +1, 1, kSLP, T>(s, nl, tw);
     else slab_fft<INV, T>(s, nl, 1, LP, a.plan, tw);
     if ((n1 & 1) == 0) {
         const int half = n1 >> 1;
         for (int idx = tid; idx < nl * half; idx += nt) {
             const int l = idx / half, e = 2 * (idx - l * half);
             cxpair<T> v;
-            v.a = s[(INV ? e : pos[e]) * LP + l];
-            v.b = s[(INV ? e + 1 : pos[e + 1]) * LP + l];
+            v.a = s[((INV || PLAIN) ? e : pos[e]) * LP + l];
+            v.b = s[((INV || PLAIN) ? e + 1 : pos[e + 1]) * LP + l];
             *reinterpret_cast<cxpair<T>*>(ob + (size_t)l * n1 + e) = v;
         }
     } else {

@@ -322,8 +322,13 @@ private:
     }
 
     // kernel table for line length n; the static instances need the default 16-line slab shape
-    StreamKernels<T> skern(int n, const SlabCfg& c) const {
-        return stream_kernels_lookup<T>(n, c.lines == kSLines && c.LP == kSLP);
+    StreamKernels<T> skern(int n, const SlabCfg& c, bool allow = true) const {
+        return stream_kernels_lookup<T>(n, allow && c.lines == kSLines && c.LP == kSLP);
+    }
+    // the static product -> column -> row chain hands scrambled rows from kernel to kernel, so all three
+    // launches of a level must agree: static only when both axis lengths have compiled instances
+    bool chain_static(int res) const {
+        return skern(lev_[res].a0.n, col_cfg_[res]).is_static && skern(lev_[res].a1.n, row_cfg_[res]).is_static;
     }
 
     // ---------------------------------------------------------------- launch wrappers
@@ -345,7 +350,7 @@ private:
                              G * a.n0 * a.n1 * sizeof(cx<T>);
         launch("rowpass_prod:L" + std::to_string(parent_res) + ">L" + std::to_string(out_res) + ":G" +
                    std::to_string((int)G / std::max(1, last_B_)),
-               bytes, st, [&] { skern(a.n1, c).row_prod<<<grid, c.block, c.smem, st>>>(a); });
+               bytes, st, [&] { skern(a.n1, c, chain_static(out_res)).row_prod<<<grid, c.block, c.smem, st>>>(a); });
     }
     template <int MODE> void col_pass(cx<T>* data, int res, int G, cudaStream_t st) {
         ColArgs<T> a{};
@@ -357,7 +362,7 @@ private:
                    ":L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
                2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
                [&] {
-                   const StreamKernels<T> k = skern(a.n0, c);
+                   const StreamKernels<T> k = skern(a.n0, c, MODE != COL_INV_MOD_FWD || chain_static(res));
                    (MODE == COL_FWD ? k.col_fwd : MODE == COL_INV ? k.col_inv : k.col_imf)<<<grid, c.block, c.smem, st>>>(a);
                });
     }
@@ -370,7 +375,10 @@ private:
         launch(std::string(INV ? "rowpass_inv" : "rowpass_fwd") + ":L" + std::to_string(res) + ":G" +
                    std::to_string(G / std::max(1, last_B_)),
                2.0 * G * a.n0 * a.n1 * sizeof(cx<T>), st,
-               [&] { (INV ? skern(a.n1, c).row_inv : skern(a.n1, c).row_fwd)<<<grid, c.block, c.smem, st>>>(a); });
+               [&] {
+                   const StreamKernels<T> k = skern(a.n1, c, INV || chain_static(res));
+                   (INV ? k.row_inv : k.row_fwd)<<<grid, c.block, c.smem, st>>>(a);
+               });
     }
     // Fourier low-pass: S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
@@ -401,7 +409,7 @@ private:
             dim3 grid((unsigned)G, ceil_div(m0_, c.lines));
             launch("rowpass_prod(low):L" + std::to_string(res),
                    (double)G * (a.P0 * a.P1 + m0_ * m1_) * sizeof(cx<T>), st,
-                   [&] { skern(a.n1, c).row_prod<<<grid, c.block, c.smem, st>>>(a); });
+                   [&] { skern(a.n1, c, false).row_prod<<<grid, c.block, c.smem, st>>>(a); });
             col_pass<COL_INV>(tmp, J, G, st);
             CropArgs<T> ca{};
             ca.in = tmp; ca.out = out; ca.m0 = m0_; ca.m1 = m1_; ca.PP = PP; ca.NF = NF; ca.ch0 = ch0; ca.chs = chs;

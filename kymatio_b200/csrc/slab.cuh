@@ -38,21 +38,23 @@ __device__ __noinline__ void slab_fft(cx<T>* s, int lines, int lstride, int estr
 
 // Compile-time variant: length N, line stride LS and element stride ES are constants, so the
 // pass loop is fully unrolled and every butterfly access is base + immediate offset.
+//   DIT = false: decimation in frequency, natural -> scrambled;  DIT = true: scrambled -> natural
+//   SIGN = -1 forward, +1 inverse (unnormalised)
 // MODULUS = true replaces every output of the LAST pass by (|v|, 0) while it is still in registers.
-template <int N, bool INV, int LS, int ES, typename T, bool MODULUS = false>
+template <int N, bool DIT, int SIGN, int LS, int ES, typename T, bool MODULUS = false>
 __device__ __forceinline__ void slab_fft_s(cx<T>* s, const int lines, const cx<T>* tw) {
     constexpr int NP = ct_plan1(N).npass;
     const int tid = flat_tid(), nt = flat_nt();
     static_for<0, NP>([&](auto pp_) {
         constexpr int pp = decltype(pp_)::value;
-        constexpr int p = INV ? NP - 1 - pp : pp;
+        constexpr int p = DIT ? NP - 1 - pp : pp;
         constexpr int r = ct_plan1(N).radix[p], m = ct_plan1(N).blen[p];
         constexpr int q = m / r, nbf = N / r, tws = N / m;
         const int items = nbf * lines;
         for (int it = tid; it < items; it += nt) {
             const int bf = it / lines, line = it - bf * lines;
             const int blk = bf / q, i = bf - blk * q;
-            butterfly_s<r, INV, q, ES, (MODULUS && pp == NP - 1), T>(s + line * LS + (blk * m + i) * ES, i * tws, tw);
+            butterfly_s<r, DIT, SIGN, q, ES, (MODULUS && pp == NP - 1), T>(s + line * LS + (blk * m + i) * ES, i * tws, tw);
         }
         __syncthreads();
     });

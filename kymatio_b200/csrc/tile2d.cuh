@@ -42,7 +42,7 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
     const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
     const size_t o_supp = take(sizeof(int2) * a.P0);
-    const size_t o_w1 = take(sizeof(T) * (size_t)a.n0 * a.o1p);
+    const size_t o_w1 = take(sizeof(T) * (size_t)a.n0 * (a.o1p + 4));
     const size_t o_g0 = take(sizeof(T) * (size_t)a.n0 * a.o0p), o_g1 = take(sizeof(T) * (size_t)a.n1 * a.o1p);
     const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
     if (L) {
@@ -59,10 +59,6 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     return off;
 }
 
-template <typename T> struct alignas(2 * sizeof(cx<T>)) cx2 { cx<T> a, b; };
-template <typename T> struct alignas(2 * sizeof(T)) re2 { T a, b; };
-template <typename T> struct alignas(4 * sizeof(T)) re4 { T a, b, c, d; };
-
 __device__ __forceinline__ float fast_abs(float x, float y) {
     const float m2 = x * x + y * y;
     return m2 > 0.f ? m2 * rsqrtf(m2) : 0.f;      // <= 2 ulp; the reference computes sqrt(x^2+y^2)
@@ -76,47 +72,96 @@ __host__ __device__ constexpr bool tile_is_big(int n0, int n1) { return n0 == 0 
 __host__ __device__ constexpr int tile_max_threads(int n0, int n1) { return tile_is_big(n0, n1) ? 576 : 288; }
 __host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_is_big(n0, n1) ? 1 : 3; }
 
-// product + periodise for VEC adjacent columns starting at column e of output row r
-template <typename T, int VEC, int KT>
+// product + periodise for VEC adjacent columns starting at column e of output row r.
+//   NATURAL = true : result stored at s[r*W + e + i] (static instances: the inverse runs as DIF)
+//   NATURAL = false: result scattered to s[pos0[r]*W + pos1[e+i]] (generic instance: DIT inverse)
+template <typename T, int VEC, int KT, bool NATURAL>
 __device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, const cx<T>* __restrict__ pb,
                                                const T* __restrict__ fb, int r, int e, int k, int n0, int n1, int W,
-                                               int P1, T scale) {
+                                               int P1, T scale, int lane) {
     T ax[VEC], ay[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { ax[i] = T(0); ay[i] = T(0); }
+    if constexpr (KT > 0 && VEC == 4) {
+        // compile-time alias count: predicated loads, no branches inside a filter row
 #pragma unroll
-    for (int c = 0; c < k; ++c) {
-        const int R = r + c * n0;
-        const int2 sp = m.supp[R];
-        if (sp.y == 0) continue;            // filter row entirely negligible
-        const size_t rowoff = (size_t)R * P1;
+        for (int c = 0; c < KT; ++c) {
+            const int R = r + c * n0;
+            const int2 sp = m.supp[R];
+            if (KT > 2 && sp.y == 0) continue;            // whole filter row negligible (common for coarse psi)
+            const size_t rowoff = (size_t)R * P1;
+            cx2<T> v0[KT], v1[KT];
+            re4<T> f[KT];
 #pragma unroll
-        for (int d = 0; d < k; ++d) {
-            const int C = e + d * n1;
-            int rel = C - sp.x;
-            if (rel < 0) rel += P1;
-            // any of the VEC columns C..C+VEC-1 inside the circular interval [start, start+len)
-            if ((rel < sp.y) | (rel > P1 - VEC)) {
-                if constexpr (VEC == 4) {
-                    const cx2<T> v0 = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
-                    const cx2<T> v1 = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C + 2);
-                    const re4<T> f = *reinterpret_cast<const re4<T>*>(fb + rowoff + C);
-                    ax[0] += v0.a.x * f.a; ay[0] += v0.a.y * f.a;
-                    ax[1] += v0.b.x * f.b; ay[1] += v0.b.y * f.b;
-                    ax[2] += v1.a.x * f.c; ay[2] += v1.a.y * f.c;
-                    ax[3] += v1.b.x * f.d; ay[3] += v1.b.y * f.d;
-                } else {
-                    const cx2<T> v = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
-                    const re2<T> f = *reinterpret_cast<const re2<T>*>(fb + rowoff + C);
-                    ax[0] += v.a.x * f.a; ay[0] += v.a.y * f.a;
-                    ax[1] += v.b.x * f.b; ay[1] += v.b.y * f.b;
+            for (int d = 0; d < KT; ++d) {
+                const int C = e + d * n1;
+                int rel = C - sp.x;
+                if (rel < 0) rel += P1;
+                const bool in = (rel < sp.y) | ((rel > P1 - 4) & (sp.y > 0));
+                v0[d] = ld_pred<cx2<T>>(pb + rowoff + C, in);
+                v1[d] = ld_pred<cx2<T>>(pb + rowoff + C + 2, in);
+                f[d] = ld_pred<re4<T>>(fb + rowoff + C, in);
+            }
+#pragma unroll
+            for (int d = 0; d < KT; ++d) {
+                ax[0] += v0[d].a.x * f[d].a; ay[0] += v0[d].a.y * f[d].a;
+                ax[1] += v0[d].b.x * f[d].b; ay[1] += v0[d].b.y * f[d].b;
+                ax[2] += v1[d].a.x * f[d].c; ay[2] += v1[d].a.y * f[d].c;
+                ax[3] += v1[d].b.x * f[d].d; ay[3] += v1[d].b.y * f[d].d;
+            }
+        }
+    } else {
+        for (int c = 0; c < k; ++c) {
+            const int R = r + c * n0;
+            const int2 sp = m.supp[R];
+            if (sp.y == 0) continue;
+            const size_t rowoff = (size_t)R * P1;
+            for (int d = 0; d < k; ++d) {
+                const int C = e + d * n1;
+                int rel = C - sp.x;
+                if (rel < 0) rel += P1;
+                if ((rel < sp.y) | (rel > P1 - VEC)) {
+                    if constexpr (VEC == 4) {
+                        const cx2<T> v0 = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
+                        const cx2<T> v1 = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C + 2);
+                        const re4<T> f = *reinterpret_cast<const re4<T>*>(fb + rowoff + C);
+                        ax[0] += v0.a.x * f.a; ay[0] += v0.a.y * f.a;
+                        ax[1] += v0.b.x * f.b; ay[1] += v0.b.y * f.b;
+                        ax[2] += v1.a.x * f.c; ay[2] += v1.a.y * f.c;
+                        ax[3] += v1.b.x * f.d; ay[3] += v1.b.y * f.d;
+                    } else {
+                        const cx2<T> v = *reinterpret_cast<const cx2<T>*>(pb + rowoff + C);
+                        const re2<T> f = *reinterpret_cast<const re2<T>*>(fb + rowoff + C);
+                        ax[0] += v.a.x * f.a; ay[0] += v.a.y * f.a;
+                        ax[1] += v.b.x * f.b; ay[1] += v.b.y * f.b;
+                    }
                 }
             }
         }
     }
-    const int prow = m.pos0[r] * W;
+    if constexpr (NATURAL) {
+        cx<T>* dst = s + r * W + e;
+        if constexpr (VEC == 4) {
+            // rotate which of its 4 columns a lane writes in each of the 4 store instructions by (lane>>2)&3:
+            // lanes l, l+4, l+8, l+12 (same bank group, columns 16 apart) then hit distinct banks
+            const int rot = (lane >> 2) & 3;
+            const bool p0 = rot & 1, p1 = rot & 2;
+            T bx[4], by[4], cxr[4], cyr[4];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) s[prow + m.pos1[e + i]] = mk<T>(ax[i] * scale, ay[i] * scale);
+            for (int i = 0; i < 4; ++i) { bx[i] = p0 ? ax[(i + 1) & 3] : ax[i]; by[i] = p0 ? ay[(i + 1) & 3] : ay[i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { cxr[i] = p1 ? bx[(i + 2) & 3] : bx[i]; cyr[i] = p1 ? by[(i + 2) & 3] : by[i]; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dst[(t + rot) & 3] = mk<T>(cxr[t] * scale, cyr[t] * scale);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dst[i] = mk<T>(ax[i] * scale, ay[i] * scale);
+        }
+    } else {
+        const int prow = m.pos0[r] * W;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s[prow + m.pos1[e + i]] = mk<T>(ax[i] * scale, ay[i] * scale);
+    }
 }
 
 template <typename T, int N0, int N1, int KT>
@@ -125,6 +170,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     const int n0 = ST ? N0 : a.n0, n1 = ST ? N1 : a.n1;
     const int W = ST ? (N1 | 1) : a.W;
     const int k = KT > 0 ? KT : a.k;
+    const int wp = a.o1p + 4;            // w1 pitch: 16-byte stores from consecutive rows hit distinct banks
     TileSmem<T> m;
     tile_smem_layout(a, &m);
     cx<T>* s = m.tile;
@@ -144,36 +190,34 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
         stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
         __syncthreads();
 
-        // 1. product + periodise into scrambled (DIT-input) order: 4 (or 2) adjacent columns per thread with
-        //    128-bit loads, two independent items per iteration, aliases outside the filter support skipped
+        // 1. product + periodise: 4 (or 2) adjacent columns per thread, 128-bit loads, aliases outside the
+        //    filter support skipped
         {
             const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
             const T* __restrict__ fb = a.filt[fi];
             const int P1 = a.P1;
             if ((n1 & 3) == 0 && (P1 & 3) == 0) {
                 const int per_row = n1 >> 2, items = n0 * per_row;
-                for (int it = tid; it < items; it += 2 * nt) {
+                for (int it = tid; it < items; it += nt) {
                     const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
-                    tile_load_item<T, 4, KT>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale);
-                    const int it1 = it + nt;
-                    if (it1 < items) {
-                        const int r1 = it1 / per_row, e1 = 4 * (it1 - r1 * per_row);
-                        tile_load_item<T, 4, KT>(s, m, pb, fb, r1, e1, k, n0, n1, W, P1, a.scale);
-                    }
+                    tile_load_item<T, 4, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
                 }
             } else {
                 const int per_row = n1 >> 1, items = n0 * per_row;
                 for (int it = tid; it < items; it += nt) {
                     const int r0 = it / per_row, e0 = 2 * (it - r0 * per_row);
-                    tile_load_item<T, 2, KT>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale);
+                    tile_load_item<T, 2, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
                 }
             }
         }
         __syncthreads();
-        // 2+3. inverse 2-D FFT -> natural-order spatial field, modulus applied in the registers of the last pass
+        // 2+3. inverse 2-D FFT and modulus.
+        //   static : DIF (natural Fourier in -> scrambled spatial out), modulus in the registers of the last pass;
+        //            the spatial field stays scrambled: U[y][x] lives at s[pos0[y]*W + pos1[x]]
+        //   generic: DIT (scattered input -> natural spatial), separate modulus sweep
         if constexpr (ST) {
-            slab_fft_s<N1, true, (N1 | 1), 1, T>(s, N0, m.tw1);
-            slab_fft_s<N0, true, 1, (N1 | 1), T, true>(s, N1, m.tw0);
+            slab_fft_s<N1, false, +1, (N1 | 1), 1, T>(s, N0, m.tw1);
+            slab_fft_s<N0, false, +1, 1, (N1 | 1), T, true>(s, N1, m.tw0);
         } else {
             slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
             slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
@@ -181,8 +225,8 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 for (int x = lane; x < n1; x += 32) s[y * W + x] = mk<T>(cabs_fast<T>(s[y * W + x]), T(0));
             __syncthreads();
         }
-        // 4a. horizontal low-pass + decimation + unpad: w1[y][xo] = sum_x U[y][x] * G1[x][xo]
-        //     register tile: 4 rows x 4 outputs per thread, x restricted to the group's input window
+        // 4a. horizontal low-pass + decimation + unpad: w1[row][xo] = sum_x U[row][x] * G1[x][xo]
+        //     register tile: 4 (storage) rows x 4 outputs per thread, x restricted to the group's input window
         {
             const int rgroups = (n0 + 3) >> 2, xgroups = a.o1p >> 2;
             for (int it = tid; it < rgroups * xgroups; it += nt) {
@@ -199,9 +243,10 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 if (x < 0) x += n1;
                 for (int st = 0; st < a.x1cnt; ++st) {
                     const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G1 + x * a.o1p + 4 * xg);
+                    const int xs = ST ? m.pos1[x] : x;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const T u = s[yy[j] + x].x;
+                        const T u = s[yy[j] + xs].x;
                         acc[j][0] += u * gq.a; acc[j][1] += u * gq.b; acc[j][2] += u * gq.c; acc[j][3] += u * gq.d;
                     }
                     x = (x + 1 == n1) ? 0 : x + 1;
@@ -211,14 +256,14 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                     const int y = rg + j * rgroups;
                     if (y < n0) {
                         re4<T> o; o.a = acc[j][0]; o.b = acc[j][1]; o.c = acc[j][2]; o.d = acc[j][3];
-                        *reinterpret_cast<re4<T>*>(m.w1 + y * a.o1p + 4 * xg) = o;
+                        *reinterpret_cast<re4<T>*>(m.w1 + y * wp + 4 * xg) = o;
                     }
                 }
             }
         }
         __syncthreads();
         // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
-        //     S[yo][xo] = sum_y G0[y][yo] * w1[y][xo]; 4 output rows per thread, lanes along xo
+        //     S[yo][xo] = sum_y G0[y][yo] * w1[row(y)][xo]; 4 output rows per thread, lanes along xo
         {
             T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
             const int ygroups = a.o0p >> 2;
@@ -229,7 +274,8 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 if (y < 0) y += n0;
                 for (int st = 0; st < a.y0cnt; ++st) {
                     const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G0 + y * a.o0p + 4 * yg);
-                    const T w = m.w1[y * a.o1p + xo];
+                    const int ys = ST ? m.pos0[y] : y;
+                    const T w = m.w1[ys * wp + xo];
                     acc0 += w * gq.a; acc1 += w * gq.b; acc2 += w * gq.c; acc3 += w * gq.d;
                     y = (y + 1 == n0) ? 0 : y + 1;
                 }
@@ -242,19 +288,26 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 }
             }
         }
-        // 5. forward 2-D FFT of U for the children of this path (natural-order store)
+        // 5. forward 2-D FFT of U for the children of this path, natural-order store
+        //    (static: DIT, scrambled spatial in -> natural Fourier out; generic: DIF + gather)
         if (a.spec_out) {
+            cx<T>* ob = a.spec_out + (size_t)g * n0 * n1;
             if constexpr (ST) {
-                slab_fft_s<N1, false, (N1 | 1), 1, T>(s, N0, m.tw1);
-                slab_fft_s<N0, false, 1, (N1 | 1), T>(s, N1, m.tw0);
+                slab_fft_s<N0, true, -1, 1, (N1 | 1), T>(s, N1, m.tw0);
+                slab_fft_s<N1, true, -1, (N1 | 1), 1, T>(s, N0, m.tw1);
+                constexpr int half = N1 / 2;
+                for (int it = tid; it < N0 * half; it += nt) {
+                    const int r = it / half, e = 2 * (it - r * half);
+                    cx2<T> v; v.a = s[r * W + e]; v.b = s[r * W + e + 1];
+                    *reinterpret_cast<cx2<T>*>(ob + (size_t)r * N1 + e) = v;
+                }
             } else {
                 slab_fft<false, T>(s, n0, W, 1, a.plan1, m.tw1);
                 slab_fft<false, T>(s, n1, 1, W, a.plan0, m.tw0);
-            }
-            cx<T>* ob = a.spec_out + (size_t)g * n0 * n1;
-            for (int r = warp; r < n0; r += nwarps) {
-                const int prow = m.pos0[r] * W;
-                for (int e = lane; e < n1; e += 32) ob[(size_t)r * n1 + e] = s[prow + m.pos1[e]];
+                for (int r = warp; r < n0; r += nwarps) {
+                    const int prow = m.pos0[r] * W;
+                    for (int e = lane; e < n1; e += 32) ob[(size_t)r * n1 + e] = s[prow + m.pos1[e]];
+                }
             }
         }
         __syncthreads();   // the next path rewrites the tile, the support rows and w1

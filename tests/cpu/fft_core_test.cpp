@@ -78,6 +78,61 @@ template <typename T> static double check(int n, int max_pow2, double tol, bool 
     return e;
 }
 
+// static (compile-time plan) butterflies: every (flow, sign) combination against the naive DFT
+template <int N, bool DIT, int SIGN, typename T> static void run_static(std::vector<cx<T>>& line, const std::vector<cx<T>>& tw) {
+    constexpr int NP = ct_plan1(N).npass;
+    static_for<0, NP>([&](auto pp_) {
+        constexpr int pp = decltype(pp_)::value;
+        constexpr int p = DIT ? NP - 1 - pp : pp;
+        constexpr int r = ct_plan1(N).radix[p], m = ct_plan1(N).blen[p];
+        constexpr int q = m / r, nbf = N / r, tws = N / m;
+        for (int bf = 0; bf < nbf; ++bf) {
+            const int blk = bf / q, i = bf - blk * q;
+            butterfly_s<r, DIT, SIGN, q, 1, false, T>(line.data() + blk * m + i, i * tws, tw.data());
+        }
+    });
+}
+template <int N> static int check_static() {
+    typedef float T;
+    Plan1 P = make_plan1(N);
+    auto tw = twiddle_table<T>(N);
+    auto pos = scramble_table(P);
+    std::vector<std::complex<long double>> x(N);
+    srand(77 + N);
+    for (int i = 0; i < N; ++i) x[i] = {(long double)rand() / RAND_MAX - 0.5L, (long double)rand() / RAND_MAX - 0.5L};
+    const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+    int bad = 0;
+    for (int sign = -1; sign <= 1; sign += 2) {
+        std::vector<std::complex<long double>> X(N);
+        for (int f = 0; f < N; ++f) {
+            std::complex<long double> acc = 0;
+            for (int t = 0; t < N; ++t) {
+                long double a = sign * tau * (long double)((long long)f * t % N) / N;
+                acc += x[t] * std::complex<long double>(cosl(a), sinl(a));
+            }
+            X[f] = acc;
+        }
+        // DIF: natural in -> scrambled out
+        std::vector<cx<T>> line(N);
+        for (int i = 0; i < N; ++i) line[i] = mk<T>((T)x[i].real(), (T)x[i].imag());
+        if (sign < 0) run_static<N, false, -1, T>(line, tw); else run_static<N, false, +1, T>(line, tw);
+        double e1 = 0, nrm = 0;
+        for (int f = 0; f < N; ++f) {
+            e1 = std::max(e1, (double)std::abs(std::complex<long double>(line[pos[f]].x, line[pos[f]].y) - X[f]));
+            nrm = std::max(nrm, (double)std::abs(X[f]));
+        }
+        // DIT: scrambled in -> natural out
+        for (int i = 0; i < N; ++i) line[pos[i]] = mk<T>((T)x[i].real(), (T)x[i].imag());
+        if (sign < 0) run_static<N, true, -1, T>(line, tw); else run_static<N, true, +1, T>(line, tw);
+        double e2 = 0;
+        for (int f = 0; f < N; ++f)
+            e2 = std::max(e2, (double)std::abs(std::complex<long double>(line[f].x, line[f].y) - X[f]));
+        printf("static N=%d sign=%+d DIF rel=%.3g DIT rel=%.3g\n", N, sign, e1 / nrm, e2 / nrm);
+        if (e1 / nrm > 2e-5 || e2 / nrm > 2e-5) ++bad;
+    }
+    return bad;
+}
+
 int main() {
     int sizes[] = {1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 16, 17, 18, 20, 24, 30, 32, 34, 36, 40, 48, 60, 64, 66, 68, 96,
                    120, 128, 136, 138, 240, 256, 272, 286, 290, 442, 512, 1016, 1024, 4096};
@@ -90,6 +145,8 @@ int main() {
         }
         if (check<double>(n, 16, 1e-12, true) > 1e-12) ++bad;
     }
+    bad += check_static<136>() + check_static<68>() + check_static<272>() + check_static<128>() +
+           check_static<240>() + check_static<34>();
     printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);
     return bad ? 1 : 0;
 }
