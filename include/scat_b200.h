@@ -75,6 +75,33 @@ size_t scat_plan2d_workspace_bytes(const scat_plan2d* plan, int64_t batch);
 int  scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, void* workspace_dev,
                          size_t workspace_bytes, int64_t batch, void* stream);
 
+/* eager primitives ----------------------------------------------------------------
+ * One entry point per backend primitive of kymatio/scattering2d/core/scattering2d.py:3-9, on
+ * contiguous device tensors in the torch backend's layout (real: trailing axis 1, complex: trailing
+ * axis 2).  Not used by the fused plan; they complete the backend protocol for the `torch_b200`
+ * backend object. */
+
+/* natural-order complex 2-D FFT on (G, n0, n1, 2): tables -> const_dev (caller-owned), then exec.
+ * replaces torch.fft.fft2 / ifft2 at kymatio/scattering2d/backend/torch_backend.py:10-12,134-155 */
+size_t scat_fft2d_const_bytes(int32_t n0, int32_t n1, int32_t dtype);
+int  scat_fft2d_init(void* const_dev, int32_t n0, int32_t n1, int32_t dtype, void* stream);
+int  scat_fft2d_exec(const void* const_dev, const void* in_dev, void* out_dev, int64_t G, int32_t n0, int32_t n1,
+                     int32_t inverse, int32_t dtype, void* stream);
+/* reflect padding, (B, M, N) real -> (B, M+top+bottom, N+left+right) real  (torch_backend.py:36-86) */
+int  scat_pad2d(const void* x_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
+                int32_t left, int32_t right, int32_t dtype, void* stream);
+/* out[b][i] = a[b][i] * b[i], a complex (batch, n), b real (n) or complex (n)  (backend/torch_backend.py:148-219) */
+int  scat_cdgmm(const void* a_dev, const void* b_dev, void* out_dev, int64_t batch, int64_t n, int32_t b_is_complex,
+                int32_t dtype, void* stream);
+/* Fourier-domain periodisation (G, n0, n1) -> (G, n0/k, n1/k)  (scattering2d/backend/torch_backend.py:93-129) */
+int  scat_subsample_fourier2d(const void* in_dev, void* out_dev, int64_t G, int32_t n0, int32_t n1, int32_t k,
+                              int32_t dtype, void* stream);
+/* |z| on n complex values  (backend/torch_backend.py:138-141) */
+int  scat_modulus(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
+/* real <-> complex views used by rfft / irfft  (scattering2d/backend/torch_backend.py:134-148) */
+int  scat_complex_from_real(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
+int  scat_real_part(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,18 @@ SIGNATURES = {
     "scat_plan2d_workspace_bytes": (_c.c_size_t, [_c.c_void_p, _c.c_int64]),
     "scat_plan2d_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t,
                                        _c.c_int64, _c.c_void_p]),
+    "scat_fft2d_const_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32, _c.c_int32]),
+    "scat_fft2d_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_fft2d_exec": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,
+                                   _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_pad2d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int32] * 7 + [_c.c_void_p]),
+    "scat_cdgmm": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int32,
+                              _c.c_int32, _c.c_void_p]),
+    "scat_subsample_fourier2d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,
+                                            _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_modulus": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_complex_from_real": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_real_part": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
 }
 
 

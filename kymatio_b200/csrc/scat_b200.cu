@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include "plan2d.cuh"
+#include "prims.cuh"
 
 using namespace sb;
 
@@ -89,6 +90,94 @@ int scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, voi
     return guarded([&] {
         if (!plan) throw std::runtime_error("null plan");
         plan->forward(x_dev, out_dev, workspace_dev, workspace_bytes, batch, static_cast<cudaStream_t>(stream));
+    });
+}
+
+// ---------------------------------------------------------------- eager primitives
+#define SB_DISPATCH(dtype, CALL)                                                     \
+    do {                                                                             \
+        if ((dtype) == 0) { typedef float T; CALL; }                                 \
+        else if ((dtype) == 1) { typedef double T; CALL; }                           \
+        else throw std::runtime_error("dtype must be 0 (float32) or 1 (float64)");   \
+    } while (0)
+
+size_t scat_fft2d_const_bytes(int32_t n0, int32_t n1, int32_t dtype) {
+    try {
+        return dtype == 1 ? Fft2dTables<double>(n0, n1).bytes : Fft2dTables<float>(n0, n1).bytes;
+    } catch (const std::exception& e) { last_error() = e.what(); return 0; }
+}
+int scat_fft2d_init(void* const_dev, int32_t n0, int32_t n1, int32_t dtype, void* stream) {
+    return guarded([&] { SB_DISPATCH(dtype, fft2d_init<T>(const_dev, n0, n1, static_cast<cudaStream_t>(stream))); });
+}
+int scat_fft2d_exec(const void* const_dev, const void* in_dev, void* out_dev, int64_t G, int32_t n0, int32_t n1,
+                    int32_t inverse, int32_t dtype, void* stream) {
+    return guarded([&] {
+        static bool enabled = false;
+        if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
+        SB_DISPATCH(dtype, fft2d_exec<T>(const_dev, in_dev, out_dev, G, n0, n1, inverse != 0, static_cast<cudaStream_t>(stream)));
+    });
+}
+int scat_pad2d(const void* x_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
+               int32_t left, int32_t right, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int P0 = M + top + bottom, P1 = N + left + right;
+        if (B <= 0) return;
+        dim3 grid(ceil_div(P1, 128), P0, (unsigned)B);
+        SB_DISPATCH(dtype, launch("prim_pad2d", (double)B * (M * N + P0 * P1) * sizeof(T), st, [&] {
+            kp_pad2d<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x_dev), static_cast<T*>(out_dev), M, N, top, left, P0, P1);
+        }));
+    });
+}
+int scat_cdgmm(const void* a_dev, const void* b_dev, void* out_dev, int64_t batch, int64_t n, int32_t b_is_complex,
+               int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const size_t total = (size_t)batch * n;
+        if (!total) return;
+        SB_DISPATCH(dtype, launch("prim_cdgmm", 2.0 * total * sizeof(cx<T>), st, [&] {
+            kp_cdgmm<T><<<blocks_for(total), 256, 0, st>>>(static_cast<const cx<T>*>(a_dev), static_cast<const T*>(b_dev),
+                                                          static_cast<cx<T>*>(out_dev), (size_t)n, total, b_is_complex);
+        }));
+    });
+}
+int scat_subsample_fourier2d(const void* in_dev, void* out_dev, int64_t G, int32_t n0, int32_t n1, int32_t k,
+                             int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (k < 1 || n0 % k || n1 % k) throw std::runtime_error("subsample_fourier: k must divide both sizes");
+        if (G <= 0) return;
+        dim3 grid(ceil_div(n1 / k, 128), n0 / k, (unsigned)G);
+        SB_DISPATCH(dtype, launch("prim_periodize2d", (double)G * n0 * n1 * sizeof(cx<T>), st, [&] {
+            kp_periodize2d<T><<<grid, 128, 0, st>>>(static_cast<const cx<T>*>(in_dev), static_cast<cx<T>*>(out_dev), n0, n1, k);
+        }));
+    });
+}
+int scat_modulus(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (n <= 0) return;
+        SB_DISPATCH(dtype, launch("prim_modulus", (double)n * 3 * sizeof(T), st, [&] {
+            kp_modulus<T><<<blocks_for((size_t)n), 256, 0, st>>>(static_cast<const cx<T>*>(in_dev), static_cast<T*>(out_dev), (size_t)n);
+        }));
+    });
+}
+int scat_complex_from_real(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (n <= 0) return;
+        SB_DISPATCH(dtype, launch("prim_from_real", (double)n * 3 * sizeof(T), st, [&] {
+            kp_from_real<T><<<blocks_for((size_t)n), 256, 0, st>>>(static_cast<const T*>(in_dev), static_cast<cx<T>*>(out_dev), (size_t)n);
+        }));
+    });
+}
+int scat_real_part(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (n <= 0) return;
+        SB_DISPATCH(dtype, launch("prim_real_part", (double)n * 3 * sizeof(T), st, [&] {
+            kp_real_scaled<T><<<blocks_for((size_t)n), 256, 0, st>>>(static_cast<const cx<T>*>(in_dev), static_cast<T*>(out_dev), (size_t)n, T(1));
+        }));
     });
 }
 

@@ -1,0 +1,329 @@
+"""Plug ``torch_b200`` into an installed, UNMODIFIED kymatio.
+
+    import kymatio_b200.kymatio_plugin as plugin
+    plugin.install()
+    from kymatio.torch import Scattering2D
+    S = Scattering2D(J=3, shape=(256, 256), backend='torch_b200').cuda()     # or backend=plugin.backend2d
+
+What ``install()`` does (no file of the reference is touched):
+  1. registers the module ``kymatio.scattering2d.backend.torch_b200_backend`` (attribute ``backend``)
+     in ``sys.modules`` so that the frontend's string route resolves it
+     (kymatio/frontend/base_frontend.py:37-42);
+  2. rebinds the name ``scattering2d`` that the torch frontend imported
+     (kymatio/scattering2d/frontend/torch_frontend.py:4,98-99) to a dispatcher which runs the whole core
+     as ONE call into libscat_b200.so when ``backend.name == 'torch_b200'`` and falls through to the
+     reference core for every other backend.
+
+``TorchB200Backend2D`` also implements every primitive of the backend protocol
+(kymatio/scattering2d/core/scattering2d.py:3-9) as its own CUDA kernel, with the reference's checks
+and error strings (kymatio/backend/torch_backend.py:102-219, kymatio/scattering2d/backend/
+torch_backend.py:19-180), so the unchanged core can also be driven primitive by primitive
+(``install(fused=False)``) and the reference's primitive tests can be pointed at it.  Like the
+reference's own GPU-only backend (torch_skcuda) the primitives are CUDA-only and not differentiable;
+gradients are provided by the fused path.
+"""
+import ctypes
+import importlib
+import sys
+import types
+
+import torch
+
+from . import _lib
+from .engine2d import Engine2D, _DTYPES
+
+NAME = "torch_b200"
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _cuda_check(x):
+    if not x.is_cuda:
+        raise TypeError("The torch_b200 backend needs CUDA tensors. Use the torch backend for CPU tensors.")
+
+
+def _dtype_code(x):
+    if x.dtype not in _DTYPES:
+        raise TypeError("torch_b200 supports float32 and float64 tensors.")
+    return _DTYPES[x.dtype]
+
+
+class _FftTables:
+    """Device-resident twiddle/permutation tables per (n0, n1, dtype, device) - torch tensors, so the
+    library itself never allocates."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, n0, n1, ref):
+        key = (n0, n1, ref.dtype, ref.device.index)
+        buf = cls._cache.get(key)
+        if buf is None:
+            lib = _lib.load()
+            code = _dtype_code(ref)
+            nbytes = lib.scat_fft2d_const_bytes(n0, n1, code)
+            if nbytes == 0:
+                raise _lib.ScatB200Error(lib.scat_last_error().decode())
+            with torch.cuda.device(ref.device):
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=ref.device)
+                _lib.check(lib.scat_fft2d_init(buf.data_ptr(), n0, n1, code, _stream(ref)))
+            cls._cache[key] = buf
+        return buf
+
+
+class Pad(object):
+    """kymatio/scattering2d/backend/torch_backend.py:19-86 (reflect padding + trailing real axis)."""
+
+    def __init__(self, pad_size, input_size):
+        self.pad_size = list(pad_size)
+        self.input_size = list(input_size)
+
+    def __call__(self, x):
+        _cuda_check(x)
+        batch_shape, (M, N) = x.shape[:-2], x.shape[-2:]
+        x = x.reshape((-1, M, N)).contiguous()
+        t, b, l, r = self.pad_size
+        out = torch.empty((x.shape[0], M + t + b, N + l + r), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_pad2d(x.data_ptr(), out.data_ptr(), x.shape[0], M, N, t, b, l, r,
+                                              _dtype_code(x), _stream(x)))
+        return out.reshape(batch_shape + out.shape[-2:] + (1,))
+
+
+class TorchB200Backend2D:
+    name = NAME
+    Pad = Pad
+
+    # -- checks (kymatio/backend/torch_backend.py:102-135) --------------------------------------------
+    @classmethod
+    def input_checks(cls, x):
+        if x is None:
+            raise TypeError("The input should be not empty.")
+        cls.contiguous_check(x)
+
+    @staticmethod
+    def contiguous_check(x):
+        if not x.is_contiguous():
+            raise RuntimeError("Tensors must be contiguous.")
+
+    @staticmethod
+    def _is_complex(x):
+        return x.shape[-1] == 2
+
+    @staticmethod
+    def _is_real(x):
+        return x.shape[-1] == 1
+
+    @classmethod
+    def complex_check(cls, x):
+        if not cls._is_complex(x):
+            raise TypeError("The input should be complex (i.e. last dimension is 2).")
+
+    @classmethod
+    def real_check(cls, x):
+        if not cls._is_real(x):
+            raise TypeError("The input should be real.")
+
+    @classmethod
+    def complex_contiguous_check(cls, x):
+        cls.complex_check(x)
+        cls.contiguous_check(x)
+
+    # -- primitives -------------------------------------------------------------------------------------
+    @classmethod
+    def modulus(cls, x):
+        cls.complex_contiguous_check(x)
+        _cuda_check(x)
+        out = torch.empty(x.shape[:-1] + (1,), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_modulus(x.data_ptr(), out.data_ptr(), out.numel(), _dtype_code(x), _stream(x)))
+        return out
+
+    @classmethod
+    def cdgmm(cls, A, B):
+        # kymatio/backend/torch_backend.py:181-219
+        if not cls._is_real(B):
+            cls.complex_contiguous_check(B)
+        else:
+            cls.contiguous_check(B)
+        cls.complex_contiguous_check(A)
+        if A.shape[-len(B.shape):-1] != B.shape[:-1]:
+            raise RuntimeError("The filters are not compatible for multiplication.")
+        if A.dtype is not B.dtype:
+            raise TypeError("Input and filter must be of the same dtype.")
+        if B.device.type == "cuda":
+            if A.device.type == "cuda":
+                if A.device.index != B.device.index:
+                    raise TypeError("Input and filter must be on the same GPU.")
+            else:
+                raise TypeError("Input must be on GPU.")
+        if B.device.type == "cpu":
+            if A.device.type == "cuda":
+                raise TypeError("Input must be on CPU.")
+            _cuda_check(A)
+        n = B.numel() // B.shape[-1]
+        out = torch.empty_like(A)
+        with torch.cuda.device(A.device):
+            _lib.check(_lib.load().scat_cdgmm(A.data_ptr(), B.data_ptr(), out.data_ptr(), A.numel() // 2 // n, n,
+                                              int(cls._is_complex(B)), _dtype_code(A), _stream(A)))
+        return out
+
+    @classmethod
+    def subsample_fourier(cls, x, k):
+        cls.contiguous_check(x)
+        cls.complex_check(x)
+        _cuda_check(x)
+        n0, n1 = x.shape[-3], x.shape[-2]
+        out = torch.empty(x.shape[:-3] + (n0 // k, n1 // k, 2), dtype=x.dtype, device=x.device)
+        G = x.numel() // (n0 * n1 * 2)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_subsample_fourier2d(x.data_ptr(), out.data_ptr(), G, n0, n1, int(k),
+                                                            _dtype_code(x), _stream(x)))
+        return out
+
+    @classmethod
+    def _fft(cls, x, inverse):
+        n0, n1 = x.shape[-3], x.shape[-2]
+        tables = _FftTables.get(n0, n1, x)
+        out = torch.empty_like(x)
+        G = x.numel() // (n0 * n1 * 2)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_fft2d_exec(tables.data_ptr(), x.data_ptr(), out.data_ptr(), G, n0, n1,
+                                                   int(inverse), _dtype_code(x), _stream(x)))
+        return out
+
+    @classmethod
+    def rfft(cls, x):
+        cls.contiguous_check(x)
+        cls.real_check(x)
+        _cuda_check(x)
+        xc = torch.empty(x.shape[:-1] + (2,), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_complex_from_real(x.data_ptr(), xc.data_ptr(), x.numel(), _dtype_code(x),
+                                                          _stream(x)))
+        return cls._fft(xc, False)
+
+    @classmethod
+    def ifft(cls, x):
+        cls.contiguous_check(x)
+        cls.complex_check(x)
+        _cuda_check(x)
+        return cls._fft(x, True)
+
+    @classmethod
+    def irfft(cls, x):
+        cls.contiguous_check(x)
+        cls.complex_check(x)
+        _cuda_check(x)
+        y = cls._fft(x, True)
+        out = torch.empty(x.shape[:-1] + (1,), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_real_part(y.data_ptr(), out.data_ptr(), out.numel(), _dtype_code(x), _stream(x)))
+        return out
+
+    @staticmethod
+    def unpad(in_):
+        # kymatio/scattering2d/backend/torch_backend.py:158-176
+        in_ = in_[..., 1:-1, 1:-1, :]
+        return in_.reshape(in_.shape[:-1])
+
+    @staticmethod
+    def stack(arrays):
+        return torch.stack(arrays, -3)
+
+    # generic helpers used by other frontends of the protocol (kymatio/backend/torch_backend.py:222-232)
+    @staticmethod
+    def reshape_input(x, signal_shape):
+        return x.reshape((-1, 1) + signal_shape)
+
+    @staticmethod
+    def reshape_output(S, batch_shape, n_kept_dims):
+        return S.reshape(batch_shape + S.shape[-n_kept_dims:])
+
+    @staticmethod
+    def shape(x):
+        return x.shape
+
+
+backend2d = TorchB200Backend2D
+backend = backend2d
+
+# ---------------------------------------------------------------------------------------------------
+# fused dispatch
+# ---------------------------------------------------------------------------------------------------
+_engines = {}
+_originals = {}
+
+
+def _fused_scattering2d(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type="array"):
+    """Same signature and return value as kymatio/scattering2d/core/scattering2d.py:1-88."""
+    from .autograd2d import scattering2d_apply
+    if not x.is_cuda:
+        raise TypeError("The torch_b200 backend needs CUDA tensors. Use the torch backend for CPU tensors.")
+    pre_pad = not isinstance(pad, Pad)            # the frontend installs a lambda when pre_pad=True
+    M, N = x.shape[-2:]
+    phi_levels = [lvl for lvl in phi["levels"]]
+    psi_levels = [lvl for p in psi for lvl in p["levels"]]
+    if phi_levels[0].dtype is not x.dtype:
+        raise TypeError("Input and filter must be of the same dtype.")
+    if phi_levels[0].device != x.device:
+        raise TypeError("Input and filter must be on the same GPU." if phi_levels[0].is_cuda else "Input must be on CPU.")
+    key = (M, N, J, L, max_order, pre_pad, x.dtype, x.device.index)
+    eng = _engines.get(key)
+    if eng is None:
+        eng = _engines[key] = Engine2D(M, N, J, L, max_order, pre_pad, x.dtype, x.device)
+    eng.bind(phi_levels, psi_levels)
+    S = scattering2d_apply(eng, x.reshape((-1, M, N)).contiguous())
+    if out_type == "array":
+        return S
+    out, ch = [], 0
+
+    def push(j, n, theta):
+        nonlocal ch
+        out.append({"coef": S[:, ch], "j": j, "n": n, "theta": theta})
+        ch += 1
+
+    push((), (), ())
+    for n1, p1 in enumerate(psi):
+        push((p1["j"],), (n1,), (p1["theta"],))
+    if max_order >= 2:
+        for n1, p1 in enumerate(psi):
+            for n2, p2 in enumerate(psi):
+                if p2["j"] > p1["j"]:
+                    push((p1["j"], p2["j"]), (n1, n2), (p1["theta"], p2["theta"]))
+    return out
+
+
+def install(fused=True):
+    """Register the backend module and (optionally) the fused core dispatcher. Idempotent."""
+    import kymatio.scattering2d.frontend.torch_frontend as tf2d   # the unmodified reference
+
+    mod_name = "kymatio.scattering2d.backend.torch_b200_backend"
+    if mod_name not in sys.modules:
+        mod = types.ModuleType(mod_name)
+        mod.backend = backend2d
+        mod.__doc__ = "torch_b200 backend (provided by kymatio_b200)"
+        sys.modules[mod_name] = mod
+        setattr(importlib.import_module("kymatio.scattering2d.backend"), "torch_b200_backend", mod)
+
+    if "scattering2d" not in _originals:
+        _originals["scattering2d"] = tf2d.scattering2d
+    reference_core = _originals["scattering2d"]
+
+    if fused:
+        def dispatch(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type="array"):
+            if getattr(backend_, "name", None) == NAME:
+                return _fused_scattering2d(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type)
+            return reference_core(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type)
+        dispatch.__wrapped__ = reference_core
+        tf2d.scattering2d = dispatch
+    else:
+        tf2d.scattering2d = reference_core
+    return backend2d
+
+
+def uninstall():
+    if "scattering2d" in _originals:
+        import kymatio.scattering2d.frontend.torch_frontend as tf2d
+        tf2d.scattering2d = _originals["scattering2d"]

@@ -31,3 +31,17 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def import_reference():
+    """Make the unmodified reference (pip --target install under baseline/_ref) importable, with the
+    scipy>=1.15 sph_harm shim.  Returns False when it is not available."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "kymatio")):
+        return False
+    import scipy.special
+    if not hasattr(scipy.special, "sph_harm"):
+        scipy.special.sph_harm = lambda m, n, az, pol: scipy.special.sph_harm_y(n, m, pol, az)
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    return True
