@@ -1,0 +1,100 @@
+"""Batch data-parallel sharding of the scattering transform over the GPUs of one box.
+
+The path shards naturally over the batch: every signal is independent (the reference core never
+mixes batch entries - all primitives act on trailing axes, kymatio/scattering2d/backend/
+torch_backend.py:118-127) and the only shared state is the read-only filter bank, replicated per
+rank.  One process per GPU (torchrun / torch.distributed); no collective on the compute path.  The
+only exchange is an optional all-gather of the coefficient blocks when the caller wants one tensor
+on every rank; its backward is the matching reduce-scatter.
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_bounds", "shard_batch", "gather_batch", "ShardedScattering"]
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced slice [lo, hi) of n items for `rank` (first n % world ranks get one more)."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(x, rank=None, world=None, group=None):
+    """This rank's slice of a batch that every rank holds in full (dim 0)."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(x.shape[0], rank, world)
+    return x[lo:hi]
+
+
+class _AllGatherBatch(torch.autograd.Function):
+    """all_gather along dim 0 with per-rank sizes from shard_bounds; backward = reduce-scatter (sum)."""
+
+    @staticmethod
+    def forward(ctx, x, total, group):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ctx.group, ctx.total = group, total
+        bounds = [shard_bounds(total, r, world) for r in range(world)]
+        assert x.shape[0] == bounds[rank][1] - bounds[rank][0], "local batch does not match shard_bounds"
+        out = x.new_empty((total,) + tuple(x.shape[1:]))
+        if total % world == 0:
+            dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        else:
+            # uneven shards: pad every block to the largest one, gather, then compact
+            maxn = max(hi - lo for lo, hi in bounds)
+            pad = x.new_zeros((maxn,) + tuple(x.shape[1:]))
+            pad[: x.shape[0]] = x
+            buf = x.new_empty((world * maxn,) + tuple(x.shape[1:]))
+            dist.all_gather_into_tensor(buf, pad, group=group)
+            for r, (lo, hi) in enumerate(bounds):
+                out[lo:hi] = buf[r * maxn: r * maxn + (hi - lo)]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        group, total = ctx.group, ctx.total
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        grad = grad.contiguous()
+        lo, hi = shard_bounds(total, rank, world)
+        backend = dist.get_backend(group)
+        if total % world == 0 and backend == "nccl":
+            out = grad.new_empty((hi - lo,) + tuple(grad.shape[1:]))
+            dist.reduce_scatter_tensor(out, grad, op=dist.ReduceOp.SUM, group=group)
+            return out, None, None
+        # gloo (CPU tests) / uneven shards: all-reduce then slice
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+        return grad[lo:hi].clone(), None, None
+
+
+def gather_batch(x_local, total=None, group=None):
+    """Differentiable all-gather of per-rank batch slices into the full (total, ...) tensor."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x_local
+    if total is None:
+        t = torch.tensor([x_local.shape[0]], device=x_local.device, dtype=torch.int64)
+        dist.all_reduce(t, group=group)
+        total = int(t.item())
+    return _AllGatherBatch.apply(x_local, total, group)
+
+
+class ShardedScattering(torch.nn.Module):
+    """Wrap a scattering module: each rank transforms its slice of the batch; `gather=True` returns the
+    full coefficient tensor on every rank (one all-gather), `gather=False` returns the local block."""
+
+    def __init__(self, scattering, gather=True, group=None, input_is_sharded=False):
+        super().__init__()
+        self.scattering, self.gather, self.group = scattering, gather, group
+        self.input_is_sharded = input_is_sharded
+
+    def forward(self, x):
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return self.scattering(x)
+        if self.input_is_sharded:
+            local, total = x, None
+        else:
+            local, total = shard_batch(x, group=self.group).contiguous(), x.shape[0]
+        y = self.scattering(local)
+        return gather_batch(y, total, self.group) if self.gather else y
