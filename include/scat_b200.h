@@ -102,6 +102,20 @@ int  scat_modulus(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, v
 int  scat_complex_from_real(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
 int  scat_real_part(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
 
+/* adjoints for the autograd graph ------------------------------------------------
+ * filter multiply with the filters broadcast over the batch: out[b][f][i] = a[b][i] * w[f][i] (w real);
+ * adjoint = 1 computes ga[b][i] = sum_f a[b][f][i] * w[f][i]  (backward of cdgmm, backend/torch_backend.py:205-206) */
+int  scat_cdgmm_bcast(const void* a_dev, const void* w_dev, void* out_dev, int64_t nb, int32_t nf, int64_t n,
+                      int32_t adjoint, int32_t dtype, void* stream);
+/* adjoint of subsample_fourier: replicate / k^2, (G, n0/k, n1/k) -> (G, n0, n1) */
+int  scat_subsample_fourier2d_bwd(const void* gout_dev, void* gin_dev, int64_t G, int32_t n0, int32_t n1, int32_t k,
+                                  int32_t dtype, void* stream);
+/* ModulusStable.backward (backend/torch_backend.py:64-96): gx = x g / |x|, 0 where |x| = 0 */
+int  scat_modulus_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t n, int32_t dtype, void* stream);
+/* adjoint of the reflect padding: fold-add (gx is zeroed first) */
+int  scat_pad2d_bwd(const void* gout_dev, void* gx_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
+                    int32_t left, int32_t right, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

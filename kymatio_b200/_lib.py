@@ -55,6 +55,12 @@ SIGNATURES = {
     "scat_modulus": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_complex_from_real": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_real_part": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_cdgmm_bcast": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int64,
+                                    _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_subsample_fourier2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,
+                                                _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_modulus_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_pad2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int32] * 7 + [_c.c_void_p]),
 }
 
 

@@ -84,6 +84,65 @@ template <typename T> __global__ void kp_scale(cx<T>* __restrict__ x, size_t n, 
     if (i < n) x[i] = scal(x[i], s);
 }
 
+// ---- adjoint / backward kernels ------------------------------------------------
+// broadcast filter multiply: out[b][f][i] = A[b][i] * W[f][i]   (W real), i < n
+template <typename T>
+__global__ void kp_cdgmm_bcast(const cx<T>* __restrict__ A, const T* __restrict__ W, cx<T>* __restrict__ out,
+                               size_t nb, int nf, size_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * n) return;
+    const size_t b = idx / n, i = idx - b * n;
+    const cx<T> a = A[idx];
+    for (int f = 0; f < nf; ++f) {
+        const T w = W[(size_t)f * n + i];
+        out[(b * nf + f) * n + i] = mk<T>(a.x * w, a.y * w);
+    }
+}
+// its adjoint w.r.t. A: gA[b][i] = sum_f g[b][f][i] * W[f][i]
+template <typename T>
+__global__ void kp_cdgmm_bcast_bwd(const cx<T>* __restrict__ g, const T* __restrict__ W, cx<T>* __restrict__ gA,
+                                   size_t nb, int nf, size_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * n) return;
+    const size_t b = idx / n, i = idx - b * n;
+    T ax = T(0), ay = T(0);
+    for (int f = 0; f < nf; ++f) {
+        const T w = W[(size_t)f * n + i];
+        const cx<T> v = g[(b * nf + f) * n + i];
+        ax += v.x * w; ay += v.y * w;
+    }
+    gA[idx] = mk<T>(ax, ay);
+}
+// adjoint of the Fourier periodisation: gin[g][u + a*m0][v + b*m1] = gout[g][u][v] / k^2
+template <typename T>
+__global__ void kp_periodize2d_bwd(const cx<T>* __restrict__ gout, cx<T>* __restrict__ gin, int n0, int n1, int k) {
+    const int m0 = n0 / k, m1 = n1 / k;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    const size_t g = blockIdx.z;
+    if (c >= n1) return;
+    const T s = T(1) / (T(k) * T(k));
+    gin[(g * n0 + r) * n1 + c] = scal(gout[(g * m0 + r % m0) * m1 + c % m1], s);
+}
+// modulus backward (kymatio/backend/torch_backend.py:85-96): gx = x * g / |x|, 0 where |x| = 0
+template <typename T>
+__global__ void kp_modulus_bwd(const cx<T>* __restrict__ x, const T* __restrict__ g, cx<T>* __restrict__ gx, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cx<T> v = x[i];
+    const T m = sqrt(v.x * v.x + v.y * v.y);
+    const T s = m > T(0) ? g[i] / m : T(0);
+    gx[i] = mk<T>(v.x * s, v.y * s);
+}
+// adjoint of reflect padding: fold-add every padded sample onto its source pixel
+template <typename T>
+__global__ void kp_pad2d_bwd(const T* __restrict__ gout, T* __restrict__ gx, int M, int N, int top, int left, int P0,
+                             int P1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    const size_t b = blockIdx.z;
+    if (c >= P1) return;
+    atomicAdd(&gx[(b * M + reflect_idx(r - top, M)) * N + reflect_idx(c - left, N)], gout[(b * P0 + r) * P1 + c]);
+}
+
 inline unsigned blocks_for(size_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
 
 // natural-order 2-D complex FFT tables: [tw0 | pos0 | tw1 | pos1]

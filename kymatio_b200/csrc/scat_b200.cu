@@ -181,4 +181,59 @@ int scat_real_part(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, 
     });
 }
 
+// ---- adjoints used by the autograd graph ------------------------------------------------------------
+int scat_cdgmm_bcast(const void* a_dev, const void* w_dev, void* out_dev, int64_t nb, int32_t nf, int64_t n,
+                     int32_t adjoint, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const size_t total = (size_t)nb * n;
+        if (!total) return;
+        SB_DISPATCH(dtype, launch(adjoint ? "prim_cdgmm_bcast_bwd" : "prim_cdgmm_bcast", (double)total * (nf + 1) * sizeof(cx<T>), st, [&] {
+            if (adjoint)
+                kp_cdgmm_bcast_bwd<T><<<blocks_for(total), 256, 0, st>>>(static_cast<const cx<T>*>(a_dev), static_cast<const T*>(w_dev),
+                                                                          static_cast<cx<T>*>(out_dev), (size_t)nb, nf, (size_t)n);
+            else
+                kp_cdgmm_bcast<T><<<blocks_for(total), 256, 0, st>>>(static_cast<const cx<T>*>(a_dev), static_cast<const T*>(w_dev),
+                                                                      static_cast<cx<T>*>(out_dev), (size_t)nb, nf, (size_t)n);
+        }));
+    });
+}
+int scat_subsample_fourier2d_bwd(const void* gout_dev, void* gin_dev, int64_t G, int32_t n0, int32_t n1, int32_t k,
+                                 int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (k < 1 || n0 % k || n1 % k) throw std::runtime_error("subsample_fourier: k must divide both sizes");
+        if (G <= 0) return;
+        dim3 grid(ceil_div(n1, 128), n0, (unsigned)G);
+        SB_DISPATCH(dtype, launch("prim_periodize2d_bwd", (double)G * n0 * n1 * sizeof(cx<T>), st, [&] {
+            kp_periodize2d_bwd<T><<<grid, 128, 0, st>>>(static_cast<const cx<T>*>(gout_dev), static_cast<cx<T>*>(gin_dev), n0, n1, k);
+        }));
+    });
+}
+int scat_modulus_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t n, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (n <= 0) return;
+        SB_DISPATCH(dtype, launch("prim_modulus_bwd", (double)n * 5 * sizeof(T), st, [&] {
+            kp_modulus_bwd<T><<<blocks_for((size_t)n), 256, 0, st>>>(static_cast<const cx<T>*>(x_dev), static_cast<const T*>(g_dev),
+                                                                      static_cast<cx<T>*>(gx_dev), (size_t)n);
+        }));
+    });
+}
+int scat_pad2d_bwd(const void* gout_dev, void* gx_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
+                   int32_t left, int32_t right, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int P0 = M + top + bottom, P1 = N + left + right;
+        if (B <= 0) return;
+        dim3 grid(ceil_div(P1, 128), P0, (unsigned)B);
+        SB_DISPATCH(dtype, {
+            SB_CUDA(cudaMemsetAsync(gx_dev, 0, (size_t)B * M * N * sizeof(T), st));
+            launch("prim_pad2d_bwd", (double)B * (M * N + P0 * P1) * sizeof(T), st, [&] {
+                kp_pad2d_bwd<T><<<grid, 128, 0, st>>>(static_cast<const T*>(gout_dev), static_cast<T*>(gx_dev), M, N, top, left, P0, P1);
+            });
+        });
+    });
+}
+
 }  // extern "C"

@@ -39,6 +39,8 @@ class Engine2D:
             self._const = torch.empty(self.lib.scat_plan2d_const_bytes(self._plan), dtype=torch.uint8,
                                       device=self.device)
         self._bound_key = None
+        self._filters = None
+        self.geometry = dict(M=int(M), N=int(N), J=int(J), L=int(L), max_order=int(max_order), pre_pad=bool(pre_pad))
 
     def __del__(self):
         plan, self._plan = getattr(self, "_plan", None), None
@@ -68,6 +70,7 @@ class Engine2D:
                 self._plan, self._const.data_ptr(), _ptr_array(phi_levels), len(phi_levels),
                 _ptr_array(psi_levels), len(psi_levels), ctypes.c_void_p(stream)))
         self._bound_key = key
+        self._filters = (list(phi_levels), list(psi_levels))
 
     # -- forward ---------------------------------------------------------------------
     def workspace(self, batch):
@@ -90,3 +93,38 @@ class Engine2D:
                 self._plan, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), B,
                 ctypes.c_void_p(stream)))
         return out
+
+    # -- backward --------------------------------------------------------------------
+    def backward(self, x, grad_out):
+        """Gradient of ``forward`` w.r.t. x: the cascade is recomputed on differentiable ops whose forward and
+        adjoint kernels are this library's own (ops2d.py) and back-propagated; processed in batch chunks to
+        bound the memory of the recomputed intermediates."""
+        from .ops2d import eager_scattering2d
+        g = self.geometry
+        phi, psi = self._filters
+        pads = None
+        if not g["pre_pad"]:
+            t, l = (self.Mp - g["M"]) // 2, (self.Np - g["N"]) // 2
+            pads = (t, self.Mp - g["M"] - t, l, self.Np - g["N"] - l)
+        per_img = self.K_paths_bytes()
+        chunk = max(1, min(x.shape[0], int((4 << 30) // max(1, per_img))))
+        gx = torch.empty_like(x)
+        for b0 in range(0, x.shape[0], chunk):
+            with torch.enable_grad():
+                xc = x[b0:b0 + chunk].detach().requires_grad_(True)
+                y = eager_scattering2d(xc, g["J"], g["L"], g["max_order"], pads, phi, psi)
+                gx[b0:b0 + chunk] = torch.autograd.grad(y, xc, grad_out[b0:b0 + chunk])[0]
+        return gx
+
+    def K_paths_bytes(self):
+        """Rough bytes of saved intermediates per image in the recomputed graph (complex fields per path)."""
+        g, esz = self.geometry, (4 if self.dtype == torch.float32 else 8)
+        J, L = g["J"], g["L"]
+        total = 0
+        for j1 in range(J):
+            n1 = (self.Mp >> j1) * (self.Np >> j1)
+            total += L * n1 * 2 * esz * 6
+            if g["max_order"] == 2:
+                for j2 in range(j1 + 1, J):
+                    total += L * L * ((self.Mp >> j1) * (self.Np >> j1) + 5 * (self.Mp >> j2) * (self.Np >> j2)) * 2 * esz
+        return total

@@ -1,0 +1,226 @@
+"""Differentiable building blocks over the library's own kernels, and the angle-batched eager cascade
+used to back-propagate through the fused forward (recomputed in ``backward``).
+
+Each ``torch.autograd.Function`` pairs a forward kernel with its hand-written adjoint (SURVEY
+Appendix B): FFT <-> the opposite FFT, filter multiply <-> filter multiply-accumulate over the filter
+axis, periodisation <-> replication / k^2, modulus <-> ``x g / |x|`` (0 at 0, the reference's
+``ModulusStable.backward``, kymatio/backend/torch_backend.py:85-96), reflect pad <-> fold-add.
+Complex tensors use the torch backend's layout (trailing axis of size 2); everything is contiguous.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .engine2d import _DTYPES
+
+
+def _st(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _code(t):
+    return _DTYPES[t.dtype]
+
+
+_tables = {}
+
+
+def _fft_tables(n0, n1, ref):
+    key = (n0, n1, ref.dtype, ref.device.index)
+    buf = _tables.get(key)
+    if buf is None:
+        lib = _lib.load()
+        nbytes = lib.scat_fft2d_const_bytes(n0, n1, _code(ref))
+        if nbytes == 0:
+            raise _lib.ScatB200Error(lib.scat_last_error().decode())
+        with torch.cuda.device(ref.device):
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=ref.device)
+            _lib.check(lib.scat_fft2d_init(buf.data_ptr(), n0, n1, _code(ref), _st(ref)))
+        _tables[key] = buf
+    return buf
+
+
+def _fft2_raw(x, inverse):
+    """x: (..., n0, n1, 2) contiguous -> same shape; unnormalised forward / (1/N) inverse."""
+    n0, n1 = x.shape[-3], x.shape[-2]
+    out = torch.empty_like(x)
+    G = x.numel() // (n0 * n1 * 2)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().scat_fft2d_exec(_fft_tables(n0, n1, x).data_ptr(), x.data_ptr(), out.data_ptr(), G,
+                                               n0, n1, int(inverse), _code(x), _st(x)))
+    return out
+
+
+class Fft2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inverse):
+        ctx.inverse = inverse
+        return _fft2_raw(x.contiguous(), inverse)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        N = g.shape[-3] * g.shape[-2]
+        if ctx.inverse:                      # y = (1/N) F^H x  ->  gx = (1/N) F g
+            return _fft2_raw(g, False) / N, None
+        return _fft2_raw(g, True) * N, None  # y = F x        ->  gx = F^H g = N ifft(g)
+
+
+class Modulus(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        out = torch.empty(x.shape[:-1], dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_modulus(x.data_ptr(), out.data_ptr(), out.numel(), _code(x), _st(x)))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_modulus_bwd(x.data_ptr(), g.data_ptr(), gx.data_ptr(), g.numel(), _code(x),
+                                                    _st(x)))
+        return gx
+
+
+class FilterBank(torch.autograd.Function):
+    """A: (nb, n0, n1, 2), W: (nf, n0, n1) real -> (nb, nf, n0, n1, 2)."""
+
+    @staticmethod
+    def forward(ctx, A, W):
+        A, W = A.contiguous(), W.contiguous()
+        nb, nf = A.shape[0], W.shape[0]
+        n = A.shape[1] * A.shape[2]
+        out = torch.empty((nb, nf) + tuple(A.shape[1:]), dtype=A.dtype, device=A.device)
+        with torch.cuda.device(A.device):
+            _lib.check(_lib.load().scat_cdgmm_bcast(A.data_ptr(), W.data_ptr(), out.data_ptr(), nb, nf, n, 0,
+                                                    _code(A), _st(A)))
+        ctx.save_for_backward(W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (W,) = ctx.saved_tensors
+        g = g.contiguous()
+        nb, nf = g.shape[0], g.shape[1]
+        n = g.shape[2] * g.shape[3]
+        gA = torch.empty((nb,) + tuple(g.shape[2:]), dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().scat_cdgmm_bcast(g.data_ptr(), W.data_ptr(), gA.data_ptr(), nb, nf, n, 1,
+                                                    _code(g), _st(g)))
+        return gA, None
+
+
+class Periodize(torch.autograd.Function):
+    """(G, n0, n1, 2) -> (G, n0/k, n1/k, 2): Fourier-domain subsampling by k."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        x = x.contiguous()
+        ctx.k, ctx.shape = k, x.shape
+        if k == 1:
+            return x
+        G, n0, n1 = x.shape[0], x.shape[1], x.shape[2]
+        out = torch.empty((G, n0 // k, n1 // k, 2), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_subsample_fourier2d(x.data_ptr(), out.data_ptr(), G, n0, n1, k, _code(x),
+                                                            _st(x)))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.k == 1:
+            return g, None
+        g = g.contiguous()
+        G, n0, n1, _ = ctx.shape
+        gin = torch.empty(ctx.shape, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().scat_subsample_fourier2d_bwd(g.data_ptr(), gin.data_ptr(), G, n0, n1, ctx.k,
+                                                                _code(g), _st(g)))
+        return gin, None
+
+
+class PadReflect(torch.autograd.Function):
+    """(B, M, N) -> (B, M+t+b, N+l+r) reflect padding."""
+
+    @staticmethod
+    def forward(ctx, x, pads):
+        x = x.contiguous()
+        t, b, l, r = pads
+        ctx.pads, ctx.shape = pads, x.shape
+        B, M, N = x.shape
+        out = torch.empty((B, M + t + b, N + l + r), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_pad2d(x.data_ptr(), out.data_ptr(), B, M, N, t, b, l, r, _code(x), _st(x)))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        t, b, l, r = ctx.pads
+        B, M, N = ctx.shape
+        gx = torch.empty(ctx.shape, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().scat_pad2d_bwd(g.data_ptr(), gx.data_ptr(), B, M, N, t, b, l, r, _code(g), _st(g)))
+        return gx, None
+
+
+def _to_complex(x):
+    return torch.stack([x, torch.zeros_like(x)], dim=-1)
+
+
+def _low(U, phi_level, k):
+    """unpad(Re ifft2(periodise_k(U * phi)))  - core/scattering2d.py:19-23.  U: (G, n0, n1, 2)."""
+    Z = Periodize.apply(FilterBank.apply(U, phi_level[None])[:, 0], k)
+    return Fft2.apply(Z, True)[..., 1:-1, 1:-1, 0]
+
+
+def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels):
+    """Angle-batched restatement of kymatio/scattering2d/core/scattering2d.py:14-86 on differentiable ops.
+
+    x: (B, M, N) CUDA; pads: (top, bottom, left, right) or None when pre-padded;
+    phi_levels: J tensors (n0, n1[, 1]); psi_levels: flattened in registration order.
+    Returns (B, K, M/2^J, N/2^J) in the reference's channel order.
+    """
+    B = x.shape[0]
+    phi = [p.reshape(p.shape[0], p.shape[1]) for p in phi_levels]
+    # psi[j][res] -> (L, n0, n1)
+    psi, n = [], 0
+    n_levels = [min(j + 1, max(J - 1, 1)) for j in range(J)]
+    for j in range(J):
+        per_theta = []
+        for _ in range(L):
+            per_theta.append([psi_levels[n + r].reshape(psi_levels[n + r].shape[0], psi_levels[n + r].shape[1])
+                              for r in range(n_levels[j])])
+            n += n_levels[j]
+        psi.append([torch.stack([per_theta[t][r] for t in range(L)]) for r in range(n_levels[j])])
+
+    xp = PadReflect.apply(x, tuple(pads)) if pads is not None else x
+    U0 = Fft2.apply(_to_complex(xp), False)
+    S0 = _low(U0, phi[0], 2 ** J)[:, None]
+    S1, S2 = [], []
+    for j1 in range(J):
+        V = FilterBank.apply(U0, psi[j1][0])
+        V = Periodize.apply(V.reshape((B * L,) + tuple(V.shape[2:])), 2 ** j1)
+        A = Modulus.apply(Fft2.apply(V, True))
+        U1 = Fft2.apply(_to_complex(A), False)
+        s1 = _low(U1, phi[j1], 2 ** (J - j1))
+        S1.append(s1.reshape((B, L) + tuple(s1.shape[1:])))
+        if max_order < 2 or j1 >= J - 1:
+            continue
+        per_j2 = []
+        for j2 in range(j1 + 1, J):
+            V2 = FilterBank.apply(U1, psi[j2][j1])
+            V2 = Periodize.apply(V2.reshape((B * L * L,) + tuple(V2.shape[2:])), 2 ** (j2 - j1))
+            A2 = Modulus.apply(Fft2.apply(V2, True))
+            U2 = Fft2.apply(_to_complex(A2), False)
+            s2 = _low(U2, phi[j2], 2 ** (J - j2))
+            per_j2.append(s2.reshape((B, L, 1, L) + tuple(s2.shape[1:])))
+        s2 = torch.cat(per_j2, dim=2)                       # (B, theta1, j2, theta2, o0, o1)
+        S2.append(s2.reshape((B, -1) + tuple(s2.shape[4:])))
+    return torch.cat([S0] + S1 + S2, dim=1)
