@@ -98,6 +98,9 @@ __device__ __forceinline__ int wrap(int t, int n) {   // t in (-n, 2n)
 // ===================================================================================
 constexpr int kSLines = 16;           // lines per CTA in the static variants
 constexpr int kSLP = kSLines | 1;     // odd shared-memory pitch
+// launch bounds of the slab kernels: static instances run 16 lines x <= 18 butterflies (<= 288 threads)
+// and are compiled for three CTAs per SM (<= 75 registers); generic ones may use up to kMaxThreads
+#define SB_SLAB_BOUNDS(NS) __launch_bounds__((NS) > 0 ? 288 : kMaxThreads, (NS) > 0 ? 3 : 1)
 
 template <typename T> struct alignas(2 * sizeof(cx<T>)) cxpair { cx<T> a, b; };
 template <typename T> struct alignas(2 * sizeof(T)) repair { T a, b; };
@@ -116,7 +119,7 @@ template <typename T> struct PadRowArgs {
     Plan1 plan; const cx<T>* tw; const int* pos;
 };
 // grid (B, ceil(P0/lines)); reflect-pad rows on the fly, forward DIF along rows, natural-order store.
-template <typename T, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_pad_rowfft(PadRowArgs<T> a) {
+template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_pad_rowfft(PadRowArgs<T> a) {
     const int P1 = NS ? NS : a.P1, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)P1 * LP;
@@ -153,7 +156,7 @@ template <typename T> struct ColArgs {
 //   COL_FWD          spatial rows in  -> forward DIF along columns -> Fourier rows out
 //   COL_INV          Fourier rows in  -> inverse DIT along columns -> spatial rows out
 //   COL_INV_MOD_FWD  Fourier rows in  -> inverse DIT, modulus, forward DIF -> Fourier rows out
-template <typename T, int MODE, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_colpass(ColArgs<T> a) {
+template <typename T, int MODE, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_colpass(ColArgs<T> a) {
     const int n0 = NS ? NS : a.n0, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)n0 * LP;
@@ -231,7 +234,7 @@ template <typename T> struct RowProdArgs {
 };
 // grid (G = Bp*NF, ceil(n0/lines)).  rows of out = inverse DIT along the row of
 //   V[r][e] = scale * sum_{c,d<k} parent[r+c*n0][e+d*n1] * filt[r+c*n0][e+d*n1]
-template <typename T, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass_prod(RowProdArgs<T> a) {
+template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_rowpass_prod(RowProdArgs<T> a) {
     const int n1 = NS ? NS : a.n1, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)n1 * LP;
@@ -315,7 +318,7 @@ template <typename T> struct RowArgs {
     Plan1 plan; const cx<T>* tw; const int* pos;
 };
 // INV=false: spatial row in -> DIF -> Fourier row out; INV=true: Fourier row in -> DIT -> spatial row out
-template <typename T, bool INV, int NS> __global__ void __launch_bounds__(kMaxThreads) k2d_rowpass(RowArgs<T> a) {
+template <typename T, bool INV, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_rowpass(RowArgs<T> a) {
     const int n1 = NS ? NS : a.n1, LP = NS ? kSLP : a.LP, lines = NS ? kSLines : a.lines;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)n1 * LP;

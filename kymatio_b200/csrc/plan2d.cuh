@@ -448,14 +448,28 @@ private:
         a.G = G;
         bool is_static = false;
         TileKernel<T> kern = tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
-        // threads: a field that runs alone on its SM takes every thread its instance allows; smaller
-        // fields use about one thread per 4 butterflies of the widest pass
-        int maxbf = 1;
-        for (int p = 0; p < a.plan1.npass; ++p) maxbf = std::max(maxbf, a.n1 / a.plan1.radix[p]);
-        const int items = a.n0 * maxbf;
+        // threads: every butterfly pass distributes (lines x butterflies) work items over the CTA in rounds;
+        // pick the warp count that wastes the fewest (cost-weighted) partially filled rounds
         const int cap = std::min(tile_threads_cap_, is_static ? tile_max_threads(a.n0, a.n1) : tile_max_threads(0, 0));
-        int threads = (2 * smem > kMaxDynSmem) ? cap : std::min(cap, std::max(96, (items / 4 + 31) / 32 * 32));
-        threads = threads / 32 * 32;
+        const int lo = (2 * smem > kMaxDynSmem) ? std::max(64, cap / 2) : std::max(64, cap / 3);
+        auto pass_cost = [](int r) { return r >= 16 ? 30.0 * r : r >= 8 ? 15.0 * r : 12.0 * r; };
+        int threads = cap / 32 * 32;
+        double best = 1e300;
+        for (int t = cap / 32 * 32; t >= lo; t -= 32) {
+            double cost = 0;
+            for (int ax = 0; ax < 2; ++ax) {
+                const Plan1& P = ax ? a.plan0 : a.plan1;
+                const int lines = ax ? a.n1 : a.n0;
+                for (int p = 0; p < P.npass; ++p) {
+                    const int items = lines * (P.n / P.radix[p]);
+                    cost += (double)((items + t - 1) / t) * pass_cost(P.radix[p]);
+                }
+            }
+            cost *= (spec_out ? 2.0 : 1.0);
+            cost += (double)((a.n0 * a.n1 / 4 + t - 1) / t) * 60.0;      // product/periodise items
+            // normalise per thread-slot: fewer threads finishing in the same number of rounds is not better
+            if (cost < best - 1e-9) { best = cost; threads = t; }
+        }
         dim3 block(32, threads / 32);
         // persistent grid: as many CTAs as fit on the device at once
         int occ = 0;

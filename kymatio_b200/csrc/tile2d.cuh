@@ -66,10 +66,10 @@ __device__ __forceinline__ float fast_abs(float x, float y) {
 __device__ __forceinline__ double fast_abs(double x, double y) { return sqrt(x * x + y * y); }
 
 // threads per CTA / CTAs per SM the instances are compiled for: a field that fills more than half of
-// the SM's shared memory runs alone with up to 576 threads (<= 112 registers); smaller fields share
-// the SM three at a time with up to 288 threads each (<= 75 registers).
+// the SM's shared memory runs alone with up to 640 threads (<= 102 registers); smaller fields share
+// the SM three at a time with up to 320 threads each (<= 68 registers).
 __host__ __device__ constexpr bool tile_is_big(int n0, int n1) { return n0 == 0 || (long long)n0 * n1 > 10000; }
-__host__ __device__ constexpr int tile_max_threads(int n0, int n1) { return tile_is_big(n0, n1) ? 576 : 288; }
+__host__ __device__ constexpr int tile_max_threads(int n0, int n1) { return tile_is_big(n0, n1) ? 640 : 320; }
 __host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_is_big(n0, n1) ? 1 : 3; }
 
 // product + periodise for VEC adjacent columns starting at column e of output row r.
