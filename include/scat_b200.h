@@ -102,6 +102,20 @@ int  scat_modulus(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, v
 int  scat_complex_from_real(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
 int  scat_real_part(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
 
+/* 1-D primitives (kymatio/scattering1d/backend/torch_backend.py:19-141) --------------------------------
+ * natural-order complex FFT of any length N = Na*Nb on (G, N, 2) via the four-step algorithm (column pass,
+ * twiddle, row pass, transposed store); tmp_dev is a caller-owned scratch of the input's size. */
+size_t scat_fft1d_const_bytes(int32_t N, int32_t dtype);
+int  scat_fft1d_init(void* const_dev, int32_t N, int32_t dtype, void* stream);
+int  scat_fft1d_exec(const void* const_dev, const void* in_dev, void* tmp_dev, void* out_dev, int64_t G, int32_t N,
+                     int32_t inverse, int32_t dtype, void* stream);
+/* reflect padding along time, (G, N) -> (G, N + pad_left + pad_right)  (torch_backend.py:51-82) */
+int  scat_pad1d(const void* x_dev, void* out_dev, int64_t G, int32_t N, int32_t pad_left, int32_t pad_right,
+                int32_t dtype, void* stream);
+/* Fourier periodisation (G, N) -> (G, N/k)  (torch_backend.py:19-48; CUDA: torch_skcuda_backend.py:133-164) */
+int  scat_subsample_fourier1d(const void* in_dev, void* out_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
+                              void* stream);
+
 /* adjoints for the autograd graph ------------------------------------------------
  * filter multiply with the filters broadcast over the batch: out[b][f][i] = a[b][i] * w[f][i] (w real);
  * adjoint = 1 computes ga[b][i] = sum_f a[b][f][i] * w[f][i]  (backward of cdgmm, backend/torch_backend.py:205-206) */

@@ -55,6 +55,14 @@ SIGNATURES = {
     "scat_modulus": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_complex_from_real": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_real_part": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_fft1d_const_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32]),
+    "scat_fft1d_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_fft1d_exec": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32,
+                                   _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_pad1d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32,
+                              _c.c_void_p]),
+    "scat_subsample_fourier1d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,
+                                            _c.c_void_p]),
     "scat_cdgmm_bcast": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int64,
                                     _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_subsample_fourier2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,

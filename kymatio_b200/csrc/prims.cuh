@@ -202,4 +202,124 @@ void fft2d_exec(const void* const_dev, const void* in, void* out, int64_t G, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 1-D primitives (kymatio/scattering1d/backend/torch_backend.py)
+// ---------------------------------------------------------------------------------------------------
+// reflect pad along the last axis, (G, N) -> (G, N + pl + pr)   (torch_backend.py:51-82)
+template <typename T>
+__global__ void kp_pad1d(const T* __restrict__ x, T* __restrict__ out, int N, int pl, int P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = blockIdx.y;
+    if (c < P) out[g * P + c] = x[g * N + reflect_idx(c - pl, N)];
+}
+
+// Second half of the four-step 1-D FFT of length N = Na * Nb (first half: column transform of the
+// [Na][Nb] view): multiply row ka by w_N^{-+ ka*jb}, transform along jb, store X[ka + Na*kb].
+template <typename T> struct RowTwArgs {
+    const cx<T>* in; cx<T>* out;
+    int Na, Nb;
+    int lines, LP;
+    T scale;
+    Plan1 plan; const cx<T>* tw; const int* pos;
+};
+__device__ __forceinline__ void sincos2pi(float t, float* s, float* c) { sincospif(2.0f * t, s, c); }
+__device__ __forceinline__ void sincos2pi(double t, double* s, double* c) { sincospi(2.0 * t, s, c); }
+
+template <typename T, bool INV> __global__ void __launch_bounds__(kMaxThreads) k1d_rowpass_tw(RowTwArgs<T> a) {
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* tw = s + (size_t)a.Nb * a.LP;
+    int* pos = reinterpret_cast<int*>(tw + a.Nb);
+    const size_t g = blockIdx.x;
+    const int r0 = blockIdx.y * a.lines;
+    const int nl = min(a.lines, a.Na - r0);
+    const size_t N = (size_t)a.Na * a.Nb;
+    stage(tw, a.tw, a.Nb);
+    stage(pos, a.pos, a.Nb);
+    __syncthreads();
+    const cx<T>* ib = a.in + g * N + (size_t)r0 * a.Nb;
+    for (int idx = flat_tid(); idx < nl * a.Nb; idx += flat_nt()) {
+        const int l = idx / a.Nb, e = idx - l * a.Nb;
+        cx<T> v = ib[(size_t)l * a.Nb + e];
+        T sn, cs;
+        sincos2pi(T((long long)(r0 + l) * e) / T(N), &sn, &cs);
+        v = INV ? cmul(v, mk<T>(cs, sn)) : cmul(v, mk<T>(cs, -sn));
+        s[(INV ? pos[e] : e) * a.LP + l] = scal(v, a.scale);
+    }
+    __syncthreads();
+    slab_fft<INV, T>(s, nl, 1, a.LP, a.plan, tw);
+    cx<T>* ob = a.out + g * N + r0;
+    for (int idx = flat_tid(); idx < nl * a.Nb; idx += flat_nt()) {
+        const int e = idx / nl, l = idx - e * nl;
+        ob[(size_t)e * a.Na + l] = s[(INV ? e : pos[e]) * a.LP + l];
+    }
+}
+
+// tables: [twA | posA | twB | posB] for N = Na * Nb (balanced power-of-two or general split)
+template <typename T> struct Fft1dTables {
+    int Na, Nb;
+    Plan1 pa, pb;
+    size_t twa, posa, twb, posb, bytes;
+    explicit Fft1dTables(int N) {
+        // Na = largest divisor of N not above sqrt(N) (1 for primes); both halves must fit a slab line
+        Na = 1;
+        for (int d = 1; (long long)d * d <= N; ++d) if (N % d == 0) Na = d;
+        Nb = N / Na;
+        pa = make_plan1(Na); pb = make_plan1(Nb);
+        size_t off = 0;
+        auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+        twa = take((size_t)Na * sizeof(cx<T>)); posa = take((size_t)Na * sizeof(int));
+        twb = take((size_t)Nb * sizeof(cx<T>)); posb = take((size_t)Nb * sizeof(int));
+        bytes = off;
+    }
+};
+template <typename T> void fft1d_init(void* const_dev, int N, cudaStream_t st) {
+    Fft1dTables<T> t(N);
+    std::vector<unsigned char> h(t.bytes, 0);
+    auto twa = twiddle_table<T>(t.Na); auto twb = twiddle_table<T>(t.Nb);
+    auto pa = scramble_table(t.pa); auto pb = scramble_table(t.pb);
+    memcpy(h.data() + t.twa, twa.data(), (size_t)t.Na * sizeof(cx<T>));
+    if (t.Na > 1) memcpy(h.data() + t.posa, pa.data(), (size_t)t.Na * sizeof(int));
+    memcpy(h.data() + t.twb, twb.data(), (size_t)t.Nb * sizeof(cx<T>));
+    if (t.Nb > 1) memcpy(h.data() + t.posb, pb.data(), (size_t)t.Nb * sizeof(int));
+    SB_CUDA(cudaMemcpyAsync(const_dev, h.data(), t.bytes, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+// in, tmp, out: (G, N) complex; natural order both sides; inverse is 1/N-normalised
+// (torch.fft.fft / ifft, kymatio/scattering1d/backend/torch_backend.py:8-10)
+template <typename T>
+void fft1d_exec(const void* const_dev, const void* in, void* tmp, void* out, int64_t G, int N, bool inverse,
+                cudaStream_t st) {
+    static bool enabled = false;
+    if (!enabled) {
+        enable_big_smem(k1d_rowpass_tw<float, false>); enable_big_smem(k1d_rowpass_tw<float, true>);
+        enable_big_smem(k1d_rowpass_tw<double, false>); enable_big_smem(k1d_rowpass_tw<double, true>);
+        enabled = true;
+    }
+    Fft1dTables<T> t(N);
+    const unsigned char* cb = static_cast<const unsigned char*>(const_dev);
+    const cx<T>* src = static_cast<const cx<T>*>(in);
+    if (t.Na > 1) {
+        const SlabCfg cc = slab_cfg(t.pa, t.Nb, sizeof(cx<T>), sizeof(int));
+        const StreamKernels<T> kc = stream_kernels_lookup<T>(t.Na, false);
+        ColArgs<T> ca{};
+        ca.in = src; ca.out = static_cast<cx<T>*>(tmp); ca.n0 = t.Na; ca.n1 = t.Nb;
+        ca.lines = cc.lines; ca.LP = cc.LP; ca.plan = t.pa;
+        ca.tw = reinterpret_cast<const cx<T>*>(cb + t.twa); ca.pos = reinterpret_cast<const int*>(cb + t.posa);
+        dim3 gc((unsigned)G, ceil_div(t.Nb, cc.lines));
+        launch(inverse ? "prim1d_colpass_inv" : "prim1d_colpass_fwd", 2.0 * G * N * sizeof(cx<T>), st,
+               [&] { (inverse ? kc.col_inv : kc.col_fwd)<<<gc, cc.block, cc.smem, st>>>(ca); });
+        src = static_cast<const cx<T>*>(tmp);
+    }
+    const SlabCfg rc = slab_cfg(t.pb, t.Na, sizeof(cx<T>), sizeof(int));
+    RowTwArgs<T> ra{};
+    ra.in = src; ra.out = static_cast<cx<T>*>(out); ra.Na = t.Na; ra.Nb = t.Nb;
+    ra.lines = rc.lines; ra.LP = rc.LP; ra.scale = inverse ? T(1) / T(N) : T(1); ra.plan = t.pb;
+    ra.tw = reinterpret_cast<const cx<T>*>(cb + t.twb); ra.pos = reinterpret_cast<const int*>(cb + t.posb);
+    dim3 gr((unsigned)G, ceil_div(t.Na, rc.lines));
+    launch(inverse ? "prim1d_rowpass_tw_inv" : "prim1d_rowpass_tw_fwd", 2.0 * G * N * sizeof(cx<T>), st, [&] {
+        if (inverse) k1d_rowpass_tw<T, true><<<gr, rc.block, rc.smem, st>>>(ra);
+        else k1d_rowpass_tw<T, false><<<gr, rc.block, rc.smem, st>>>(ra);
+    });
+}
+
 }  // namespace sb

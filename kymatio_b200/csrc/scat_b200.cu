@@ -181,6 +181,49 @@ int scat_real_part(const void* in_dev, void* out_dev, int64_t n, int32_t dtype, 
     });
 }
 
+// ---- 1-D primitives -----------------------------------------------------------------------------------
+size_t scat_fft1d_const_bytes(int32_t N, int32_t dtype) {
+    try {
+        return dtype == 1 ? Fft1dTables<double>(N).bytes : Fft1dTables<float>(N).bytes;
+    } catch (const std::exception& e) { last_error() = e.what(); return 0; }
+}
+int scat_fft1d_init(void* const_dev, int32_t N, int32_t dtype, void* stream) {
+    return guarded([&] { SB_DISPATCH(dtype, fft1d_init<T>(const_dev, N, static_cast<cudaStream_t>(stream))); });
+}
+int scat_fft1d_exec(const void* const_dev, const void* in_dev, void* tmp_dev, void* out_dev, int64_t G, int32_t N,
+                    int32_t inverse, int32_t dtype, void* stream) {
+    return guarded([&] {
+        static bool enabled = false;
+        if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
+        if (G <= 0) return;
+        SB_DISPATCH(dtype, fft1d_exec<T>(const_dev, in_dev, tmp_dev, out_dev, G, N, inverse != 0, static_cast<cudaStream_t>(stream)));
+    });
+}
+int scat_pad1d(const void* x_dev, void* out_dev, int64_t G, int32_t N, int32_t pad_left, int32_t pad_right,
+               int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int P = N + pad_left + pad_right;
+        if (G <= 0) return;
+        dim3 grid(ceil_div(P, 256), (unsigned)G);
+        SB_DISPATCH(dtype, launch("prim_pad1d", (double)G * (N + P) * sizeof(T), st, [&] {
+            kp_pad1d<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x_dev), static_cast<T*>(out_dev), N, pad_left, P);
+        }));
+    });
+}
+int scat_subsample_fourier1d(const void* in_dev, void* out_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
+                             void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (k < 1 || N % k) throw std::runtime_error("subsample_fourier: k must divide the length");
+        if (G <= 0) return;
+        dim3 grid(ceil_div(N / k, 256), (unsigned)G);
+        SB_DISPATCH(dtype, launch("prim_periodize1d", (double)G * N * sizeof(cx<T>), st, [&] {
+            kp_periodize1d<T><<<grid, 256, 0, st>>>(static_cast<const cx<T>*>(in_dev), static_cast<cx<T>*>(out_dev), N, k);
+        }));
+    });
+}
+
 // ---- adjoints used by the autograd graph ------------------------------------------------------------
 int scat_cdgmm_bcast(const void* a_dev, const void* w_dev, void* out_dev, int64_t nb, int32_t nf, int64_t n,
                      int32_t adjoint, int32_t dtype, void* stream) {

@@ -249,6 +249,115 @@ class TorchB200Backend2D:
 backend2d = TorchB200Backend2D
 backend = backend2d
 
+
+# ---------------------------------------------------------------------------------------------------
+# 1-D backend (kymatio/scattering1d/backend/torch_backend.py) - eager primitives
+# ---------------------------------------------------------------------------------------------------
+class _Fft1dTables:
+    _cache = {}
+
+    @classmethod
+    def get(cls, n, ref):
+        key = (n, ref.dtype, ref.device.index)
+        buf = cls._cache.get(key)
+        if buf is None:
+            lib = _lib.load()
+            code = _dtype_code(ref)
+            nbytes = lib.scat_fft1d_const_bytes(n, code)
+            if nbytes == 0:
+                raise _lib.ScatB200Error(lib.scat_last_error().decode())
+            with torch.cuda.device(ref.device):
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=ref.device)
+                _lib.check(lib.scat_fft1d_init(buf.data_ptr(), n, code, _stream(ref)))
+            cls._cache[key] = buf
+        return buf
+
+
+class TorchB200Backend1D(TorchB200Backend2D):
+    """Same generic primitives (checks, modulus, cdgmm) plus the 1-D specific ones."""
+    Pad = None
+
+    @classmethod
+    def subsample_fourier(cls, x, k):
+        # kymatio/scattering1d/backend/torch_backend.py:19-48
+        cls.complex_check(x)
+        _cuda_check(x)
+        x = x.contiguous()
+        N = x.shape[-2]
+        out = torch.empty(x.shape[:-2] + (N // k, 2), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_subsample_fourier1d(x.data_ptr(), out.data_ptr(), x.numel() // (2 * N), N,
+                                                            int(k), _dtype_code(x), _stream(x)))
+        return out
+
+    @staticmethod
+    def pad(x, pad_left, pad_right, mode="reflect"):
+        # torch_backend.py:51-82 (only the reflect mode is used by the scattering frontends)
+        if mode != "reflect":
+            raise ValueError("torch_b200 implements reflect padding only.")
+        if (pad_left >= x.shape[-1]) or (pad_right >= x.shape[-1]):
+            raise ValueError("Indefinite padding size (larger than tensor).")
+        _cuda_check(x)
+        x = x.contiguous()
+        N = x.shape[-1]
+        out = torch.empty(x.shape[:-1] + (N + pad_left + pad_right,), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_pad1d(x.data_ptr(), out.data_ptr(), x.numel() // N, N, int(pad_left),
+                                              int(pad_right), _dtype_code(x), _stream(x)))
+        return out[..., None]
+
+    @staticmethod
+    def unpad(x, i0, i1):
+        x = x.reshape(x.shape[:-1])
+        return x[..., i0:i1]
+
+    @classmethod
+    def _fft(cls, x, inverse):
+        N = x.shape[-2]
+        tables = _Fft1dTables.get(N, x)
+        out, tmp = torch.empty_like(x), torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_fft1d_exec(tables.data_ptr(), x.data_ptr(), tmp.data_ptr(), out.data_ptr(),
+                                                   x.numel() // (2 * N), N, int(inverse), _dtype_code(x), _stream(x)))
+        return out
+
+    @classmethod
+    def cfft(cls, x):
+        cls.contiguous_check(x)
+        cls.complex_check(x)
+        _cuda_check(x)
+        return cls._fft(x, False)
+
+    @classmethod
+    def average_global(cls, x):
+        cls.contiguous_check(x)
+        cls.real_check(x)
+        return torch.sum(x, axis=-2, keepdims=True)
+
+    @staticmethod
+    def stack(arrays, dim=2):
+        return torch.stack(arrays, dim=dim)
+
+    # joint time-frequency helpers are pure reshapes in the reference (torch_backend.py:151-223)
+    @classmethod
+    def pad_frequency(cls, x, padding):
+        return torch.nn.functional.pad(x, (0, 0, 0, padding), mode="constant", value=0)
+
+    @classmethod
+    def swap_time_frequency(cls, x):
+        return torch.transpose(x, dim0=-2, dim1=-3).contiguous()
+
+    @staticmethod
+    def unpad_frequency(x, n1_max, n1_stride):
+        return x[:, :, :1 + (n1_max // n1_stride), :]
+
+    @staticmethod
+    def split_frequency_axis(x):
+        return torch.split(x, 1, dim=-3)
+
+
+backend1d = TorchB200Backend1D
+
 # ---------------------------------------------------------------------------------------------------
 # fused dispatch
 # ---------------------------------------------------------------------------------------------------
@@ -306,6 +415,14 @@ def install(fused=True):
         mod.__doc__ = "torch_b200 backend (provided by kymatio_b200)"
         sys.modules[mod_name] = mod
         setattr(importlib.import_module("kymatio.scattering2d.backend"), "torch_b200_backend", mod)
+
+    mod1 = "kymatio.scattering1d.backend.torch_b200_backend"
+    if mod1 not in sys.modules:
+        m1 = types.ModuleType(mod1)
+        m1.backend = backend1d
+        m1.__doc__ = "torch_b200 1-D backend (provided by kymatio_b200)"
+        sys.modules[mod1] = m1
+        setattr(importlib.import_module("kymatio.scattering1d.backend"), "torch_b200_backend", m1)
 
     if "scattering2d" not in _originals:
         _originals["scattering2d"] = tf2d.scattering2d
