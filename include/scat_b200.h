@@ -116,6 +116,18 @@ int  scat_pad1d(const void* x_dev, void* out_dev, int64_t G, int32_t N, int32_t 
 int  scat_subsample_fourier1d(const void* in_dev, void* out_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
                               void* stream);
 
+/* 3-D primitives (kymatio/scattering3d/backend/torch_backend.py:73-151) --------------------------------
+ * natural-order complex 3-D FFT on (G, M, N, O, 2) - replaces torch.fft.fftn / ifftn (torch_backend.py:39-40) */
+size_t scat_fft3d_const_bytes(int32_t M, int32_t N, int32_t O, int32_t dtype);
+int  scat_fft3d_init(void* const_dev, int32_t M, int32_t N, int32_t O, int32_t dtype, void* stream);
+int  scat_fft3d_exec(const void* const_dev, const void* in_dev, void* out_dev, int64_t G, int32_t M, int32_t N, int32_t O,
+                     int32_t inverse, int32_t dtype, void* stream);
+/* out = sqrt(prev^2 + |x|^2), prev may be NULL  (modulus_rotation, torch_backend.py:102-124) */
+int  scat_modulus_rotation(const void* x_dev, const void* prev_dev, void* out_dev, int64_t n, int32_t dtype, void* stream);
+/* out[b][p] = sum_i x[b][i]^powers[p], float64 accumulators (compute_integrals, torch_backend.py:127-151) */
+int  scat_compute_integrals(const void* x_dev, void* out_f64_dev, int64_t B, int64_t n, const void* powers_f32_dev,
+                            int32_t P, int32_t dtype, void* stream);
+
 /* adjoints for the autograd graph ------------------------------------------------
  * filter multiply with the filters broadcast over the batch: out[b][f][i] = a[b][i] * w[f][i] (w real);
  * adjoint = 1 computes ga[b][i] = sum_f a[b][f][i] * w[f][i]  (backward of cdgmm, backend/torch_backend.py:205-206) */

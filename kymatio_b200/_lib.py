@@ -63,6 +63,13 @@ SIGNATURES = {
                               _c.c_void_p]),
     "scat_subsample_fourier1d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,
                                             _c.c_void_p]),
+    "scat_fft3d_const_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
+    "scat_fft3d_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_fft3d_exec": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,
+                                   _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_modulus_rotation": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_compute_integrals": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int32,
+                                          _c.c_int32, _c.c_void_p]),
     "scat_cdgmm_bcast": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int64,
                                     _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_subsample_fourier2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,

@@ -322,4 +322,112 @@ void fft1d_exec(const void* const_dev, const void* in, void* tmp, void* out, int
     });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 3-D primitives (kymatio/scattering3d/backend/torch_backend.py)
+// ---------------------------------------------------------------------------------------------------
+// sqrt(prev^2 + |x|^2): the running rotation-covariant modulus (torch_backend.py:102-124); prev may be null
+template <typename T>
+__global__ void kp_modulus_rotation(const cx<T>* __restrict__ x, const T* __restrict__ prev, T* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cx<T> v = x[i];
+    T m2 = v.x * v.x + v.y * v.y;
+    if (prev) { const T p = prev[i]; m2 += p * p; }
+    out[i] = sqrt(m2);
+}
+// integrals[b][p] += sum_i x[b][i]^q_p  (torch_backend.py:127-151); out must be zeroed by the caller
+template <typename T>
+__global__ void kp_integrals(const T* __restrict__ x, double* __restrict__ out, size_t n, const float* __restrict__ powers,
+                             int P) {
+    __shared__ double red[8][32];
+    const size_t b = blockIdx.y;
+    double acc[8];
+    for (int p = 0; p < 8; ++p) acc[p] = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const T v = x[b * n + i];
+        for (int p = 0; p < P; ++p) {
+            const float q = powers[p];
+            acc[p] += q == 1.f ? (double)v : q == 2.f ? (double)v * (double)v : pow((double)v, (double)q);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = 0; p < P; ++p) {
+        double a = acc[p];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+        if (lane == 0) red[p][warp] = a;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int p = 0; p < P; ++p) {
+            double a = lane < (int)(blockDim.x >> 5) ? red[p][lane] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+            if (lane == 0) atomicAdd(&out[b * P + p], a);
+        }
+    }
+}
+
+// natural-order complex 3-D FFT on (G, M, N, O): one row pass (O) and two column passes (N, then M)
+template <typename T> struct Fft3dTables {
+    int n[3]; Plan1 p[3]; size_t tw[3], pos[3], bytes;
+    Fft3dTables(int M, int N, int O) {
+        n[0] = M; n[1] = N; n[2] = O;
+        size_t off = 0;
+        auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+        for (int a = 0; a < 3; ++a) {
+            p[a] = make_plan1(n[a]);
+            tw[a] = take((size_t)n[a] * sizeof(cx<T>)); pos[a] = take((size_t)n[a] * sizeof(int));
+        }
+        bytes = off;
+    }
+};
+template <typename T> void fft3d_init(void* const_dev, int M, int N, int O, cudaStream_t st) {
+    Fft3dTables<T> t(M, N, O);
+    std::vector<unsigned char> h(t.bytes, 0);
+    for (int a = 0; a < 3; ++a) {
+        auto tw = twiddle_table<T>(t.n[a]); auto ps = scramble_table(t.p[a]);
+        memcpy(h.data() + t.tw[a], tw.data(), (size_t)t.n[a] * sizeof(cx<T>));
+        if (t.n[a] > 1) memcpy(h.data() + t.pos[a], ps.data(), (size_t)t.n[a] * sizeof(int));
+    }
+    SB_CUDA(cudaMemcpyAsync(const_dev, h.data(), t.bytes, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+template <typename T>
+void fft3d_exec(const void* const_dev, const void* in, void* out, int64_t G, int M, int N, int O, bool inverse, cudaStream_t st) {
+    Fft3dTables<T> t(M, N, O);
+    const unsigned char* cb = static_cast<const unsigned char*>(const_dev);
+    auto twp = [&](int a) { return reinterpret_cast<const cx<T>*>(cb + t.tw[a]); };
+    auto posp = [&](int a) { return reinterpret_cast<const int*>(cb + t.pos[a]); };
+    // along O: rows of the (G*M, N, O) view
+    {
+        const SlabCfg rc = slab_cfg(t.p[2], N, sizeof(cx<T>), sizeof(int));
+        const StreamKernels<T> k = stream_kernels_lookup<T>(O, false);
+        RowArgs<T> ra{};
+        ra.in = static_cast<const cx<T>*>(in); ra.out = static_cast<cx<T>*>(out); ra.n0 = N; ra.n1 = O;
+        ra.lines = rc.lines; ra.LP = rc.LP; ra.plan = t.p[2]; ra.tw = twp(2); ra.pos = posp(2);
+        dim3 g((unsigned)(G * M), ceil_div(N, rc.lines));
+        launch("prim3d_rowpass", 2.0 * G * M * N * O * sizeof(cx<T>), st,
+               [&] { (inverse ? k.row_inv : k.row_fwd)<<<g, rc.block, rc.smem, st>>>(ra); });
+    }
+    // along N: columns of the (G*M, N, O) view; along M: columns of the (G, M, N*O) view
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ax = pass == 0 ? 1 : 0;
+        const int n0 = t.n[ax], n1 = pass == 0 ? O : N * O;
+        const int64_t g = pass == 0 ? G * M : G;
+        const SlabCfg cc = slab_cfg(t.p[ax], n1, sizeof(cx<T>), sizeof(int));
+        const StreamKernels<T> k = stream_kernels_lookup<T>(n0, false);
+        ColArgs<T> ca{};
+        ca.in = static_cast<cx<T>*>(out); ca.out = static_cast<cx<T>*>(out); ca.n0 = n0; ca.n1 = n1;
+        ca.lines = cc.lines; ca.LP = cc.LP; ca.plan = t.p[ax]; ca.tw = twp(ax); ca.pos = posp(ax);
+        dim3 grid((unsigned)g, ceil_div(n1, cc.lines));
+        launch("prim3d_colpass", 2.0 * G * M * N * O * sizeof(cx<T>), st,
+               [&] { (inverse ? k.col_inv : k.col_fwd)<<<grid, cc.block, cc.smem, st>>>(ca); });
+    }
+    if (inverse) {
+        const size_t n = (size_t)G * M * N * O;
+        launch("prim_scale", 2.0 * n * sizeof(cx<T>), st, [&] {
+            kp_scale<T><<<blocks_for(n), 256, 0, st>>>(static_cast<cx<T>*>(out), n, T(1) / (T(M) * T(N) * T(O)));
+        });
+    }
+}
+
 }  // namespace sb

@@ -224,6 +224,49 @@ int scat_subsample_fourier1d(const void* in_dev, void* out_dev, int64_t G, int32
     });
 }
 
+// ---- 3-D primitives -----------------------------------------------------------------------------------
+size_t scat_fft3d_const_bytes(int32_t M, int32_t N, int32_t O, int32_t dtype) {
+    try {
+        return dtype == 1 ? Fft3dTables<double>(M, N, O).bytes : Fft3dTables<float>(M, N, O).bytes;
+    } catch (const std::exception& e) { last_error() = e.what(); return 0; }
+}
+int scat_fft3d_init(void* const_dev, int32_t M, int32_t N, int32_t O, int32_t dtype, void* stream) {
+    return guarded([&] { SB_DISPATCH(dtype, fft3d_init<T>(const_dev, M, N, O, static_cast<cudaStream_t>(stream))); });
+}
+int scat_fft3d_exec(const void* const_dev, const void* in_dev, void* out_dev, int64_t G, int32_t M, int32_t N, int32_t O,
+                    int32_t inverse, int32_t dtype, void* stream) {
+    return guarded([&] {
+        static bool enabled = false;
+        if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
+        if (G <= 0) return;
+        SB_DISPATCH(dtype, fft3d_exec<T>(const_dev, in_dev, out_dev, G, M, N, O, inverse != 0, static_cast<cudaStream_t>(stream)));
+    });
+}
+int scat_modulus_rotation(const void* x_dev, const void* prev_dev, void* out_dev, int64_t n, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (n <= 0) return;
+        SB_DISPATCH(dtype, launch("prim_modulus_rotation", (double)n * 4 * sizeof(T), st, [&] {
+            kp_modulus_rotation<T><<<blocks_for((size_t)n), 256, 0, st>>>(static_cast<const cx<T>*>(x_dev), static_cast<const T*>(prev_dev),
+                                                                           static_cast<T*>(out_dev), (size_t)n);
+        }));
+    });
+}
+int scat_compute_integrals(const void* x_dev, void* out_f64_dev, int64_t B, int64_t n, const void* powers_f32_dev,
+                           int32_t P, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (P < 1 || P > 8) throw std::runtime_error("compute_integrals supports 1..8 powers");
+        if (B <= 0 || n <= 0) return;
+        SB_CUDA(cudaMemsetAsync(out_f64_dev, 0, (size_t)B * P * sizeof(double), st));
+        dim3 grid((unsigned)std::min<int64_t>(1024, (n + 1023) / 1024), (unsigned)B);
+        SB_DISPATCH(dtype, launch("prim_integrals", (double)B * n * sizeof(T), st, [&] {
+            kp_integrals<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x_dev), static_cast<double*>(out_f64_dev), (size_t)n,
+                                                   static_cast<const float*>(powers_f32_dev), P);
+        }));
+    });
+}
+
 // ---- adjoints used by the autograd graph ------------------------------------------------------------
 int scat_cdgmm_bcast(const void* a_dev, const void* w_dev, void* out_dev, int64_t nb, int32_t nf, int64_t n,
                      int32_t adjoint, int32_t dtype, void* stream) {

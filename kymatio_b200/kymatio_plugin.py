@@ -358,6 +358,83 @@ class TorchB200Backend1D(TorchB200Backend2D):
 
 backend1d = TorchB200Backend1D
 
+
+# ---------------------------------------------------------------------------------------------------
+# 3-D backend (kymatio/scattering3d/backend/torch_backend.py) - eager primitives
+# ---------------------------------------------------------------------------------------------------
+class _Fft3dTables:
+    _cache = {}
+
+    @classmethod
+    def get(cls, shape, ref):
+        key = (tuple(shape), ref.dtype, ref.device.index)
+        buf = cls._cache.get(key)
+        if buf is None:
+            lib = _lib.load()
+            code = _dtype_code(ref)
+            nbytes = lib.scat_fft3d_const_bytes(shape[0], shape[1], shape[2], code)
+            if nbytes == 0:
+                raise _lib.ScatB200Error(lib.scat_last_error().decode())
+            with torch.cuda.device(ref.device):
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=ref.device)
+                _lib.check(lib.scat_fft3d_init(buf.data_ptr(), shape[0], shape[1], shape[2], code, _stream(ref)))
+            cls._cache[key] = buf
+        return buf
+
+
+class TorchB200Backend3D(TorchB200Backend2D):
+    Pad = None
+
+    @staticmethod
+    def stack(arrays, L):
+        # torch_backend.py:73-76
+        S = torch.stack(arrays, dim=1)
+        return S.reshape((S.shape[0], S.shape[1] // (L + 1), (L + 1)) + S.shape[2:])
+
+    @classmethod
+    def _fft(cls, x, inverse):
+        M, N, O = x.shape[-4], x.shape[-3], x.shape[-2]
+        tables = _Fft3dTables.get((M, N, O), x)
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_fft3d_exec(tables.data_ptr(), x.data_ptr(), out.data_ptr(),
+                                                   x.numel() // (2 * M * N * O), M, N, O, int(inverse), _dtype_code(x),
+                                                   _stream(x)))
+        return out
+
+    @classmethod
+    def cdgmm3d(cls, A, B):
+        return cls.cdgmm(A, B)
+
+    @staticmethod
+    def modulus_rotation(x, module=None):
+        # torch_backend.py:102-124
+        _cuda_check(x)
+        x = x.contiguous()
+        out = torch.empty(x.shape[:-1] + (1,), dtype=x.dtype, device=x.device)
+        prev = 0 if module is None else module.contiguous().data_ptr()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_modulus_rotation(x.data_ptr(), prev, out.data_ptr(), out.numel(),
+                                                         _dtype_code(x), _stream(x)))
+        return out
+
+    @staticmethod
+    def compute_integrals(input_array, integral_powers):
+        # torch_backend.py:127-151 (the result takes torch's default dtype there, which is kept)
+        _cuda_check(input_array)
+        x = input_array.contiguous()
+        B = x.shape[0]
+        powers = torch.tensor([float(q) for q in integral_powers], dtype=torch.float32, device=x.device)
+        acc = torch.empty((B, len(integral_powers)), dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().scat_compute_integrals(x.data_ptr(), acc.data_ptr(), B, x.numel() // max(B, 1),
+                                                          powers.data_ptr(), len(integral_powers), _dtype_code(x),
+                                                          _stream(x)))
+        return acc.to(torch.get_default_dtype())
+
+
+backend3d = TorchB200Backend3D
+
 # ---------------------------------------------------------------------------------------------------
 # fused dispatch
 # ---------------------------------------------------------------------------------------------------
@@ -423,6 +500,14 @@ def install(fused=True):
         m1.__doc__ = "torch_b200 1-D backend (provided by kymatio_b200)"
         sys.modules[mod1] = m1
         setattr(importlib.import_module("kymatio.scattering1d.backend"), "torch_b200_backend", m1)
+
+    mod3 = "kymatio.scattering3d.backend.torch_b200_backend"
+    if mod3 not in sys.modules:
+        m3 = types.ModuleType(mod3)
+        m3.backend = backend3d
+        m3.__doc__ = "torch_b200 3-D backend (provided by kymatio_b200)"
+        sys.modules[mod3] = m3
+        setattr(importlib.import_module("kymatio.scattering3d.backend"), "torch_b200_backend", m3)
 
     if "scattering2d" not in _originals:
         _originals["scattering2d"] = tf2d.scattering2d

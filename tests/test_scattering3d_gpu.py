@@ -1,0 +1,78 @@
+"""3-D solid-harmonic scattering through the unmodified kymatio torch frontend with
+backend='torch_b200' (eager primitives), against reference-generated goldens and the reference's own
+fixture (tests/scattering3d/test_torch_scattering3d.py:151-201: rel-L1 < 1e-6 there in fp64; here fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import import_reference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def plugin():
+    if not import_reference():
+        pytest.skip("reference not installed under baseline/_ref")
+    import kymatio_b200.kymatio_plugin as p
+    p.install()
+    return p
+
+
+def _rel_l1(a, b):
+    return float(np.abs(a - b).sum() / max(np.abs(a).sum(), np.abs(b).sum()))
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 8), (12, 16, 20), (32, 32, 32), (128, 128, 128)])
+def test_fft3d_against_torch(plugin, shape):
+    be = plugin.backend3d
+    B = 1 if shape[0] >= 128 else 2
+    z = torch.randn(B, *shape, 2, device="cuda")
+    ref = torch.view_as_real(torch.fft.fftn(torch.view_as_complex(z), dim=[-1, -2, -3]))
+    tol = 3e-6 * float(ref.abs().max()) * np.log2(np.prod(shape))
+    assert torch.allclose(be._fft(z, False), ref, atol=tol)
+    refi = torch.view_as_real(torch.fft.ifftn(torch.view_as_complex(z), dim=[-1, -2, -3]))
+    assert torch.allclose(be.ifft(z), refi, atol=3e-6 * float(refi.abs().max()) * np.log2(np.prod(shape)) + 1e-9)
+
+
+def test_modulus_rotation_and_integrals(plugin):
+    be = plugin.backend3d
+    x = torch.randn(2, 6, 5, 4, 2, device="cuda")
+    m1 = be.modulus_rotation(x)
+    assert torch.allclose(m1, torch.sqrt((x ** 2).sum(-1, keepdim=True)))
+    y = torch.randn(2, 6, 5, 4, 2, device="cuda")
+    m2 = be.modulus_rotation(y, m1)
+    assert torch.allclose(m2, torch.sqrt(m1 ** 2 + (y ** 2).sum(-1, keepdim=True)), atol=1e-6)
+    u = torch.rand(3, 7, 6, 5, 1, device="cuda") + 0.1
+    got = be.compute_integrals(u, (0.5, 1.0, 2.0))
+    ref = torch.stack([(u ** q).reshape(3, -1).sum(1) for q in (0.5, 1.0, 2.0)], 1)
+    assert got.shape == (3, 3) and torch.allclose(got, ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["J2_L2_16", "J2_L2_32", "J1_L3_12x16x20"])
+def test_scattering3d_golden(plugin, golden_dir, name):
+    from kymatio.torch import HarmonicScattering3D
+    d = np.load(os.path.join(golden_dir, f"golden_3d_{name}.npz"))
+    kw = dict(J=int(d["J"]), shape=tuple(int(v) for v in d["shape"]), L=int(d["L"]))
+    if "integral_powers" in d.files:
+        kw["integral_powers"] = tuple(float(v) for v in d["integral_powers"])
+    S = HarmonicScattering3D(backend="torch_b200", **kw).cuda()
+    y = S(torch.from_numpy(d["x"]).cuda())
+    assert tuple(y.shape) == d["Sx64"].shape
+    assert _rel_l1(y.cpu().numpy().astype(np.float64), d["Sx64"]) < 1e-4
+
+
+def test_scattering3d_reference_fixture(plugin, golden_dir):
+    from kymatio.torch import HarmonicScattering3D
+    d = np.load(os.path.join(golden_dir, "ref_fixture_3d.npz"))
+    x = torch.from_numpy(d["x"]).cuda()
+    J, L, powers = int(d["J"]), int(d["L"]), tuple(float(v) for v in d["integral_powers"])
+    S = HarmonicScattering3D(J, x.shape[1:], L=L, sigma_0=1, integral_powers=powers, max_order=2,
+                             backend="torch_b200").cuda()
+    order_0 = plugin.backend3d.compute_integrals(x, powers)
+    y = S(x)
+    out = torch.cat([order_0.reshape(x.shape[0], -1), y.reshape(x.shape[0], -1)], 1).cpu().numpy()
+    assert out.shape == d["Sx"].shape
+    assert _rel_l1(out.astype(np.float64), d["Sx"].astype(np.float64)) < 1e-4
