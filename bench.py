@@ -230,9 +230,11 @@ def run_b200_arm(args):
         # ---- end to end: pinned host in -> H2D -> forward -> D2H pinned host out, every step -------
         xh = torch.randn(B, *SHAPE, dtype=torch.float32).pin_memory()
         yh = torch.empty((B,) + tuple(y.shape[1:]), dtype=torch.float32).pin_memory()
-        nchunk = 4 if B % 4 == 0 and B >= 16 else 1
+        nchunk = int(os.environ.get("BENCH_E2E_CHUNKS", "8"))
+        if B % nchunk or B < 4 * nchunk:
+            nchunk = 1
         cb = B // nchunk
-        streams = [torch.cuda.Stream(device=dev) for _ in range(min(2, nchunk))]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("BENCH_E2E_STREAMS", "3")), nchunk))]
 
         def e2e_step():
             for c in range(nchunk):
@@ -299,7 +301,7 @@ def run_b200_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": xh.numel() * 4,
                 "d2h_bytes_per_step": yh.numel() * 4,
-                "note": "pinned host in/out, 4 chunks pipelined on 2 streams, wall clock, max over ranks"},
+                "note": f"pinned host in/out, {nchunk} chunks pipelined on {len(streams)} streams, wall clock, max over ranks"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "kernel": top["label"],

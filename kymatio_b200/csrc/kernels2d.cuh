@@ -316,6 +316,10 @@ template <typename T> struct RowArgs {
     int n0, n1;
     int lines, LP;
     Plan1 plan; const cx<T>* tw; const int* pos;
+    // optional (forward static instances): also emit the low-pass product folded along the row,
+    //   low_out[g][u][v'] = sum_d out[g][u][v' + d*low_m1] * low_filt[u][v' + d*low_m1],  v' < low_m1
+    // so that the Fourier low-pass of this band needs n0 x low_m1 values per path instead of n0 x n1
+    const T* low_filt; const int2* low_supp; cx<T>* low_out; int low_m1;
 };
 // INV=false: spatial row in -> DIF -> Fourier row out; INV=true: Fourier row in -> DIT -> spatial row out
 template <typename T, bool INV, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_rowpass(RowArgs<T> a) {
@@ -352,6 +356,31 @@ template <typename T, bool INV, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_r
     if constexpr (PLAIN) slab_fft_s<NS, true, -1, 1, kSLP, T>(s, nl, tw);
     else if constexpr (NS > 0) slab_fft_s<NS, true, +1, 1, kSLP, T>(s, nl, tw);
     else slab_fft<INV, T>(s, nl, 1, LP, a.plan, tw);
+    if (PLAIN && a.low_out) {
+        // natural-order Fourier rows are in shared memory: fold (row * phi) onto low_m1 columns
+        const int m1 = a.low_m1, kf = n1 / m1;
+        cx<T>* lo = a.low_out + ((size_t)g * a.n0 + r0) * m1;
+        for (int idx = tid; idx < nl * m1; idx += nt) {
+            const int l = idx / m1, e = idx - l * m1;
+            const int u = r0 + l;
+            const int2 sp = a.low_supp[u];
+            T ax = T(0), ay = T(0);
+            if (sp.y > 0) {
+                const T* __restrict__ fr = a.low_filt + (size_t)u * n1;
+                for (int d = 0; d < kf; ++d) {
+                    const int C = e + d * m1;
+                    int rel = C - sp.x;
+                    if (rel < 0) rel += n1;
+                    if (rel < sp.y) {
+                        const cx<T> v = s[C * LP + l];
+                        const T f = fr[C];
+                        ax += v.x * f; ay += v.y * f;
+                    }
+                }
+            }
+            lo[(size_t)l * m1 + e] = mk<T>(ax, ay);
+        }
+    }
     if ((n1 & 1) == 0) {
         const int half = n1 >> 1;
         for (int idx = tid; idx < nl * half; idx += nt) {
@@ -379,6 +408,7 @@ template <typename T> struct LowArgs {
     int PP, NF, ch0, chs, K;
     T scale;
     Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
+    int row_folded;       // 1: `in` is [G][P0][m1], already multiplied by the filter and folded along rows
 };
 // grid (G).  One CTA: periodise (in*filt) to m0 x m1, inverse 2-D DIT in shared memory,
 // keep the real part, crop one sample per side (unpad) and write the channel plane.
@@ -397,7 +427,15 @@ template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_lowpass
     const cx<T>* pb = a.in + (size_t)g * a.P0 * a.P1;
     for (int idx = flat_tid(); idx < a.m0 * a.m1; idx += flat_nt()) {
         const int r = idx / a.m1, e = idx - r * a.m1;
-        const cx<T> v = prod_fold<T>(pb, a.filt, a.supp, r, e, a.k, a.m0, a.m1, a.P1);
+        cx<T> v;
+        if (a.row_folded) {
+            T ax = T(0), ay = T(0);
+            const cx<T>* rb = a.in + (size_t)g * a.P0 * a.m1;
+            for (int c = 0; c < a.k; ++c) { const cx<T> t = rb[(size_t)(r + c * a.m0) * a.m1 + e]; ax += t.x; ay += t.y; }
+            v = mk<T>(ax, ay);
+        } else {
+            v = prod_fold<T>(pb, a.filt, a.supp, r, e, a.k, a.m0, a.m1, a.P1);
+        }
         s[pos0[r] * a.W + pos1[e]] = scal(v, a.scale);
     }
     __syncthreads();

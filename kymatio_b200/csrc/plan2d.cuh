@@ -318,7 +318,8 @@ private:
             for (int j2 = 1; j2 < J; ++j2)
                 if (!bound_ || !tile_ok_[j2]) ws_u2_ = std::max(ws_u2_, (size_t)L * L * fsize(j2));
         ws_low_ = low_tile_ ? 0 : (size_t)std::max(1, d_.max_order == 2 && J >= 2 ? L * L : L) * m0_ * m1_;
-        per_img_ = (ws_u0_ + ws_u1_ + ws_u2_ + ws_low_) * sizeof(cx<T>);
+        ws_rf_ = (size_t)L * P0_ * m1_;     // row-folded low-pass product of the full-resolution band
+        per_img_ = (ws_u0_ + ws_u1_ + ws_u2_ + ws_low_ + ws_rf_) * sizeof(cx<T>);
     }
 
     // kernel table for line length n; the static instances need the default 16-line slab shape
@@ -366,9 +367,10 @@ private:
                    (MODE == COL_FWD ? k.col_fwd : MODE == COL_INV ? k.col_inv : k.col_imf)<<<grid, c.block, c.smem, st>>>(a);
                });
     }
-    template <bool INV> void row_pass(cx<T>* data, int res, int G, cudaStream_t st) {
+    template <bool INV> void row_pass(cx<T>* data, int res, int G, cudaStream_t st, cx<T>* low_out = nullptr) {
         RowArgs<T> a{};
         a.in = data; a.out = data; a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n;
+        if (low_out) { a.low_filt = phi(res); a.low_supp = phi_supp(res); a.low_out = low_out; a.low_m1 = m1_; }
         const SlabCfg& c = row_cfg_[res];
         a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a1.plan; a.tw = tw(lev_[res].a1); a.pos = pos(lev_[res].a1);
         dim3 grid((unsigned)G, ceil_div(a.n0, c.lines));
@@ -382,7 +384,7 @@ private:
     }
     // Fourier low-pass: S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool row_folded = false) {
         const int k = 1 << (d_.J - res);
         const T scale = T(1) / (T(k) * T(k) * T(m0_) * T(m1_));
         const int J = d_.J;
@@ -393,6 +395,7 @@ private:
             a.PP = PP; a.NF = NF; a.ch0 = ch0; a.chs = chs; a.K = K_; a.scale = scale;
             a.plan0 = lev_[J].a0.plan; a.plan1 = lev_[J].a1.plan;
             a.tw0 = tw(lev_[J].a0); a.tw1 = tw(lev_[J].a1); a.pos0 = pos(lev_[J].a0); a.pos1 = pos(lev_[J].a1);
+            a.row_folded = row_folded ? 1 : 0;
             const double G = (double)B * PP;
             launch("lowpass:L" + std::to_string(res) + ":G" + std::to_string(PP),
                    G * a.P0 * a.P1 * sizeof(cx<T>) + (double)a.P0 * a.P1 * sizeof(T) + G * o0_ * o1_ * sizeof(T), st,
@@ -489,6 +492,7 @@ private:
         cx<T>* U1 = U0 + (size_t)B * ws_u0_;
         cx<T>* U2 = U1 + (size_t)B * ws_u1_;
         cx<T>* TL = U2 + (size_t)B * ws_u2_;
+        cx<T>* RF = TL + (size_t)B * ws_low_;
         // U0 = fft2(pad(x))   (core/scattering2d.py:14-16)
         {
             PadRowArgs<T> a{};
@@ -514,8 +518,10 @@ private:
                 const T sc1 = T(1) / (T(1 << j1) * T(1 << j1) * T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
                 row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), U1, 0, j1, B, L, sc1, st);
                 col_pass<COL_INV_MOD_FWD>(U1, j1, B * L, st);
-                row_pass<false>(U1, j1, B * L, st);
-                low_pass(U1, j1, out, B, L, L, 1 + j1 * L, 0, TL, st);
+                // static chains emit the phi-product folded along the row while Û1 is still in shared memory
+                const bool fold = low_tile_ && chain_static(j1) && lev_[j1].a1.n % m1_ == 0;
+                row_pass<false>(U1, j1, B * L, st, fold ? RF : nullptr);
+                low_pass(fold ? RF : U1, j1, out, B, L, L, 1 + j1 * L, 0, TL, st, fold);
             }
             if (d_.max_order < 2) continue;
             const int nchild = (J - 1 - j1) * L;
@@ -556,7 +562,7 @@ private:
     bool force_stream_ = false;
     int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 576);
     int num_sms_ = 148;
-    size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, per_img_ = 0;
+    size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, ws_rf_ = 0, per_img_ = 0;
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;
     int last_B_ = 1;
