@@ -398,6 +398,109 @@ template <typename T, bool INV, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_r
     }
 }
 
+// ------------------------------------------------------------------ real-input (Hermitian) variants of the chain
+// The field between the inverse and the forward transform is a modulus, i.e. REAL.  Static chains use it:
+//   k2d_colpass_imrf : column inverse DIF(+), modulus, then ONE complex forward DIT(-) per PAIR of columns
+//                      (z = A[:,x0] + i A[:,x1]); the two spectra are untangled and only rows v <= n0/2 are
+//                      stored (the rest is the conjugate mirror);
+//   k2d_rowpass_fwdh : forward DIT(-) along the rows v <= n0/2 only; every row is also written as its mirror
+//                      U[(n0-v)%n0][(n1-w)%n1] = conj(U[v][w]), and (optionally) both feed the row-folded
+//                      low-pass product (see RowArgs).
+template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_colpass_imrf(ColArgs<T> a) {
+    static_assert(NS > 0 && NS % 2 == 0, "static even sizes only");
+    constexpr int n0 = NS, LP = kSLP, H = NS / 2;
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* tw = s + (size_t)n0 * LP;
+    const int g = blockIdx.x, c0 = blockIdx.y * kSLines;    // launch requires n1 % kSLines == 0
+    stage(tw, a.tw, n0);
+    const cx<T>* ib = a.in + (size_t)g * n0 * a.n1 + c0;
+    cx<T>* ob = a.out + (size_t)g * n0 * a.n1 + c0;
+    const int tid = flat_tid(), nt = flat_nt();
+    for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+        const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+        const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)e * a.n1 + l);
+        s[e * LP + l] = v.a; s[e * LP + l + 1] = v.b;
+    }
+    __syncthreads();
+    slab_fft_s<NS, false, +1, 1, kSLP, T, true>(s, kSLines, tw);           // inverse + modulus -> (|u|, 0), rows scrambled
+    // pack column pairs: (|u|_{2m}, |u|_{2m+1}) -> one complex column at lane 2m
+    for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+        const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+        s[e * LP + l].y = s[e * LP + l + 1].x;
+    }
+    __syncthreads();
+    slab_fft_s<NS, true, -1, 2, kSLP, T>(s, kSLines / 2, tw);              // forward on the 8 packed columns
+    // untangle: A[v] = (Z[v] + conj Z[n-v]) / 2,  B[v] = (Z[v] - conj Z[n-v]) / (2i);  rows v = 0..n0/2
+    for (int idx = tid; idx < (H + 1) * (kSLines / 2); idx += nt) {
+        const int v = idx / (kSLines / 2), l = 2 * (idx - v * (kSLines / 2));
+        const cx<T> z = s[v * LP + l], zm = s[(v == 0 ? 0 : n0 - v) * LP + l];
+        cxpair<T> o;
+        o.a = mk<T>(T(0.5) * (z.x + zm.x), T(0.5) * (z.y - zm.y));
+        o.b = mk<T>(T(0.5) * (z.y + zm.y), T(0.5) * (zm.x - z.x));
+        *reinterpret_cast<cxpair<T>*>(ob + (size_t)v * a.n1 + l) = o;
+    }
+}
+
+template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_rowpass_fwdh(RowArgs<T> a) {
+    static_assert(NS > 0 && NS % 2 == 0, "static even sizes only");
+    constexpr int n1 = NS, LP = kSLP;
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* tw = s + (size_t)n1 * LP;
+    const int g = blockIdx.x, r0 = blockIdx.y * kSLines;
+    const int H = a.n0 / 2;
+    const int nl = min(kSLines, H + 1 - r0);                 // rows v = r0 .. r0+nl-1 <= n0/2
+    stage(tw, a.tw, n1);
+    const cx<T>* ib = a.in + ((size_t)g * a.n0 + r0) * n1;
+    cx<T>* ob = a.out + (size_t)g * a.n0 * n1;
+    const int tid = flat_tid(), nt = flat_nt();
+    constexpr int half = n1 / 2;
+    for (int idx = tid; idx < nl * half; idx += nt) {
+        const int l = idx / half, e = 2 * (idx - l * half);
+        const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)l * n1 + e);
+        s[e * LP + l] = v.a; s[(e + 1) * LP + l] = v.b;
+    }
+    __syncthreads();
+    slab_fft_s<NS, true, -1, 1, kSLP, T>(s, nl, tw);
+    // row v and its conjugate mirror row (n0 - v): U[n0-v][w] = conj(U[v][(n1-w)%n1])
+    for (int idx = tid; idx < nl * half; idx += nt) {
+        const int l = idx / half, e = 2 * (idx - l * half);
+        const int v = r0 + l;
+        cxpair<T> o; o.a = s[e * LP + l]; o.b = s[(e + 1) * LP + l];
+        *reinterpret_cast<cxpair<T>*>(ob + (size_t)v * n1 + e) = o;
+        if (v > 0 && v < H) {
+            const cx<T> m0 = s[(e == 0 ? 0 : n1 - e) * LP + l], m1 = s[(n1 - e - 1) * LP + l];
+            cxpair<T> om; om.a = mk<T>(m0.x, -m0.y); om.b = mk<T>(m1.x, -m1.y);
+            *reinterpret_cast<cxpair<T>*>(ob + (size_t)(a.n0 - v) * n1 + e) = om;
+        }
+    }
+    if (a.low_out) {
+        const int m1 = a.low_m1, kf = n1 / m1;
+        for (int idx = tid; idx < 2 * nl * m1; idx += nt) {
+            const int mir = idx / (nl * m1), rem = idx - mir * nl * m1;
+            const int l = rem / m1, e = rem - l * m1;
+            const int v = r0 + l;
+            if (mir && !(v > 0 && v < H)) continue;
+            const int u = mir ? a.n0 - v : v;
+            const int2 sp = a.low_supp[u];
+            T ax = T(0), ay = T(0);
+            if (sp.y > 0) {
+                const T* __restrict__ fr = a.low_filt + (size_t)u * n1;
+                for (int d = 0; d < kf; ++d) {
+                    const int C = e + d * m1;
+                    int rel = C - sp.x;
+                    if (rel < 0) rel += n1;
+                    if (rel < sp.y) {
+                        const cx<T> t = s[(mir ? (C == 0 ? 0 : n1 - C) : C) * LP + l];
+                        const T f = fr[C];
+                        ax += t.x * f; ay += (mir ? -t.y : t.y) * f;
+                    }
+                }
+            }
+            a.low_out[((size_t)g * a.n0 + u) * m1 + e] = mk<T>(ax, ay);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ Fourier low-pass tile (generic phi)
 template <typename T> struct LowArgs {
     const cx<T>* in;      // [G][P0][P1] natural-order spectra
@@ -479,6 +582,8 @@ template <typename T> struct StreamKernels {
     void (*row_prod)(RowProdArgs<T>);
     void (*row_fwd)(RowArgs<T>);
     void (*row_inv)(RowArgs<T>);
+    void (*col_imrf)(ColArgs<T>);     // real-input column pass (static even sizes only, else null)
+    void (*row_fwdh)(RowArgs<T>);     // Hermitian forward row pass (static even sizes only, else null)
     bool is_static;
 };
 template <typename T> StreamKernels<T> stream_kernels_lookup(int n, bool allow_static);

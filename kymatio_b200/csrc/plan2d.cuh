@@ -382,6 +382,38 @@ private:
                    (INV ? k.row_inv : k.row_fwd)<<<grid, c.block, c.smem, st>>>(a);
                });
     }
+    // real-input variants of the column / forward-row passes (kernels2d.cuh): static even square-ish levels
+    bool hermitian_ok(int res) const {
+        if (env_int("SCAT_B200_NO_HERMITIAN", 0)) return false;
+        const int n0 = lev_[res].a0.n, n1 = lev_[res].a1.n;
+        return chain_static(res) && n0 % 2 == 0 && n1 % kSLines == 0 &&
+               skern(n0, col_cfg_[res]).col_imrf != nullptr && skern(n1, row_cfg_[res]).row_fwdh != nullptr;
+    }
+    void hermitian_chain(cx<T>* data, int res, int G, cudaStream_t st, cx<T>* low_out) {
+        const int n0 = lev_[res].a0.n, n1 = lev_[res].a1.n;
+        {
+            ColArgs<T> a{};
+            a.in = data; a.out = data; a.n0 = n0; a.n1 = n1;
+            const SlabCfg& c = col_cfg_[res];
+            a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a0.plan; a.tw = tw(lev_[res].a0); a.pos = pos(lev_[res].a0);
+            dim3 grid((unsigned)G, n1 / kSLines);
+            launch("colpass_inv_mod_rfwd:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
+                   1.5 * G * n0 * n1 * sizeof(cx<T>), st,
+                   [&] { skern(n0, c).col_imrf<<<grid, c.block, c.smem, st>>>(a); });
+        }
+        {
+            RowArgs<T> a{};
+            a.in = data; a.out = data; a.n0 = n0; a.n1 = n1;
+            const SlabCfg& c = row_cfg_[res];
+            a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a1.plan; a.tw = tw(lev_[res].a1); a.pos = pos(lev_[res].a1);
+            if (low_out) { a.low_filt = phi(res); a.low_supp = phi_supp(res); a.low_out = low_out; a.low_m1 = m1_; }
+            dim3 grid((unsigned)G, ceil_div(n0 / 2 + 1, kSLines));
+            launch("rowpass_fwd_herm:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
+                   1.5 * G * n0 * n1 * sizeof(cx<T>), st,
+                   [&] { skern(n1, c).row_fwdh<<<grid, c.block, c.smem, st>>>(a); });
+        }
+    }
+
     // Fourier low-pass: S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
                   cudaStream_t st, bool row_folded = false) {
@@ -517,10 +549,14 @@ private:
             } else {
                 const T sc1 = T(1) / (T(1 << j1) * T(1 << j1) * T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
                 row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), U1, 0, j1, B, L, sc1, st);
-                col_pass<COL_INV_MOD_FWD>(U1, j1, B * L, st);
                 // static chains emit the phi-product folded along the row while Û1 is still in shared memory
                 const bool fold = low_tile_ && chain_static(j1) && lev_[j1].a1.n % m1_ == 0;
-                row_pass<false>(U1, j1, B * L, st, fold ? RF : nullptr);
+                if (hermitian_ok(j1)) {
+                    hermitian_chain(U1, j1, B * L, st, fold ? RF : nullptr);
+                } else {
+                    col_pass<COL_INV_MOD_FWD>(U1, j1, B * L, st);
+                    row_pass<false>(U1, j1, B * L, st, fold ? RF : nullptr);
+                }
                 low_pass(fold ? RF : U1, j1, out, B, L, L, 1 + j1 * L, 0, TL, st, fold);
             }
             if (d_.max_order < 2) continue;

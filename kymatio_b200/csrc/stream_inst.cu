@@ -17,6 +17,8 @@ template <typename T, int NS> static StreamKernels<T> make_table() {
     k.row_prod = k2d_rowpass_prod<T, NS>;
     k.row_fwd = k2d_rowpass<T, false, NS>;
     k.row_inv = k2d_rowpass<T, true, NS>;
+    if constexpr (NS > 0 && NS % 2 == 0) { k.col_imrf = k2d_colpass_imrf<T, NS>; k.row_fwdh = k2d_rowpass_fwdh<T, NS>; }
+    else { k.col_imrf = nullptr; k.row_fwdh = nullptr; }
     k.is_static = NS > 0;
     return k;
 }
@@ -35,6 +37,7 @@ template <typename T, int NS> static void enable_table() {
     enable_big_smem(k.pad_rowfft); enable_big_smem(k.col_fwd); enable_big_smem(k.col_inv);
     enable_big_smem(k.col_imf); enable_big_smem(k.row_prod); enable_big_smem(k.row_fwd);
     enable_big_smem(k.row_inv);
+    if (k.col_imrf) { enable_big_smem(k.col_imrf); enable_big_smem(k.row_fwdh); }
 }
 template <typename T> void stream_kernels_enable_smem() {
 #define SB_EN(N) enable_table<T, N>();
