@@ -478,6 +478,8 @@ private:
         a.kl = 1 << (d_.J - res);
         a.o0 = o0_; a.o1 = o1_; a.o0p = o0p(); a.o1p = o1p();
         a.PP = PP; a.NFch = NFch; a.ch0 = ch0; a.chs = chs; a.K = K_;
+        // dense (full-circle) low-pass windows go to the tensor cores (float static instances only)
+        a.use_mma = (use_mma_ && sizeof(T) == 4 && F.x1cnt >= a.n1 && F.y0cnt >= a.n0 && a.o1p % 16 == 0 && a.o0p % 16 == 0) ? 1 : 0;
         const size_t smem = tile_smem_layout<T>(a, nullptr);
         const int G = Bp * NF;
         a.G = G;
@@ -598,6 +600,7 @@ private:
     bool force_stream_ = false;
     int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 576);
     int num_sms_ = 148;
+    bool use_mma_ = env_int("SCAT_B200_NO_MMA", 0) == 0;
     size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, ws_rf_ = 0, per_img_ = 0;
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;

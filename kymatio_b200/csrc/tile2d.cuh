@@ -31,6 +31,7 @@ template <typename T> struct TileArgs {
     int kl, o0, o1, o0p, o1p;              // o?p = o? rounded up to a multiple of 4
     int PP, NFch, ch0, chs, K;
     int G;                                 // number of paths; CTAs are persistent and stride over them
+    int use_mma;                           // 1: dense low-pass products on the tensor cores (3xTF32 mma.sync)
 };
 
 template <typename T> struct TileSmem {
@@ -42,8 +43,10 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
     const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
     const size_t o_supp = take(sizeof(int2) * a.P0);
-    const size_t o_w1 = take(sizeof(T) * (size_t)a.n0 * (a.o1p + 4));
-    const size_t o_g0 = take(sizeof(T) * (size_t)a.n0 * a.o0p), o_g1 = take(sizeof(T) * (size_t)a.n1 * a.o1p);
+    // pitches: +4 (CUDA-core path, 16-byte rows) or +8 (mma path, conflict-free fragment loads); K padded to 8
+    const size_t o_w1 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o1p + 8));
+    const size_t o_g0 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
+    const size_t o_g1 = take(sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
     const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
     if (L) {
 #ifdef __CUDA_ARCH__
@@ -164,6 +167,52 @@ __device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core low-pass (float only).  Both products of the separable low-pass,
+//     W1[q][xo] = sum_p U[q][p] G1s[p][xo]            (n0 x n1) x (n1 x o1)
+//     S[yo][xo] = sum_q G0s[q][yo] W1[q][xo]          (o0 x n0) x (n0 x o1)
+// are dense when the spatial taps of phi cover the whole circle (the finest resolution).  They run on
+// mma.sync.m16n8k8 TF32 with the 3xTF32 split a = a_hi + a_lo, b = b_hi + b_lo,
+//     a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi        (fp32 accumulate)
+// which keeps fp32-level accuracy (dropped term ~2^-22).  G0s/G1s are G0/G1 with rows permuted into the
+// storage (scrambled) order of the field, so no position lookups are needed.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// C[M x N] += A[M x K] * B[K x N] for one 16 x (8*NT) warp tile.  A(row, col) = Aptr[row*ars + col*acs] (rows
+// clamped to M-1), B(k, n) = Bptr[k*brs + n] (the caller pads B with zero rows up to a multiple of 8).
+template <int NT>
+__device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float* Aptr, int ars, int acs, int M, int K,
+                                                 const float* Bptr, int brs, int m0, int n0, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = min(m0 + g, M - 1), r1 = min(m0 + g + 8, M - 1);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        const int ka = min(k0 + t, K - 1), kb = min(k0 + t + 4, K - 1);     // clamped: B is zero beyond K
+        unsigned ah[4], al[4];
+        tf32_split(Aptr[r0 * ars + ka * acs], ah[0], al[0]);
+        tf32_split(Aptr[r1 * ars + ka * acs], ah[1], al[1]);
+        tf32_split(Aptr[r0 * ars + kb * acs], ah[2], al[2]);
+        tf32_split(Aptr[r1 * ars + kb * acs], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            unsigned bh[2], bl[2];
+            tf32_split(Bptr[(k0 + t) * brs + n0 + 8 * j + g], bh[0], bl[0]);
+            tf32_split(Bptr[(k0 + t + 4) * brs + n0 + 8 * j + g], bh[1], bl[1]);
+            mma_tf32(c[j], al, bh);
+            mma_tf32(c[j], ah, bl);
+            mma_tf32(c[j], ah, bh);
+        }
+    }
+}
+
 template <typename T, int N0, int N1, int KT>
 __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     constexpr bool ST = N0 > 0;
@@ -180,8 +229,22 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     // constants shared by every path this (persistent) CTA processes
     stage(m.tw0, a.tw0, n0); stage(m.tw1, a.tw1, n1);
     stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
-    stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
-    stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
+    const bool mma = ST && std::is_same<T, float>::value && a.use_mma;
+    const int gp0 = a.o0p + 8, gp1 = a.o1p + 8;      // mma-path pitches of G0s / G1s (and of w1)
+    if (mma) {
+        // rows in storage order, zero rows up to a multiple of 8 (positions are read after the barrier below)
+        __syncthreads();
+        const int k0p = (n0 + 7) & ~7, k1p = (n1 + 7) & ~7;
+        for (int i = tid; i < k0p * gp0; i += nt) m.G0[i] = T(0);
+        for (int i = tid; i < k1p * gp1; i += nt) m.G1[i] = T(0);
+        for (int i = tid; i < (k0p - n0) * gp1; i += nt) m.w1[n0 * gp1 + i] = T(0);   // K padding of the 4b B operand
+        __syncthreads();
+        for (int i = tid; i < n0 * a.o0p; i += nt) { const int y = i / a.o0p, o = i - y * a.o0p; m.G0[m.pos0[y] * gp0 + o] = a.G0[i]; }
+        for (int i = tid; i < n1 * a.o1p; i += nt) { const int x = i / a.o1p, o = i - x * a.o1p; m.G1[m.pos1[x] * gp1 + o] = a.G1[i]; }
+    } else {
+        stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
+        stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
+    }
 
     for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
         const int fi = g % a.NF, pg = g / a.NF;
@@ -225,6 +288,53 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 for (int x = lane; x < n1; x += 32) s[y * W + x] = mk<T>(cabs_fast<T>(s[y * W + x]), T(0));
             __syncthreads();
         }
+        if constexpr (ST && std::is_same<T, float>::value) {
+          if (mma) {
+            const int nwarp = nt >> 5, wid = tid >> 5;
+            // 4a on tensor cores: W1 = U * G1s; warp task = (16-row tile, 16-column half)
+            {
+                const int mt = (n0 + 15) >> 4, nh = (a.o1p + 15) >> 4;
+                for (int task = wid; task < mt * nh; task += nwarp) {
+                    const int m0 = (task / nh) * 16, c0 = (task % nh) * 16;
+                    float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                    warp_gemm_3xtf32<2>(c, reinterpret_cast<const float*>(s), 2 * W, 2, n0, n1,
+                                        reinterpret_cast<const float*>(m.G1), gp1, m0, c0, lane);
+                    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int col = c0 + 8 * j + 2 * tq;
+                        if (m0 + gq < n0) { m.w1[(m0 + gq) * gp1 + col] = c[j][0]; m.w1[(m0 + gq) * gp1 + col + 1] = c[j][1]; }
+                        if (m0 + gq + 8 < n0) { m.w1[(m0 + gq + 8) * gp1 + col] = c[j][2]; m.w1[(m0 + gq + 8) * gp1 + col + 1] = c[j][3]; }
+                    }
+                }
+                // zero the K-padding rows of w1 read (clamped) by 4b - B operand must be finite; rows >= n0 unused
+            }
+            __syncthreads();
+            // 4b on tensor cores: S = G0s^T * W1; warp task = (16 output rows, 8 output columns)
+            {
+                float* ob = reinterpret_cast<float*>(a.out) + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+                const int mt = (a.o0p + 15) >> 4, ntl = (a.o1p + 7) >> 3;
+                for (int task = wid; task < mt * ntl; task += nwarp) {
+                    const int m0 = (task / ntl) * 16, c0 = (task % ntl) * 8;
+                    float c[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+                    // A(row = yo, col = q) = G0s[q][yo]; rows beyond o0p are clamped (their outputs are discarded)
+                    warp_gemm_3xtf32<1>(c, reinterpret_cast<const float*>(m.G0), 1, gp0, a.o0p, n0,
+                                        reinterpret_cast<const float*>(m.w1), gp1, m0, c0, lane);
+                    const int gq = lane >> 2, tq = lane & 3;
+                    const int col = c0 + 2 * tq;
+                    if (m0 + gq < a.o0) {
+                        if (col < a.o1) ob[(m0 + gq) * a.o1 + col] = c[0][0];
+                        if (col + 1 < a.o1) ob[(m0 + gq) * a.o1 + col + 1] = c[0][1];
+                    }
+                    if (m0 + gq + 8 < a.o0) {
+                        if (col < a.o1) ob[(m0 + gq + 8) * a.o1 + col] = c[0][2];
+                        if (col + 1 < a.o1) ob[(m0 + gq + 8) * a.o1 + col + 1] = c[0][3];
+                    }
+                }
+            }
+          }
+        }
+        if (!mma) {
         // 4a. horizontal low-pass + decimation + unpad: w1[row][xo] = sum_x U[row][x] * G1[x][xo]
         //     register tile: 4 (storage) rows x 4 outputs per thread, x restricted to the group's input window
         {
@@ -288,6 +398,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 }
             }
         }
+        }   // !mma
         // 5. forward 2-D FFT of U for the children of this path, natural-order store
         //    (static: DIT, scrambled spatial in -> natural Fourier out; generic: DIF + gather)
         if (a.spec_out) {
