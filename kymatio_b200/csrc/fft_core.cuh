@@ -1,21 +1,20 @@
 // fft_core.cuh - register-level mixed-radix FFT building blocks (host+device).
 //
-// Data-flow conventions used by every kernel in this library:
-//   * forward transform  = decimation-in-frequency (DIF), sign -, natural order in,
-//     "canonical scrambled" order out;
-//   * inverse transform  = decimation-in-time (DIT), sign +, canonical scrambled order
-//     in, natural order out (the exact transpose of the DIF flow graph).
-// Spatial-domain data is therefore always in natural order and Fourier-domain data
-// always in canonical scrambled order, so no permutation pass is ever needed on the
-// hot path; filters are permuted once when they are bound to a plan.
+// A 1-D transform of length n is a sequence of in-place radix passes over a line (Plan1).  Two data
+// flows are provided, each for either exponent sign:
+//   * DIF (decimation in frequency): natural-order input  -> "scrambled" (digit-reversed) output
+//   * DIT (decimation in time)     : scrambled input      -> natural-order output (the exact
+//                                    transpose of the DIF flow graph, same plan, same positions)
+// scramble_table() (plan_host.h) gives pos[f], the scrambled position of natural index f.
+// The kernels pair them so that no permutation pass is needed: inverse transforms run as DIF
+// (natural Fourier data in), forward transforms as DIT (natural Fourier data out); the spatial field in
+// between stays scrambled and is only consumed by order-agnostic ops (modulus) or through pos[].
+// Generic runtime-size kernels use the older pairing (DIT inverse / DIF forward with pos[] gathers).
 //
-// Canonical scrambled order for n = (odd primes r1 >= r2 >= ...) * 2^a: the DIF passes
-// run odd radices first, then the power-of-two part; a frequency f lands at
-//   pos(f) = (((f mod r1) * r2 + (f/r1 mod r2)) * ... ) * 2^a + bitrev_a(f / odd)
-// Property used everywhere: the 2^b aliases {u + c*n/2^b} of the Fourier-domain
-// periodisation (kymatio/scattering2d/backend/torch_backend.py:93-129) are ADJACENT in
-// this order, and summing them yields the child spectrum already in the child's own
-// canonical order.
+// Radices: 2, 4, 8, 16 (in-register radix-2 networks with compile-time twiddles) and odd primes
+// 3, 5, 7, 11, 13, 17 (x_n +- x_{R-n} pairing, compile-time constants); any other odd prime <= 127 goes
+// through a generic O(R^2) butterfly.  On sm_100+ complex add / subtract / multiply-by-real use the
+// packed fp32 instructions (FADD2 / FFMA2).
 #pragma once
 #include <type_traits>
 #include <utility>
@@ -28,11 +27,47 @@
 
 namespace sb {
 
-template <typename T> struct cx { T x, y; };
+template <typename T> struct alignas(2 * sizeof(T)) cx { T x, y; };
 
 template <typename T> SB_HD cx<T> mk(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
 template <typename T> SB_HD cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
 template <typename T> SB_HD cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+// acc + a * c with a complex and c real (the inner step of the odd-prime DFTs)
+template <typename T> SB_HD cx<T> fma_rc(cx<T> acc, cx<T> a, T c) { return mk<T>(acc.x + a.x * c, acc.y + a.y * c); }
+
+// ---------------------------------------------------------------------------
+// Blackwell packed fp32 (FADD2 / FFMA2, PTX add/sub/fma.f32x2, sm_100+): a complex number is one
+// (re, im) register pair, so complex add / subtract / multiply-by-real each issue ONE instruction
+// instead of two.  The kernels are issue-bound on the butterfly arithmetic, so this matters.
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+__device__ __forceinline__ unsigned long long sb_pk(cx<float> a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ cx<float> sb_upk(unsigned long long v) {
+    cx<float> r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ cx<float> operator+(cx<float> a, cx<float> b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(sb_pk(a)), "l"(sb_pk(b)));
+    return sb_upk(r);
+}
+__device__ __forceinline__ cx<float> operator-(cx<float> a, cx<float> b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(sb_pk(a)), "l"(sb_pk(b)));
+    return sb_upk(r);
+}
+__device__ __forceinline__ cx<float> fma_rc(cx<float> acc, cx<float> a, float c) {
+    unsigned long long r;
+    cx<float> cc; cc.x = c; cc.y = c;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(sb_pk(a)), "l"(sb_pk(cc)), "l"(sb_pk(acc)));
+    return sb_upk(r);
+}
+#endif
 template <typename T> SB_HD cx<T> cmul(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 template <typename T> SB_HD cx<T> cmulc(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
@@ -155,30 +190,31 @@ template <int R, int SIGN, typename T> SB_HD void dit_pow2(cx<T>* v) {
 // ---------------------------------------------------------------------------
 template <int R, int SIGN, typename T> SB_HD void dft_prime(cx<T>* v) {
     constexpr int H = (R - 1) / 2;
-    cx<T> a[H], b[H];
+    cx<T> a[H], bi[H];
     static_for<0, H>([&](auto n_) {
         constexpr int n = decltype(n_)::value;
         a[n] = v[n + 1] + v[R - 1 - n];
-        b[n] = v[n + 1] - v[R - 1 - n];
+        const cx<T> b = v[n + 1] - v[R - 1 - n];
+        bi[n] = mk<T>(-b.y, b.x);                       // i * (x_n - x_{R-n})
     });
-    cx<T> x0 = v[0];
+    const cx<T> x0 = v[0];
     cx<T> s0 = x0;
     static_for<0, H>([&](auto n_) { s0 = s0 + a[decltype(n_)::value]; });
     v[0] = s0;
     static_for<1, H + 1>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
-        cx<T> p = x0, q = mk<T>(T(0), T(0));
+        cx<T> p = x0, qi = mk<T>(T(0), T(0));
         static_for<0, H>([&](auto n_) {
             constexpr int n = decltype(n_)::value;
             constexpr int idx = ((n + 1) * k) % R;
             constexpr T c = T(Root<idx, R>::c);
-            constexpr T s = T(Root<idx, R>::s);
-            p.x += a[n].x * c; p.y += a[n].y * c;
-            q.x += b[n].x * s; q.y += b[n].y * s;
+            constexpr T sn = T(Root<idx, R>::s);
+            p = fma_rc(p, a[n], c);
+            qi = fma_rc(qi, bi[n], sn);
         });
-        // y_k = p + SIGN*i*q ; y_{R-k} = p - SIGN*i*q ; i*q = (-q.y, q.x)
-        if (SIGN > 0) { v[k] = mk<T>(p.x - q.y, p.y + q.x); v[R - k] = mk<T>(p.x + q.y, p.y - q.x); }
-        else          { v[k] = mk<T>(p.x + q.y, p.y - q.x); v[R - k] = mk<T>(p.x - q.y, p.y + q.x); }
+        // y_k = p + SIGN * i*q, y_{R-k} = p - SIGN * i*q  with qi = i*q
+        if (SIGN > 0) { v[k] = p + qi; v[R - k] = p - qi; }
+        else          { v[k] = p - qi; v[R - k] = p + qi; }
     });
 }
 
