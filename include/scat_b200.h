@@ -75,6 +75,18 @@ size_t scat_plan2d_workspace_bytes(const scat_plan2d* plan, int64_t batch);
 int  scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, void* workspace_dev,
                          size_t workspace_bytes, int64_t batch, void* stream);
 
+/* The second-order block of first-order scale j1 as a stand-alone differentiable operator (used by the
+ * autograd path): u1_dev = (batch*L, n0_j1, n1_j1) complex natural-order spectra of the first-order moduli
+ * (what `rfft(modulus(...))` returns at core/scattering2d.py:38-40); out = (batch, C2, out_h, out_w) with
+ * C2 = scat_plan2d_order2_channels(j1) channels ordered (theta1, j2, theta2) (core/scattering2d.py:55-83).
+ * backward overwrites gu1_dev (same shape as u1_dev) with the gradient; it accumulates with atomics, so
+ * results may differ in the last bits from run to run.  _channels returns 0 when the block is unavailable. */
+int32_t scat_plan2d_order2_channels(const scat_plan2d* plan, int32_t j1);
+int  scat_plan2d_order2_forward(scat_plan2d* plan, int32_t j1, const void* u1_dev, void* out_dev, int64_t batch,
+                                void* stream);
+int  scat_plan2d_order2_backward(scat_plan2d* plan, int32_t j1, const void* u1_dev, const void* gout_dev,
+                                 void* gu1_dev, int64_t batch, void* stream);
+
 /* eager primitives ----------------------------------------------------------------
  * One entry point per backend primitive of kymatio/scattering2d/core/scattering2d.py:3-9, on
  * contiguous device tensors in the torch backend's layout (real: trailing axis 1, complex: trailing

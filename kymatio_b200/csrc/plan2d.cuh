@@ -27,6 +27,10 @@ struct scat_plan2d {
                       cudaStream_t st) = 0;
     virtual size_t workspace_bytes(int64_t batch) const = 0;
     virtual void forward(const void* x, void* out, void* ws, size_t ws_bytes, int64_t batch, cudaStream_t st) = 0;
+    // second-order block of first-order scale j1 on caller-provided parent spectra (autograd building block)
+    virtual int order2_channels(int j1) const = 0;     // 0 when the fused block is not available for j1
+    virtual void order2_forward(int j1, const void* u1, void* out, int64_t batch, cudaStream_t st) = 0;
+    virtual void order2_backward(int j1, const void* u1, const void* gout, void* gu1, int64_t batch, cudaStream_t st) = 0;
 };
 
 namespace sb {
@@ -231,6 +235,36 @@ public:
             forward_chunk(static_cast<const T*>(x) + b0 * in_img, static_cast<T*>(out) + b0 * out_img,
                           static_cast<cx<T>*>(ws), B, st);
         }
+    }
+
+    // ---- second-order block as a stand-alone (differentiable) operator --------------------------------
+    int order2_channels(int j1) const override {
+        if (!bound_ || d_.max_order < 2 || j1 < 0 || j1 >= d_.J - 1) return 0;
+        for (int j2 = j1 + 1; j2 < d_.J; ++j2) if (!tile_ok_[j2]) return 0;
+        return d_.L * (d_.J - 1 - j1) * d_.L;
+    }
+    // u1: [batch*L][n0_j1][n1_j1] natural-order spectra of the first-order moduli at scale j1;
+    // out: [batch][order2_channels(j1)][o0][o1], channels ordered (theta1, j2, theta2) as in the full output
+    void order2_forward(int j1, const void* u1, void* out, int64_t batch, cudaStream_t st) override {
+        const int C2 = order2_channels(j1);
+        if (!C2) throw std::runtime_error("fused second-order block not available for this scale");
+        const int L = d_.L, nchild = (d_.J - 1 - j1) * L;
+        last_B_ = (int)batch;
+        for (int j2 = j1 + 1; j2 < d_.J; ++j2)
+            tile(static_cast<const cx<T>*>(u1), psi_ptrs(j2, j1), psi_supp(j2, j1), j1, j2, (int)batch * L, L,
+                 static_cast<T*>(out), L * L, L, (j2 - j1 - 1) * L, nchild, nullptr, "o2", st, C2);
+    }
+    // gu1 (same shape as u1) receives the gradient w.r.t. u1 (overwritten)
+    void order2_backward(int j1, const void* u1, const void* gout, void* gu1, int64_t batch, cudaStream_t st) override {
+        const int C2 = order2_channels(j1);
+        if (!C2) throw std::runtime_error("fused second-order block not available for this scale");
+        const int L = d_.L, nchild = (d_.J - 1 - j1) * L;
+        last_B_ = (int)batch;
+        SB_CUDA(cudaMemsetAsync(gu1, 0, (size_t)batch * L * fsize(j1) * sizeof(cx<T>), st));
+        for (int j2 = j1 + 1; j2 < d_.J; ++j2)
+            tile(static_cast<const cx<T>*>(u1), psi_ptrs(j2, j1), psi_supp(j2, j1), j1, j2, (int)batch * L, L,
+                 nullptr, L * L, L, (j2 - j1 - 1) * L, nchild, nullptr, "o2_bwd", st, C2,
+                 static_cast<const T*>(gout), static_cast<cx<T>*>(gu1));
     }
 
 private:
@@ -462,9 +496,11 @@ private:
     // fused tile: product/periodise from `parent` (resolution parent_res) with NF filters, ifft2,
     // modulus, spatial low-pass to `out`, optional fft2 to `spec_out`
     void tile(const cx<T>* parent, const T* const* filt, const int2* supp, int parent_res, int res, int Bp, int NF,
-              T* out, int PP, int NFch, int ch0, int chs, cx<T>* spec_out, const char* what, cudaStream_t st) {
+              T* out, int PP, int NFch, int ch0, int chs, cx<T>* spec_out, const char* what, cudaStream_t st,
+              int Kstride = -1, const T* gout = nullptr, cx<T>* gparent = nullptr) {
         TileArgs<T> a{};
         a.parent = parent; a.filt = filt; a.supp = supp; a.spec_out = spec_out; a.out = out;
+        a.gout = gout; a.gparent = gparent;
         a.P0 = lev_[parent_res].a0.n; a.P1 = lev_[parent_res].a1.n;
         a.k = 1 << (res - parent_res);
         a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n; a.W = a.n1 | 1; a.NF = NF;
@@ -477,14 +513,16 @@ private:
         a.y0lo = F.y0lo; a.y0cnt = F.y0cnt; a.x1lo = F.x1lo; a.x1cnt = F.x1cnt;
         a.kl = 1 << (d_.J - res);
         a.o0 = o0_; a.o1 = o1_; a.o0p = o0p(); a.o1p = o1p();
-        a.PP = PP; a.NFch = NFch; a.ch0 = ch0; a.chs = chs; a.K = K_;
+        a.PP = PP; a.NFch = NFch; a.ch0 = ch0; a.chs = chs; a.K = Kstride > 0 ? Kstride : K_;
         // dense (full-circle) low-pass windows go to the tensor cores (float static instances only)
-        a.use_mma = (use_mma_ && sizeof(T) == 4 && F.x1cnt >= a.n1 && F.y0cnt >= a.n0 && a.o1p % 16 == 0 && a.o0p % 16 == 0) ? 1 : 0;
+        a.use_mma = (!gparent && !spec_out && use_mma_ && sizeof(T) == 4 && F.x1cnt >= a.n1 && F.y0cnt >= a.n0 &&
+                     a.o1p % 16 == 0 && a.o0p % 16 == 0) ? 1 : 0;
         const size_t smem = tile_smem_layout<T>(a, nullptr);
         const int G = Bp * NF;
         a.G = G;
         bool is_static = false;
-        TileKernel<T> kern = tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
+        TileKernel<T> kern = gparent ? tile_bwd_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static)
+                                     : tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
         // threads: every butterfly pass distributes (lines x butterflies) work items over the CTA in rounds;
         // pick the warp count that wastes the fewest (cost-weighted) partially filled rounds
         const int cap = std::min(tile_threads_cap_, is_static ? tile_max_threads(a.n0, a.n1) : tile_max_threads(0, 0));

@@ -93,6 +93,21 @@ int scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, voi
     });
 }
 
+int32_t scat_plan2d_order2_channels(const scat_plan2d* plan, int32_t j1) { return plan ? plan->order2_channels(j1) : 0; }
+int scat_plan2d_order2_forward(scat_plan2d* plan, int32_t j1, const void* u1_dev, void* out_dev, int64_t batch, void* stream) {
+    return guarded([&] {
+        if (!plan) throw std::runtime_error("null plan");
+        plan->order2_forward(j1, u1_dev, out_dev, batch, static_cast<cudaStream_t>(stream));
+    });
+}
+int scat_plan2d_order2_backward(scat_plan2d* plan, int32_t j1, const void* u1_dev, const void* gout_dev, void* gu1_dev,
+                                int64_t batch, void* stream) {
+    return guarded([&] {
+        if (!plan) throw std::runtime_error("null plan");
+        plan->order2_backward(j1, u1_dev, gout_dev, gu1_dev, batch, static_cast<cudaStream_t>(stream));
+    });
+}
+
 // ---------------------------------------------------------------- eager primitives
 #define SB_DISPATCH(dtype, CALL)                                                     \
     do {                                                                             \

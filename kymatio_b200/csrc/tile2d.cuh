@@ -32,10 +32,13 @@ template <typename T> struct TileArgs {
     int PP, NFch, ch0, chs, K;
     int G;                                 // number of paths; CTAs are persistent and stride over them
     int use_mma;                           // 1: dense low-pass products on the tensor cores (3xTF32 mma.sync)
+    // backward kernel only: gradient w.r.t. the output planes (same layout / channel mapping as `out`) and the
+    // parent-gradient accumulator [NPAR][P0][P1] (atomically added to; zeroed by the caller)
+    const T* gout; cx<T>* gparent;
 };
 
 template <typename T> struct TileSmem {
-    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1;
+    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1; T* gs;
 };
 template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
     size_t off = 0;
@@ -48,6 +51,7 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     const size_t o_g0 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
     const size_t o_g1 = take(sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
     const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
+    const size_t o_gs = take(sizeof(T) * (size_t)a.o0p * a.o1p);     // backward: staged output-plane gradient
     if (L) {
 #ifdef __CUDA_ARCH__
         unsigned char* base = dyn_smem<unsigned char>();
@@ -57,6 +61,7 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
         L->w1 = reinterpret_cast<T*>(base + o_w1);
         L->G0 = reinterpret_cast<T*>(base + o_g0); L->G1 = reinterpret_cast<T*>(base + o_g1);
         L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
+        L->gs = reinterpret_cast<T*>(base + o_gs);
 #endif
     }
     return off;
@@ -430,10 +435,139 @@ __global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, 
     tile_body<T, N0, N1, KT>(a);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backward of one leaf path, same tile, same persistent structure:
+//   u      = ifft2(periodise_k(parent * filt) * scale)            recomputed, no modulus
+//   gA     = G0 . gS . G1^T                                        adjoint of low-pass + decimation + unpad
+//   gu     = gA * u / |u|   (0 where |u| = 0)                      ModulusStable.backward, backend/torch_backend.py:85-96
+//   gV     = F(gu)                                                 adjoint of the unnormalised inverse transform
+//   gparent[r + c*n0][e + d*n1] += scale * filt[..] * gV[r][e]     adjoint of periodisation and filter multiply
+// The last step uses atomic adds: the children of one parent run in different CTAs.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int N0, int N1, int KT>
+__device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
+    constexpr bool ST = N0 > 0;
+    const int n0 = ST ? N0 : a.n0, n1 = ST ? N1 : a.n1;
+    const int W = ST ? (N1 | 1) : a.W;
+    const int k = KT > 0 ? KT : a.k;
+    const int wp = a.o1p + 4;
+    TileSmem<T> m;
+    tile_smem_layout(a, &m);
+    cx<T>* s = m.tile;
+    const int tid = flat_tid(), nt = flat_nt();
+    const int lane = tid & 31;
+
+    stage(m.tw0, a.tw0, n0); stage(m.tw1, a.tw1, n1);
+    stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
+    stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
+    stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
+
+    for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
+        const int fi = g % a.NF, pg = g / a.NF;
+        const int b = g / a.PP, path = g - b * a.PP;
+        const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
+        stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
+        {
+            const T* gb = a.gout + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+            for (int i = tid; i < a.o0p * a.o1p; i += nt) {
+                const int yo = i / a.o1p, xo = i - yo * a.o1p;
+                m.gs[i] = (yo < a.o0 && xo < a.o1) ? gb[yo * a.o1 + xo] : T(0);
+            }
+        }
+        __syncthreads();
+        const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
+        const T* __restrict__ fb = a.filt[fi];
+        const int P1 = a.P1;
+        // 1. recompute the product + periodise
+        if ((n1 & 3) == 0 && (P1 & 3) == 0) {
+            const int per_row = n1 >> 2, items = n0 * per_row;
+            for (int it = tid; it < items; it += nt) {
+                const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
+                tile_load_item<T, 4, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
+            }
+        } else {
+            const int per_row = n1 >> 1, items = n0 * per_row;
+            for (int it = tid; it < items; it += nt) {
+                const int r0 = it / per_row, e0 = 2 * (it - r0 * per_row);
+                tile_load_item<T, 2, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
+            }
+        }
+        // 3a. T[row][xo] = sum_yo G0[y][yo] * gS[yo][xo]   (row = storage row of y) - independent of the tile
+        for (int it = tid; it < n0 * a.o1p; it += nt) {
+            const int y = it / a.o1p, xo = it - y * a.o1p;
+            T acc = T(0);
+            for (int yo = 0; yo < a.o0; ++yo) acc += m.G0[y * a.o0p + yo] * m.gs[yo * a.o1p + xo];
+            m.w1[(ST ? m.pos0[y] : y) * wp + xo] = acc;
+        }
+        __syncthreads();
+        // 2. inverse 2-D FFT (no modulus): static -> scrambled spatial order, generic -> natural
+        if constexpr (ST) {
+            slab_fft_s<N1, false, +1, (N1 | 1), 1, T>(s, N0, m.tw1);
+            slab_fft_s<N0, false, +1, 1, (N1 | 1), T>(s, N1, m.tw0);
+        } else {
+            slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
+            slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
+        }
+        // 3b. gu = (sum_xo T[row][xo] G1[x][xo]) * u / |u|
+        for (int it = tid; it < n0 * n1; it += nt) {
+            const int q = it / n1, x = it - q * n1;
+            const T* __restrict__ tr = m.w1 + q * wp;
+            const T* __restrict__ gr = m.G1 + x * a.o1p;
+            T gA = T(0);
+            for (int xo = 0; xo < a.o1; ++xo) gA += tr[xo] * gr[xo];
+            const int idx = q * W + (ST ? m.pos1[x] : x);
+            const cx<T> v = s[idx];
+            const T mag = sqrt(v.x * v.x + v.y * v.y);
+            const T sc = mag > T(0) ? gA / mag : T(0);
+            s[idx] = mk<T>(v.x * sc, v.y * sc);
+        }
+        __syncthreads();
+        // 4. forward 2-D FFT: static DIT(-) -> natural Fourier order; generic DIF -> scrambled (read through pos)
+        if constexpr (ST) {
+            slab_fft_s<N0, true, -1, 1, (N1 | 1), T>(s, N1, m.tw0);
+            slab_fft_s<N1, true, -1, (N1 | 1), 1, T>(s, N0, m.tw1);
+        } else {
+            slab_fft<false, T>(s, n0, W, 1, a.plan1, m.tw1);
+            slab_fft<false, T>(s, n1, 1, W, a.plan0, m.tw0);
+        }
+        // 5. adjoint of periodise + filter multiply, accumulated into the parent gradient
+        {
+            cx<T>* gp = a.gparent + (size_t)pg * a.P0 * a.P1;
+            for (int it = tid; it < n0 * n1; it += nt) {
+                const int r = it / n1, e = it - r * n1;
+                const cx<T> gv = scal(ST ? s[r * W + e] : s[m.pos0[r] * W + m.pos1[e]], a.scale);
+                for (int c = 0; c < k; ++c) {
+                    const int R = r + c * n0;
+                    const int2 sp = m.supp[R];
+                    if (sp.y == 0) continue;
+                    for (int d = 0; d < k; ++d) {
+                        const int C = e + d * n1;
+                        int rel = C - sp.x;
+                        if (rel < 0) rel += P1;
+                        if (rel < sp.y) {
+                            const T f = fb[(size_t)R * P1 + C];
+                            cx<T>* dst = gp + (size_t)R * P1 + C;
+                            atomicAdd(&dst->x, gv.x * f);
+                            atomicAdd(&dst->y, gv.y * f);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int N0, int N1, int KT>
+__global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, N1)) k2d_tile_bwd(TileArgs<T> a) {
+    tile_bwd_body<T, N0, N1, KT>(a);
+}
+
 // specialised instances are compiled in tile_inst_*.cu; returns the kernel for (n0, n1, k) or the
 // generic one
 template <typename T> using TileKernel = void (*)(TileArgs<T>);
 template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bool* is_static);
+template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k, bool* is_static);
 template <typename T> void tile_kernels_enable_smem();
 
 }  // namespace sb

@@ -24,16 +24,34 @@ template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bo
     return k2d_tile<T, 0, 0, 0>;
 }
 
+// backward instances: the generic alias-count version (K = 0) per static size keeps compile time in check
+template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k, bool* is_static) {
+    if (is_static) *is_static = true;
+    if (n0 == n1) {
+#define SB_CASE(N) if (n0 == N) return k2d_tile_bwd<T, N, N, 0>;
+        SB_TILE_SIZES(SB_CASE)
+#undef SB_CASE
+    }
+    if (is_static) *is_static = false;
+    return k2d_tile_bwd<T, 0, 0, 0>;
+}
+
 template <typename T> void tile_kernels_enable_smem() {
 #define SB_EN(N) enable_big_smem(k2d_tile<T, N, N, 2>); enable_big_smem(k2d_tile<T, N, N, 4>); \
                  enable_big_smem(k2d_tile<T, N, N, 0>);
     SB_TILE_SIZES(SB_EN)
 #undef SB_EN
     enable_big_smem(k2d_tile<T, 0, 0, 0>);
+#define SB_ENB(N) enable_big_smem(k2d_tile_bwd<T, N, N, 0>);
+    SB_TILE_SIZES(SB_ENB)
+#undef SB_ENB
+    enable_big_smem(k2d_tile_bwd<T, 0, 0, 0>);
 }
 
 template TileKernel<float> tile_kernel_lookup<float>(int, int, int, bool*);
 template TileKernel<double> tile_kernel_lookup<double>(int, int, int, bool*);
+template TileKernel<float> tile_bwd_kernel_lookup<float>(int, int, int, bool*);
+template TileKernel<double> tile_bwd_kernel_lookup<double>(int, int, int, bool*);
 template void tile_kernels_enable_smem<float>();
 template void tile_kernels_enable_smem<double>();
 

@@ -94,6 +94,26 @@ class Engine2D:
                 ctypes.c_void_p(stream)))
         return out
 
+    # -- second-order block (autograd building block) --------------------------------------
+    def order2_channels(self, j1):
+        return int(self.lib.scat_plan2d_order2_channels(self._plan, int(j1)))
+
+    def order2_forward(self, j1, u1, batch):
+        out = torch.empty((batch, self.order2_channels(j1), self.out_h, self.out_w), dtype=self.dtype, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_order2_forward(self._plan, int(j1), u1.data_ptr(), out.data_ptr(), int(batch),
+                                                           ctypes.c_void_p(stream)))
+        return out
+
+    def order2_backward(self, j1, u1, gout, batch):
+        gu1 = torch.empty_like(u1)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_order2_backward(self._plan, int(j1), u1.data_ptr(), gout.data_ptr(),
+                                                            gu1.data_ptr(), int(batch), ctypes.c_void_p(stream)))
+        return gu1
+
     # -- backward --------------------------------------------------------------------
     def backward(self, x, grad_out):
         """Gradient of ``forward`` w.r.t. x: the cascade is recomputed on differentiable ops whose forward and
@@ -112,7 +132,7 @@ class Engine2D:
         for b0 in range(0, x.shape[0], chunk):
             with torch.enable_grad():
                 xc = x[b0:b0 + chunk].detach().requires_grad_(True)
-                y = eager_scattering2d(xc, g["J"], g["L"], g["max_order"], pads, phi, psi)
+                y = eager_scattering2d(xc, g["J"], g["L"], g["max_order"], pads, phi, psi, eng=self)
                 gx[b0:b0 + chunk] = torch.autograd.grad(y, xc, grad_out[b0:b0 + chunk])[0]
         return gx
 

@@ -170,6 +170,23 @@ class PadReflect(torch.autograd.Function):
         return gx, None
 
 
+class Order2(torch.autograd.Function):
+    """All second-order paths below first-order scale j1, fused: U1 (B*L, n0, n1, 2) -> (B, C2, o0, o1).
+    Forward and backward are one tile-kernel launch per (j1, j2) pair (csrc/tile2d.cuh)."""
+
+    @staticmethod
+    def forward(ctx, U1, eng, j1, batch):
+        U1 = U1.contiguous()
+        ctx.eng, ctx.j1, ctx.batch = eng, j1, batch
+        ctx.save_for_backward(U1)
+        return eng.order2_forward(j1, U1, batch)
+
+    @staticmethod
+    def backward(ctx, g):
+        (U1,) = ctx.saved_tensors
+        return ctx.eng.order2_backward(ctx.j1, U1, g.contiguous(), ctx.batch), None, None, None
+
+
 def _to_complex(x):
     return torch.stack([x, torch.zeros_like(x)], dim=-1)
 
@@ -180,12 +197,14 @@ def _low(U, phi_level, k):
     return Fft2.apply(Z, True)[..., 1:-1, 1:-1, 0]
 
 
-def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels):
+def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=None):
     """Angle-batched restatement of kymatio/scattering2d/core/scattering2d.py:14-86 on differentiable ops.
 
     x: (B, M, N) CUDA; pads: (top, bottom, left, right) or None when pre-padded;
     phi_levels: J tensors (n0, n1[, 1]); psi_levels: flattened in registration order.
     Returns (B, K, M/2^J, N/2^J) in the reference's channel order.
+    With ``eng`` (an Engine2D bound to the same filters) the second-order block of every first-order scale
+    runs as the fused tile kernels (forward and backward); orders 0 and 1 stay on the per-op graph.
     """
     B = x.shape[0]
     phi = [p.reshape(p.shape[0], p.shape[1]) for p in phi_levels]
@@ -212,6 +231,9 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels):
         s1 = _low(U1, phi[j1], 2 ** (J - j1))
         S1.append(s1.reshape((B, L) + tuple(s1.shape[1:])))
         if max_order < 2 or j1 >= J - 1:
+            continue
+        if eng is not None and eng.order2_channels(j1) > 0:
+            S2.append(Order2.apply(U1, eng, j1, B))         # fused second-order block (forward and backward)
             continue
         per_j2 = []
         for j2 in range(j1 + 1, J):
