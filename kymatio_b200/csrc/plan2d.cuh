@@ -180,7 +180,7 @@ public:
         if (n_phi != d_.J) throw std::runtime_error("expected J low-pass levels");
         if (n_psi != n_psi_expected_) throw std::runtime_error("unexpected number of band-pass levels");
         cbuf_ = static_cast<unsigned char*>(const_dev);
-        const double supp_thr = 1e-7;
+        const double supp_thr = sizeof(T) == 8 ? 1e-16 : 1e-7;   // relative to max|filter|
         std::vector<T> host;
         auto fetch = [&](const void* dev, int res) {
             host.resize(fsize(res));
@@ -295,7 +295,9 @@ private:
             for (int v = 0; v < n1; ++v)
                 resid = std::max(resid, std::fabs((double)f[(size_t)u * n1 + v] * c -
                                                   (double)f[(size_t)u * n1] * (double)f[v]));
-        if (resid > 4e-6 * c * c) return;   // not separable to float32 rounding: keep the Fourier low-pass
+        // separable to the working precision?  (float32-generated filters are rank-1 only to ~2.5e-7, so the
+        // float64 instantiation keeps the exact Fourier low-pass unless the filters are separable to 1e-12)
+        if (resid > (sizeof(T) == 8 ? 1e-12 : 4e-6) * c * c) return;
         const double tau = 6.283185307179586476925286766559;
         // spatial taps a[t] (circular), truncated where |a| <= 1e-6 max|a|, expanded into the dense
         // matrix G[x][o] = a[(kl*(o+1) - x) mod n] (zero outside the kept radius / for padded columns)
@@ -311,7 +313,7 @@ private:
             }
             int R = 0;
             for (int y = 0; y < n; ++y)
-                if (std::fabs(a[y]) > 1e-6 * mx) R = std::max(R, std::min(y, n - y));
+                if (std::fabs(a[y]) > (sizeof(T) == 8 ? 1e-14 : 1e-6) * mx) R = std::max(R, std::min(y, n - y));
             const bool full = 2 * R + 1 >= n;
             const int tcnt = full ? n : 2 * R + 1, tlo = full ? 0 : -R;
             // group of outputs 4g..4g+3 reads inputs kl*(4g+1) - tlo - tcnt + 1 ... kl*(4g+4) - tlo

@@ -56,3 +56,32 @@ def test_zero_input_gradient_is_finite():
     x = torch.zeros(1, 16, 16, device="cuda", requires_grad=True)
     S(x).sum().backward()
     assert torch.isfinite(x.grad).all()
+
+
+def test_fused_order2_block_matches_per_op_graph():
+    """Order2 (fused tile forward + backward) vs the same block on the per-op graph: values and gradients."""
+    from kymatio_b200 import Scattering2D
+    from kymatio_b200.ops2d import eager_scattering2d
+    for (J, shape, L, dt, tol) in [(3, (64, 64), 8, torch.float32, 2e-5), (2, (24, 40), 4, torch.float64, 1e-9),
+                                   (3, (256, 256), 8, torch.float32, 2e-5)]:
+        S = Scattering2D(J, shape, L=L).cuda()
+        if dt == torch.float64:
+            S = S.double()
+        B = 2
+        x = torch.randn(B, *shape, device="cuda", dtype=dt)
+        S(x)                                              # binds the filters
+        eng = S._engine(dt, x.device)
+        # float64 keeps the exact Fourier low-pass (float32-born filters are rank-1 only to 2.5e-7): no fused block
+        assert eng.order2_channels(0) == (L * (J - 1) * L if dt == torch.float32 else 0)
+        phi, psi = S.load_filters()
+        t, l = (eng.Mp - shape[0]) // 2, (eng.Np - shape[1]) // 2
+        pads = (t, eng.Mp - shape[0] - t, l, eng.Np - shape[1] - l)
+        w = torch.randn(B, eng.K, eng.out_h, eng.out_w, device="cuda", dtype=dt)
+        outs, grads = [], []
+        for e in (None, eng):
+            xi = x.clone().requires_grad_(True)
+            y = eager_scattering2d(xi, J, L, 2, pads, phi, psi, eng=e)
+            (y * w).sum().backward()
+            outs.append(y.detach()); grads.append(xi.grad)
+        assert_parity(outs[1].cpu().numpy(), outs[0].cpu().numpy(), tol=tol, what="order2 fwd")
+        assert_parity(grads[1].cpu().numpy()[:, None], grads[0].cpu().numpy()[:, None], tol=10 * tol, what="order2 bwd")
