@@ -590,14 +590,24 @@ private:
                      need_spec ? U1 : nullptr, need_spec ? "o1p" : "o1", st);
             } else {
                 const T sc1 = T(1) / (T(1 << j1) * T(1 << j1) * T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
-                row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), U1, 0, j1, B, L, sc1, st);
                 // static chains emit the phi-product folded along the row while Û1 is still in shared memory
                 const bool fold = low_tile_ && chain_static(j1) && lev_[j1].a1.n % m1_ == 0;
-                if (hermitian_ok(j1)) {
-                    hermitian_chain(U1, j1, B * L, st, fold ? RF : nullptr);
-                } else {
-                    col_pass<COL_INV_MOD_FWD>(U1, j1, B * L, st);
-                    row_pass<false>(U1, j1, B * L, st, fold ? RF : nullptr);
+                // the three passes hand a full field per path to each other: run them over sub-batches whose
+                // intermediates (L * field bytes per image) stay resident in L2 between the kernels
+                const size_t img_bytes = (size_t)L * fsize(j1) * sizeof(cx<T>);
+                int sub = B;
+                if (l2_sub_bytes_ > 0) sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, l2_sub_bytes_ / img_bytes));
+                for (int b0 = 0; b0 < B; b0 += sub) {
+                    const int nb = std::min(sub, B - b0);
+                    cx<T>* u1 = U1 + (size_t)b0 * L * fsize(j1);
+                    row_prod(U0 + (size_t)b0 * fsize(0), psi_ptrs(j1, 0), psi_supp(j1, 0), u1, 0, j1, nb, L, sc1, st);
+                    cx<T>* rf = fold ? RF + (size_t)b0 * L * lev_[j1].a0.n * m1_ : nullptr;
+                    if (hermitian_ok(j1)) {
+                        hermitian_chain(u1, j1, nb * L, st, rf);
+                    } else {
+                        col_pass<COL_INV_MOD_FWD>(u1, j1, nb * L, st);
+                        row_pass<false>(u1, j1, nb * L, st, rf);
+                    }
                 }
                 low_pass(fold ? RF : U1, j1, out, B, L, L, 1 + j1 * L, 0, TL, st, fold);
             }
@@ -641,6 +651,7 @@ private:
     int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 576);
     int num_sms_ = 148;
     bool use_mma_ = env_int("SCAT_B200_NO_MMA", 0) == 0;
+    size_t l2_sub_bytes_ = (size_t)env_int("SCAT_B200_L2_SUB_MB", 0) << 20;   // 0 disables sub-batching
     size_t ws_u0_ = 0, ws_u1_ = 0, ws_u2_ = 0, ws_low_ = 0, ws_rf_ = 0, per_img_ = 0;
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;
