@@ -38,7 +38,7 @@ template <typename T> struct TileArgs {
 };
 
 template <typename T> struct TileSmem {
-    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1; T* gs;
+    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1; T* gs; int2* xr;
 };
 template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
     size_t off = 0;
@@ -52,6 +52,7 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     const size_t o_g1 = take(sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
     const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
     const size_t o_gs = take(sizeof(T) * (size_t)a.o0p * a.o1p);     // backward: staged output-plane gradient
+    const size_t o_xr = take(sizeof(int2) * (size_t)a.n1);           // backward: nonzero output range of each G1 row
     if (L) {
 #ifdef __CUDA_ARCH__
         unsigned char* base = dyn_smem<unsigned char>();
@@ -62,6 +63,7 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
         L->G0 = reinterpret_cast<T*>(base + o_g0); L->G1 = reinterpret_cast<T*>(base + o_g1);
         L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
         L->gs = reinterpret_cast<T*>(base + o_gs);
+        L->xr = reinterpret_cast<int2*>(base + o_xr);
 #endif
     }
     return off;
@@ -461,6 +463,15 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
     stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
     stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
     stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
+    __syncthreads();
+    // the low-pass is banded: row x of G1 touches only outputs [first, last] (a few of them, all for the
+    // full-circle level); found once per persistent CTA
+    for (int x = tid; x < n1; x += nt) {
+        int first = a.o1, last = -1;
+        for (int xo = 0; xo < a.o1; ++xo)
+            if (m.G1[x * a.o1p + xo] != T(0)) { if (first == a.o1) first = xo; last = xo; }
+        m.xr[x] = make_int2(first, last);
+    }
 
     for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
         const int fi = g % a.NF, pg = g / a.NF;
@@ -514,7 +525,8 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             const T* __restrict__ tr = m.w1 + q * wp;
             const T* __restrict__ gr = m.G1 + x * a.o1p;
             T gA = T(0);
-            for (int xo = 0; xo < a.o1; ++xo) gA += tr[xo] * gr[xo];
+            const int2 rng = m.xr[x];
+            for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gr[xo];
             const int idx = q * W + (ST ? m.pos1[x] : x);
             const cx<T> v = s[idx];
             const T mag = sqrt(v.x * v.x + v.y * v.y);
