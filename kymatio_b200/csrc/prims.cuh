@@ -180,7 +180,10 @@ void fft2d_exec(const void* const_dev, const void* in, void* out, int64_t G, int
     const unsigned char* cb = static_cast<const unsigned char*>(const_dev);
     const SlabCfg rc = slab_cfg(t.p1, n0, sizeof(cx<T>), sizeof(int));
     const SlabCfg cc = slab_cfg(t.p0, n1, sizeof(cx<T>), sizeof(int));
-    const StreamKernels<T> kr = stream_kernels_lookup<T>(n1, false), kc = stream_kernels_lookup<T>(n0, false);
+    // compile-time specialised instances keep natural order on both sides for the column passes and the inverse
+    // row pass (only the static FORWARD row pass belongs to the scrambled-row chain of plan2d.cuh)
+    const StreamKernels<T> kr = stream_kernels_lookup<T>(n1, inverse && rc.lines == kSLines && rc.LP == kSLP);
+    const StreamKernels<T> kc = stream_kernels_lookup<T>(n0, cc.lines == kSLines && cc.LP == kSLP);
     RowArgs<T> ra{};
     ra.in = static_cast<const cx<T>*>(in); ra.out = static_cast<cx<T>*>(out); ra.n0 = n0; ra.n1 = n1;
     ra.lines = rc.lines; ra.LP = rc.LP; ra.plan = t.p1;
