@@ -28,8 +28,8 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -140,7 +140,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -157,9 +157,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.rows:
-            if t < t_begin or t > t_end + 0.1:
-                continue
+        in_window = [(t, l) for t, l in self.rows if t_begin <= t <= t_end + 0.1]
+        # a very short timed region can fall between two samples: then use the samples taken since the
+        # sampler started (warm-up included, the GPU is under the same load)
+        for t, line in (in_window or self.rows):
             parts = [p.strip() for p in line.split(",")]
             try:
                 sm.append(float(parts[0])); mx = float(parts[1])
@@ -204,6 +205,7 @@ def run_b200_arm(args):
     x = torch.randn(B, *SHAPE, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    sampler = ClockSampler(local)
     with torch.no_grad():
         for _ in range(max(3, args.warmup)):
             y = S(x)
@@ -212,7 +214,6 @@ def run_b200_arm(args):
         # ---- device-resident timing: K steps, L2 flushed between steps (not timed) ---------------
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(args.steps)]
-        sampler = ClockSampler(local)
         n0 = _lib.launch_count()
         t_begin = time.perf_counter()
         barrier()
