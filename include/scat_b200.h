@@ -128,6 +128,39 @@ int  scat_pad1d(const void* x_dev, void* out_dev, int64_t G, int32_t N, int32_t 
 int  scat_subsample_fourier1d(const void* in_dev, void* out_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
                               void* stream);
 
+/* fused 1-D path (kymatio/scattering1d/core/scattering1d.py:40-107), float32 ------------------------------
+ * The cascade (which paths, filters, channels) is driven by the host engine (kymatio_b200/engine1d.py); the
+ * library exposes one entry point per fused kernel.  A path transform of length N = Na*Nb (powers of two,
+ * 16 <= N <= 2^18) is three passes: col_prod -> row_mod -> col_fwd (parents) or col_prod -> row_mod(leaf)
+ * (paths whose spectrum only feeds the low-pass), then finish.  `algo_bytes` is the caller's algorithmic byte
+ * count of the launch (only recorded by scat_timing_*).  tables_dev / fin_tables_dev are caller-owned. */
+int    scat1d_split(int32_t N, int32_t* Na, int32_t* Nb);
+size_t scat1d_tables_bytes(int32_t N);
+int    scat1d_tables_init(void* tables_dev, int32_t N, void* stream);
+size_t scat1d_fin_tables_bytes(int32_t M);
+int    scat1d_fin_tables_init(void* tables_dev, int32_t M, void* stream);
+/* Y[g] = twiddled column-inverse of periodise_{Npar/N}(parent(g) * filt[g % NI]) / (N k); path g = b*NI + i reads the
+ * natural-order parent spectrum at parent_dev + b*ps_b + i*ps_i (complex elements); filt_ptrs_dev: device array of NI
+ * pointers to real filters of length Npar (cdgmm + subsample_fourier + first half of ifft,
+ * core/scattering1d.py:61-63,92-94); supp_dev: NI (start, len) int32 pairs, circular support of each filter */
+int    scat1d_col_prod(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
+                       const void* supp_dev, void* y_dev, int64_t G, int32_t NI, int32_t Npar, int32_t N, double algo_bytes,
+                       void* stream);
+/* second half of ifft, modulus, first half of rfft (core/scattering1d.py:63-69,94-100), in place on y_dev;
+ * part_dev != NULL: leaf mode, writes the Fc lowest bins of the spectrum as ceil(Na/16) partial sums per path,
+ * part_dev[(g*ceil(Na/16) + c)*Fc + f] */
+int    scat1d_row_mod(const void* tables_dev, void* y_dev, int64_t G, int32_t N, void* part_dev, int32_t Fc, double algo_bytes,
+                      void* stream);
+/* second half of rfft: natural-order spectrum (G, N) out */
+int    scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t G, int32_t N, double algo_bytes,
+                      void* stream);
+/* cdgmm(phi) -> subsample_fourier(N/M) -> irfft -> unpad[i0:i0+W] (core/scattering1d.py:72-77,101-105 and
+ * frontend/base_frontend.py:137-139) from the Fc lowest bins of each path's spectrum, X[f] = sum_{q<nparts}
+ * src[g*ss_g + q*ss_part + f]; writes out[b*os_b + chan[i]*W + n], g = b*NI + i */
+int    scat1d_finish(const void* fin_tables_dev, const void* src_dev, int64_t ss_g, int64_t ss_part, int32_t nparts,
+                     const void* phi_dev, int32_t N, int32_t Fc, int32_t M, void* out_dev, int64_t os_b, const void* chan_dev,
+                     int32_t NI, int64_t G, int32_t i0, int32_t W, double algo_bytes, void* stream);
+
 /* 3-D primitives (kymatio/scattering3d/backend/torch_backend.py:73-151) --------------------------------
  * natural-order complex 3-D FFT on (G, M, N, O, 2) - replaces torch.fft.fftn / ifftn (torch_backend.py:39-40) */
 size_t scat_fft3d_const_bytes(int32_t M, int32_t N, int32_t O, int32_t dtype);

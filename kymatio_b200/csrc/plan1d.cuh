@@ -1,0 +1,169 @@
+// plan1d.cuh - host side of the fused 1-D kernels: the N = NA*NB split, the per-length constant tables
+// and one launcher per kernel of kernels1d.cuh.  The cascade itself (which paths, which filters, which
+// channel) is driven by kymatio_b200/engine1d.py through the scat1d_* entry points of include/scat_b200.h.
+#pragma once
+#include "common.cuh"
+#include "kernels1d.cuh"
+#include "plan_host.h"
+
+namespace sb {
+
+struct Split1d { int n, Na, Nb, lb, nhi, nlo; };
+inline Split1d split1d(int N) {
+    if (N < 16 || N > (1 << 18) || (N & (N - 1))) throw std::runtime_error("fused 1-D transform length must be a power of two in [16, 2^18], got " + std::to_string(N));
+    Split1d s{};
+    s.n = ct_log2(N);
+    const int lgb = std::max(4, (s.n + 1) / 2);
+    s.Nb = 1 << lgb; s.Na = N / s.Nb;
+    s.lb = (s.n + 1) / 2; s.nlo = 1 << s.lb; s.nhi = N >> s.lb;
+    return s;
+}
+
+// [twA | twB | hi | lo | invA]
+struct Tables1d {
+    Split1d sp; size_t twa, twb, hi, lo, inva, bytes;
+    explicit Tables1d(int N) : sp(split1d(N)) {
+        size_t off = 0;
+        auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+        twa = take((size_t)sp.Na * sizeof(cx<float>)); twb = take((size_t)sp.Nb * sizeof(cx<float>));
+        hi = take((size_t)sp.nhi * sizeof(cx<float>)); lo = take((size_t)sp.nlo * sizeof(cx<float>));
+        inva = take((size_t)sp.Na * sizeof(int));
+        bytes = off;
+    }
+};
+inline void tables1d_init(void* dev, int N, cudaStream_t st) {
+    Tables1d t(N);
+    std::vector<unsigned char> h(t.bytes, 0);
+    auto twa = twiddle_table<float>(t.sp.Na); auto twb = twiddle_table<float>(t.sp.Nb);
+    memcpy(h.data() + t.twa, twa.data(), (size_t)t.sp.Na * sizeof(cx<float>));
+    memcpy(h.data() + t.twb, twb.data(), (size_t)t.sp.Nb * sizeof(cx<float>));
+    cx<float>* hi = reinterpret_cast<cx<float>*>(h.data() + t.hi);
+    cx<float>* lo = reinterpret_cast<cx<float>*>(h.data() + t.lo);
+    const long double tau = -2.0L * 3.14159265358979323846264338327950288L / (long double)N;
+    for (int a = 0; a < t.sp.nhi; ++a) { long double x = tau * (long double)((long long)a << t.sp.lb); hi[a].x = (float)cosl(x); hi[a].y = (float)sinl(x); }
+    for (int b = 0; b < t.sp.nlo; ++b) { long double x = tau * (long double)b; lo[b].x = (float)cosl(x); lo[b].y = (float)sinl(x); }
+    int* inva = reinterpret_cast<int*>(h.data() + t.inva);
+    if (t.sp.Na > 1) {
+        auto pos = scramble_table(ct_plan1(t.sp.Na));
+        for (int f = 0; f < t.sp.Na; ++f) inva[pos[f]] = f;
+    } else inva[0] = 0;
+    SB_CUDA(cudaMemcpyAsync(dev, h.data(), t.bytes, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+
+// [twM | posM]
+struct FinTables1d {
+    int M; size_t tw, pos, bytes;
+    explicit FinTables1d(int M_) : M(M_) {
+        if (M < 8 || M > 1024 || (M & (M - 1))) throw std::runtime_error("fused 1-D low-pass length must be a power of two in [8, 1024], got " + std::to_string(M));
+        size_t off = 0;
+        auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+        tw = take((size_t)M * sizeof(cx<float>)); pos = take((size_t)M * sizeof(int));
+        bytes = off;
+    }
+};
+inline void fin_tables1d_init(void* dev, int M, cudaStream_t st) {
+    FinTables1d t(M);
+    std::vector<unsigned char> h(t.bytes, 0);
+    auto tw = twiddle_table<float>(M);
+    auto pos = scramble_table(ct_plan1(M));
+    memcpy(h.data() + t.tw, tw.data(), (size_t)M * sizeof(cx<float>));
+    memcpy(h.data() + t.pos, pos.data(), (size_t)M * sizeof(int));
+    SB_CUDA(cudaMemcpyAsync(dev, h.data(), t.bytes, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+
+inline void enable1d_once() {
+    static bool done = false;
+    if (!done) { kern1d_enable_smem(); done = true; }
+}
+inline TwN<float> twn_of(const Tables1d& t, const unsigned char* cb) {
+    TwN<float> w;
+    w.hi = reinterpret_cast<const cx<float>*>(cb + t.hi); w.lo = reinterpret_cast<const cx<float>*>(cb + t.lo);
+    w.lb = t.sp.lb; w.nhi = t.sp.nhi;
+    return w;
+}
+inline dim3 block1d() { return dim3(k1L, k1Threads / k1L, 1); }
+
+inline void col_prod1d(const void* tables, const void* parent, long long ps_b, long long ps_i, const void* filt_dev,
+                       const void* supp_dev, void* Y, long long G, int NI, int Npar, int N, double algo_bytes,
+                       cudaStream_t st) {
+    if (G <= 0) return;
+    enable1d_once();
+    Tables1d t(N);
+    if (Npar % N || NI < 1) throw std::runtime_error("col_prod1d: bad sizes");
+    const unsigned char* cb = static_cast<const unsigned char*>(tables);
+    auto k = kern1d_cols<float>(t.sp.Na);
+    if (!k.col_prod) throw std::runtime_error("col_prod1d: no instance for NA=" + std::to_string(t.sp.Na));
+    ColProd1<float> a{};
+    a.parent = static_cast<const cx<float>*>(parent); a.ps_b = ps_b; a.ps_i = ps_i;
+    a.filt = static_cast<const float* const*>(filt_dev); a.supp = static_cast<const int2*>(supp_dev);
+    a.Y = static_cast<cx<float>*>(Y);
+    a.NI = NI; a.Npar = Npar; a.k = Npar / N; a.NB = t.sp.Nb;
+    a.scale = 1.0f / ((float)N * (float)a.k);
+    a.twA = reinterpret_cast<const cx<float>*>(cb + t.twa); a.invA = reinterpret_cast<const int*>(cb + t.inva);
+    a.w = twn_of(t, cb);
+    const size_t smem = ((size_t)t.sp.Na * k1LP + t.sp.Na + t.sp.nhi + t.sp.nlo) * sizeof(cx<float>) + (size_t)t.sp.Na * sizeof(int);
+    dim3 grid((unsigned)G, t.sp.Nb / k1L);
+    launch("1d_col_prod:N" + std::to_string(N) + ":k" + std::to_string(a.k), algo_bytes, st,
+           [&] { k.col_prod<<<grid, block1d(), smem, st>>>(a); });
+}
+
+inline void row_mod1d(const void* tables, void* Y, long long G, int N, void* part, int Fc, double algo_bytes, cudaStream_t st) {
+    if (G <= 0) return;
+    enable1d_once();
+    Tables1d t(N);
+    const unsigned char* cb = static_cast<const unsigned char*>(tables);
+    auto k = kern1d_rows<float>(t.sp.Nb);
+    if (!k.parent) throw std::runtime_error("row_mod1d: no instance for NB=" + std::to_string(t.sp.Nb));
+    if (part && (Fc < 1 || Fc > N / 2 + 1)) throw std::runtime_error("row_mod1d: Fc out of range");
+    RowMod1<float> a{};
+    a.Y = static_cast<cx<float>*>(Y); a.NA = t.sp.Na; a.N = N;
+    a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb); a.invA = reinterpret_cast<const int*>(cb + t.inva);
+    a.w = twn_of(t, cb);
+    a.part = static_cast<cx<float>*>(part); a.Fc = Fc;
+    const size_t smem = ((size_t)t.sp.Nb * k1LP + t.sp.Nb + t.sp.nhi + t.sp.nlo) * sizeof(cx<float>) + k1L * sizeof(int);
+    dim3 grid((unsigned)G, ceil_div(t.sp.Na, k1L));
+    launch(std::string(part ? "1d_row_mod_leaf:N" : "1d_row_mod:N") + std::to_string(N), algo_bytes, st,
+           [&] { (part ? k.leaf : k.parent)<<<grid, block1d(), smem, st>>>(a); });
+}
+
+inline void col_fwd1d(const void* tables, const void* Z, void* out, long long G, int N, double algo_bytes, cudaStream_t st) {
+    if (G <= 0) return;
+    enable1d_once();
+    Tables1d t(N);
+    const unsigned char* cb = static_cast<const unsigned char*>(tables);
+    auto k = kern1d_cols<float>(t.sp.Na);
+    if (!k.col_fwd) throw std::runtime_error("col_fwd1d: no instance for NA=" + std::to_string(t.sp.Na));
+    ColFwd1<float> a{};
+    a.Z = static_cast<const cx<float>*>(Z); a.out = static_cast<cx<float>*>(out); a.NB = t.sp.Nb;
+    a.twA = reinterpret_cast<const cx<float>*>(cb + t.twa);
+    const size_t smem = ((size_t)t.sp.Na * k1LP + t.sp.Na) * sizeof(cx<float>);
+    dim3 grid((unsigned)G, t.sp.Nb / k1L);
+    launch("1d_col_fwd:N" + std::to_string(N), algo_bytes, st, [&] { k.col_fwd<<<grid, block1d(), smem, st>>>(a); });
+}
+
+inline void finish1d(const void* fin_tables, const void* src, long long ss_g, long long ss_part, int nparts, const void* phi,
+                     int N, int Fc, int M, void* out, long long os_b, const void* chan_dev, int NI, long long G, int i0, int W,
+                     double algo_bytes, cudaStream_t st) {
+    if (G <= 0) return;
+    enable1d_once();
+    FinTables1d t(M);
+    if (N % M || Fc < 1 || Fc > N / 2 + 1 || i0 < 0 || i0 + W > M || NI < 1 || nparts < 1)
+        throw std::runtime_error("finish1d: bad sizes");
+    const unsigned char* cb = static_cast<const unsigned char*>(fin_tables);
+    auto kern = kern1d_finish<float>(M);
+    if (!kern) throw std::runtime_error("finish1d: no instance for M=" + std::to_string(M));
+    Finish1<float> a{};
+    a.src = static_cast<const cx<float>*>(src); a.ss_g = ss_g; a.ss_part = ss_part; a.nparts = nparts;
+    a.phi = static_cast<const float*>(phi); a.N = N; a.Fc = Fc; a.scale = 1.0f / (float)N;
+    a.out = static_cast<float*>(out); a.os_b = os_b; a.chan = static_cast<const int*>(chan_dev); a.NI = NI;
+    a.G = (int)G; a.i0 = i0; a.W = W;
+    a.twM = reinterpret_cast<const cx<float>*>(cb + t.tw); a.posM = reinterpret_cast<const int*>(cb + t.pos);
+    const size_t smem = ((size_t)M * k1LP + M) * sizeof(cx<float>) + (size_t)M * sizeof(int);
+    dim3 grid((unsigned)ceil_div((int)G, k1L));
+    launch("1d_finish:N" + std::to_string(N) + ":M" + std::to_string(M), algo_bytes, st,
+           [&] { kern<<<grid, block1d(), smem, st>>>(a); });
+}
+
+}  // namespace sb

@@ -3,6 +3,7 @@
 #include <cstring>
 #include "plan2d.cuh"
 #include "prims.cuh"
+#include "plan1d.cuh"
 
 using namespace sb;
 
@@ -334,6 +335,47 @@ int scat_pad2d_bwd(const void* gout_dev, void* gx_dev, int64_t B, int32_t M, int
                 kp_pad2d_bwd<T><<<grid, 128, 0, st>>>(static_cast<const T*>(gout_dev), static_cast<T*>(gx_dev), M, N, top, left, P0, P1);
             });
         });
+    });
+}
+
+// ---------------------------------------------------------------- fused 1-D kernels (engine1d.py drives the cascade)
+int scat1d_split(int32_t N, int32_t* Na, int32_t* Nb) {
+    return guarded([&] { Split1d s = split1d(N); if (Na) *Na = s.Na; if (Nb) *Nb = s.Nb; });
+}
+size_t scat1d_tables_bytes(int32_t N) {
+    try { return Tables1d(N).bytes; } catch (const std::exception& e) { last_error() = e.what(); return 0; }
+}
+int scat1d_tables_init(void* tables_dev, int32_t N, void* stream) {
+    return guarded([&] { tables1d_init(tables_dev, N, static_cast<cudaStream_t>(stream)); });
+}
+size_t scat1d_fin_tables_bytes(int32_t M) {
+    try { return FinTables1d(M).bytes; } catch (const std::exception& e) { last_error() = e.what(); return 0; }
+}
+int scat1d_fin_tables_init(void* tables_dev, int32_t M, void* stream) {
+    return guarded([&] { fin_tables1d_init(tables_dev, M, static_cast<cudaStream_t>(stream)); });
+}
+int scat1d_col_prod(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
+                    const void* supp_dev, void* y_dev, int64_t G, int32_t NI, int32_t Npar, int32_t N, double algo_bytes,
+                    void* stream) {
+    return guarded([&] {
+        col_prod1d(tables_dev, parent_dev, ps_b, ps_i, filt_ptrs_dev, supp_dev, y_dev, G, NI, Npar, N, algo_bytes,
+                   static_cast<cudaStream_t>(stream));
+    });
+}
+int scat1d_row_mod(const void* tables_dev, void* y_dev, int64_t G, int32_t N, void* part_dev, int32_t Fc, double algo_bytes,
+                   void* stream) {
+    return guarded([&] { row_mod1d(tables_dev, y_dev, G, N, part_dev, Fc, algo_bytes, static_cast<cudaStream_t>(stream)); });
+}
+int scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t G, int32_t N, double algo_bytes,
+                   void* stream) {
+    return guarded([&] { col_fwd1d(tables_dev, z_dev, out_dev, G, N, algo_bytes, static_cast<cudaStream_t>(stream)); });
+}
+int scat1d_finish(const void* fin_tables_dev, const void* src_dev, int64_t ss_g, int64_t ss_part, int32_t nparts,
+                  const void* phi_dev, int32_t N, int32_t Fc, int32_t M, void* out_dev, int64_t os_b, const void* chan_dev,
+                  int32_t NI, int64_t G, int32_t i0, int32_t W, double algo_bytes, void* stream) {
+    return guarded([&] {
+        finish1d(fin_tables_dev, src_dev, ss_g, ss_part, nparts, phi_dev, N, Fc, M, out_dev, os_b, chan_dev, NI, G, i0, W,
+                 algo_bytes, static_cast<cudaStream_t>(stream));
     });
 }
 

@@ -481,6 +481,51 @@ def _fused_scattering2d(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_
     return out
 
 
+_engines1d = {}
+
+
+def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
+    """Generator with the signature and yield order of kymatio/scattering1d/core/scattering1d.py:2-107; the whole
+    cascade runs as fused launches (engine1d.py) and every yielded 'coef' is a view of one (B, K, M) buffer."""
+    from .engine1d import Engine1D
+    phi, psi1 = filters[0], filters[1]
+    psi2 = filters[2] if len(filters) > 2 else None
+    Np = U_0.shape[-2]
+    tensors = list(phi["levels"]) + [lv for p in psi1 for lv in p["levels"]]
+    if psi2 is not None:
+        tensors += [lv for p in psi2 for lv in p["levels"]]
+    key = (U_0.device.index, Np, int(log2_stride), psi2 is None) + tuple((t.data_ptr(), t._version) for t in tensors)
+    eng = _engines1d.get(key)
+    if eng is None:
+        if len(_engines1d) > 16:
+            _engines1d.clear()
+        eng = _engines1d[key] = Engine1D(Np, log2_stride, phi, psi1, psi2, U_0.device)
+    U0_hat = backend_.rfft(U_0)                                   # (B, 1, Np, 2), this library's four-step FFT
+    S = eng.forward(U0_hat.reshape(-1, Np, 2))
+    B = S.shape[0]
+    for kind, n1, n2, ch in eng.order:
+        coef = S[:, ch].reshape(B, 1, eng.M, 1)
+        if kind == "S0":
+            yield {"coef": coef, "j": (), "n": ()}
+        elif kind == "S1":
+            yield {"coef": coef, "j": (psi1[n1]["j"],), "n": (n1,)}
+        else:
+            yield {"coef": coef, "j": (psi1[n1]["j"], psi2[n2]["j"]), "n": (n1, n2)}
+
+
+def _fusable1d(U_0, backend_, filters, log2_stride, average_local):
+    if getattr(backend_, "name", None) != NAME or not average_local:
+        return False
+    if not (torch.is_tensor(U_0) and U_0.is_cuda and U_0.dtype == torch.float32 and U_0.dim() == 4):
+        return False
+    if filters[0]["levels"][0].dtype != torch.float32 or not filters[0]["levels"][0].is_cuda:
+        return False
+    Np = U_0.shape[-2]
+    M = Np >> int(log2_stride)
+    return Np & (Np - 1) == 0 and Np <= (1 << 18) and 8 <= M <= 1024 and (Np >> max(
+        [p["j"] for p in filters[1]] + [0])) >= 16
+
+
 def install(fused=True):
     """Register the backend module and (optionally) the fused core dispatcher. Idempotent."""
     import kymatio.scattering2d.frontend.torch_frontend as tf2d   # the unmodified reference
@@ -513,6 +558,27 @@ def install(fused=True):
         _originals["scattering2d"] = tf2d.scattering2d
     reference_core = _originals["scattering2d"]
 
+    import kymatio.scattering1d.frontend.base_frontend as bf1d
+    if "scattering1d" not in _originals:
+        _originals["scattering1d"] = bf1d.scattering1d
+    reference_core1d = _originals["scattering1d"]
+    if fused:
+        def dispatch1d(U_0, backend_, filters, log2_stride, average_local):
+            if _fusable1d(U_0, backend_, filters, log2_stride, average_local):
+                from .engine1d import Unsupported
+                try:
+                    gen = _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local)
+                    first = next(gen)
+                except Unsupported:
+                    return reference_core1d(U_0, backend_, filters, log2_stride, average_local)
+                import itertools
+                return itertools.chain([first], gen)
+            return reference_core1d(U_0, backend_, filters, log2_stride, average_local)
+        dispatch1d.__wrapped__ = reference_core1d
+        bf1d.scattering1d = dispatch1d
+    else:
+        bf1d.scattering1d = reference_core1d
+
     if fused:
         def dispatch(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type="array"):
             if getattr(backend_, "name", None) == NAME:
@@ -529,3 +595,6 @@ def uninstall():
     if "scattering2d" in _originals:
         import kymatio.scattering2d.frontend.torch_frontend as tf2d
         tf2d.scattering2d = _originals["scattering2d"]
+    if "scattering1d" in _originals:
+        import kymatio.scattering1d.frontend.base_frontend as bf1d
+        bf1d.scattering1d = _originals["scattering1d"]

@@ -1,0 +1,94 @@
+"""Stage-level check of the fused 1-D kernels against torch.fft on the GPU (run through gpurun)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from kymatio_b200 import _lib  # noqa: E402
+from kymatio_b200.engine1d import _Tables, _split, _stream, circular_support  # noqa: E402
+
+dev = torch.device("cuda:0")
+lib = _lib.load()
+tabs = _Tables(dev)
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def run(N, k, NI, B, M, full_support=False):
+    Npar = N * k
+    st = _stream(dev)
+    torch.manual_seed(N + k)
+    parent = torch.randn(B, Npar, 2, device=dev)
+    filt = torch.zeros(NI, Npar, device=dev)
+    for i in range(NI):
+        if full_support:
+            filt[i] = torch.randn(Npar, device=dev)
+        else:
+            lo = (37 + 1000 * i) % Npar
+            ln = max(3, Npar // (3 + i))
+            idx = (torch.arange(ln, device=dev) + lo) % Npar
+            filt[i, idx] = torch.rand(ln, device=dev) + 0.1
+    supp = [circular_support(filt[i].cpu().numpy(), 1e-7) for i in range(NI)]
+    filt_dev = torch.tensor([filt[i].data_ptr() for i in range(NI)], dtype=torch.int64, device=dev)
+    supp_dev = torch.tensor(supp, dtype=torch.int32, device=dev).reshape(-1, 2).contiguous()
+    G = B * NI
+    Y = torch.empty(G, N, 2, device=dev)
+    tab = tabs.for_length(N)
+    _lib.check(lib.scat1d_col_prod(tab.data_ptr(), parent.data_ptr(), Npar, 0, filt_dev.data_ptr(), supp_dev.data_ptr(),
+                                   Y.data_ptr(), G, NI, Npar, N, 0.0, st))
+    # reference
+    pc = torch.view_as_complex(parent)
+    X = (pc[:, None, :] * filt[None]).reshape(B, NI, k, N).mean(2)
+    u = torch.fft.ifft(X)
+    U = u.abs()
+    U1 = torch.fft.fft(U)
+    Yl = Y.clone()
+    _lib.check(lib.scat1d_row_mod(tab.data_ptr(), Y.data_ptr(), G, N, None, 0, 0.0, st))
+    out = torch.empty(G, N, 2, device=dev)
+    _lib.check(lib.scat1d_col_fwd(tab.data_ptr(), Y.data_ptr(), out.data_ptr(), G, N, 0.0, st))
+    torch.cuda.synchronize()
+    got = torch.view_as_complex(out).reshape(B, NI, N)
+    e1 = rel(torch.view_as_real(got), torch.view_as_real(U1))
+    # leaf + finish
+    Na, Nb = _split(N)
+    nparts = (Na + 15) // 16
+    Fc = min(N // 2 + 1, 48)
+    phi = torch.zeros(N, device=dev)
+    w = torch.exp(-0.5 * (torch.arange(Fc, device=dev, dtype=torch.float32) / (Fc / 5.0)) ** 2)
+    phi[:Fc] = w
+    phi[N - Fc + 1:] = w[1:].flip(0)
+    part = torch.empty(G, nparts, Fc, 2, device=dev)
+    _lib.check(lib.scat1d_row_mod(tab.data_ptr(), Yl.data_ptr(), G, N, part.data_ptr(), Fc, 0.0, st))
+    K = NI + 2
+    chan = torch.arange(NI, dtype=torch.int32, device=dev) + 1
+    S = torch.zeros(B, K, M, device=dev)
+    ft = tabs.for_lowpass(M)
+    _lib.check(lib.scat1d_finish(ft.data_ptr(), part.data_ptr(), nparts * Fc, Fc, nparts, phi.data_ptr(), N, Fc, M,
+                                 S.data_ptr(), K * M, chan.data_ptr(), NI, G, 0, M, 0.0, st))
+    S2 = torch.zeros(B, K, M, device=dev)
+    _lib.check(lib.scat1d_finish(ft.data_ptr(), out.data_ptr(), N, 0, 1, phi.data_ptr(), N, Fc, M,
+                                 S2.data_ptr(), K * M, chan.data_ptr(), NI, G, 0, M, 0.0, st))
+    torch.cuda.synchronize()
+    low = (U1 * phi).reshape(B, NI, N // M, M).mean(2)
+    ref = torch.fft.ifft(low).real
+    e2 = rel(S[:, 1:1 + NI], ref)
+    e3 = rel(S2[:, 1:1 + NI], ref)
+    print(f"N={N:7d} k={k:3d} NI={NI} Na={Na} Nb={Nb} M={M}: spectrum {e1:.2e}  leaf-finish {e2:.2e}  spec-finish {e3:.2e}",
+          "OK" if max(e1, e2, e3) < 2e-5 else "FAIL", flush=True)
+    return max(e1, e2, e3) < 2e-5
+
+
+ok = True
+for (N, k, NI, B, M, full) in [(16, 1, 1, 2, 8, True), (32, 2, 2, 3, 16, True), (64, 1, 3, 2, 32, False),
+                               (128, 4, 2, 2, 32, False), (256, 2, 3, 3, 64, False), (512, 1, 2, 2, 128, True),
+                               (1024, 8, 3, 2, 256, False), (2048, 2, 2, 2, 512, False), (4096, 1, 2, 2, 512, False),
+                               (8192, 4, 3, 2, 512, False), (16384, 2, 2, 2, 512, False), (32768, 4, 2, 2, 512, False),
+                               (65536, 2, 3, 2, 512, False), (131072, 1, 2, 2, 512, False), (262144, 1, 1, 2, 1024, False)]:
+    ok &= run(N, k, NI, B, M, full)
+print("ALL OK" if ok else "SOME FAILED")
+sys.exit(0 if ok else 1)
