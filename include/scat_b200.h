@@ -155,11 +155,20 @@ int    scat1d_row_mod(const void* tables_dev, void* y_dev, int64_t G, int32_t N,
 int    scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t G, int32_t N, double algo_bytes,
                       void* stream);
 /* cdgmm(phi) -> subsample_fourier(N/M) -> irfft -> unpad[i0:i0+W] (core/scattering1d.py:72-77,101-105 and
- * frontend/base_frontend.py:137-139) from the Fc lowest bins of each path's spectrum, X[f] = sum_{q<nparts}
- * src[g*ss_g + q*ss_part + f]; writes out[b*os_b + chan[i]*W + n], g = b*NI + i */
-int    scat1d_finish(const void* fin_tables_dev, const void* src_dev, int64_t ss_g, int64_t ss_part, int32_t nparts,
-                     const void* phi_dev, int32_t N, int32_t Fc, int32_t M, void* out_dev, int64_t os_b, const void* chan_dev,
-                     int32_t NI, int64_t G, int32_t i0, int32_t W, double algo_bytes, void* stream);
+ * frontend/base_frontend.py:137-139) for every path of a batch chunk in ONE launch.  Line (= path) `line` belongs to
+ * the last segment with line0 <= line; with gl = line - line0 = b*NI + i its spectrum is
+ * X[f] = sum_{q<nparts} base[which][src_off + gl*ss_g + q*ss_part + f], f < Fc (the negative bins follow from the
+ * Hermitian symmetry), base = {u0_dev, u1_dev, part_dev}; writes out[b*os_b + chan[i]*W + n]. */
+typedef struct scat1d_finseg {
+    int64_t src_off, ss_g, ss_part;   /* complex elements */
+    const void* phi_dev;              /* real low-pass on the length-N grid */
+    const void* chan_dev;             /* int32[NI] */
+    int32_t which, nparts, N, Fc, NI, line0;
+} scat1d_finseg;
+size_t scat1d_finseg_bytes(void);
+int    scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1_dev, const void* part_dev,
+                     const void* segs_dev, int32_t nseg, int64_t total_lines, int32_t M, void* out_dev, int64_t os_b,
+                     int32_t i0, int32_t W, double algo_bytes, void* stream);
 
 /* 3-D primitives (kymatio/scattering3d/backend/torch_backend.py:73-151) --------------------------------
  * natural-order complex 3-D FFT on (G, M, N, O, 2) - replaces torch.fft.fftn / ifftn (torch_backend.py:39-40) */

@@ -77,9 +77,9 @@ SIGNATURES = {
     "scat1d_row_mod": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_double,
                                   _c.c_void_p]),
     "scat1d_col_fwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_double, _c.c_void_p]),
-    "scat1d_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int32, _c.c_void_p, _c.c_int32,
-                                 _c.c_int32, _c.c_int32, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int32, _c.c_int64,
-                                 _c.c_int32, _c.c_int32, _c.c_double, _c.c_void_p]),
+    "scat1d_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int64,
+                                 _c.c_int32, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_double, _c.c_void_p]),
+    "scat1d_finseg_bytes": (_c.c_size_t, []),
     "scat_fft3d_const_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
     "scat_fft3d_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_fft3d_exec": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,

@@ -37,10 +37,26 @@ constexpr int k1L = 16;            // lines per CTA
 constexpr int k1LP = k1L | 1;      // odd shared-memory pitch
 constexpr int k1Threads = 256;
 
+// 8-byte predicated read-only global load (zero when the predicate is false)
+template <typename V> __device__ __forceinline__ V ld8_pred(const void* ptr, bool pred) {
+    static_assert(sizeof(V) == 8, "ld8_pred loads 8 bytes");
+    union { V v; uint2 q; } u;
+    u.q = make_uint2(0u, 0u);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+        : "+r"(u.q.x), "+r"(u.q.y)
+        : "l"(ptr), "r"((int)pred));
+    return u.v;
+}
+
 // exp(-2 pi i j / N) = hi[j >> lb] * lo[j & (2^lb - 1)]
 template <typename T> struct TwN { const cx<T>* hi; const cx<T>* lo; int lb, nhi; };
+template <typename T> __device__ __forceinline__ cx<T> ldg_cx(const cx<T>* p) {
+    if constexpr (sizeof(T) == 4) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
+    else { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
+}
+// the two small tables are read through the read-only path (L1-resident), not staged per CTA
 template <typename T> __device__ __forceinline__ cx<T> twn(const cx<T>* hi, const cx<T>* lo, int lb, int j) {
-    return cmul(hi[j >> lb], lo[j & ((1 << lb) - 1)]);
+    return cmul(ldg_cx(hi + (j >> lb)), ldg_cx(lo + (j & ((1 << lb) - 1))));
 }
 
 // ------------------------------------------------------------------ P1: product + periodise + column inverse
@@ -54,51 +70,67 @@ template <typename T> struct ColProd1 {
     const cx<T>* twA; const int* invA;           // length-NA twiddles; invA[p] = t1 held at scrambled row p
     TwN<T> w;
 };
-template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 2) k1d_col_prod(ColProd1<T> a) {
+template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 3) k1d_col_prod(ColProd1<T> a) {
     constexpr int LP = k1LP;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twA = s + (size_t)NA * LP;
-    cx<T>* hi = twA + NA;
-    cx<T>* lo = hi + a.w.nhi;
-    int* invA = reinterpret_cast<int*>(lo + (1 << a.w.lb));
-    const int g = blockIdx.x, c0 = blockIdx.y * k1L;
+    const cx<T>* hi = a.w.hi; const cx<T>* lo = a.w.lo;
+    const int* __restrict__ invA = a.invA;
+    const int ncol = a.NB / k1L;
+    const int g = blockIdx.x / ncol, c0 = (blockIdx.x - g * ncol) * k1L;   // column group fastest: neighbours share DRAM rows
     const int i = g % a.NI, b = g / a.NI;
     const int tid = flat_tid(), nt = flat_nt();
     stage(twA, a.twA, NA);
-    stage(hi, a.w.hi, a.w.nhi);
-    stage(lo, a.w.lo, 1 << a.w.lb);
-    stage(invA, a.invA, NA);
     const cx<T>* __restrict__ pb = a.parent + (long long)b * a.ps_b + (long long)i * a.ps_i;
     const T* __restrict__ fb = a.filt[i];
     const int2 sp = a.supp[i];
     const int NB = a.NB, KNA = a.k * NA, Npar = a.Npar;
     const int Rb = sp.x / NB;                                         // first parent row meeting the support
     const int nr = min(KNA, (sp.x - Rb * NB + sp.y + NB - 1) / NB);   // number of such rows (circular)
-    for (int idx = tid; idx < NA * (k1L / 2); idx += nt) {
-        const int f1 = idx / (k1L / 2), l = 2 * (idx - f1 * (k1L / 2));
-        T ax0 = T(0), ay0 = T(0), ax1 = T(0), ay1 = T(0);
-        for (int d = (f1 - Rb) & (NA - 1); d < nr; d += NA) {         // aliases f1 + a*NA inside the support rows
-            int R = Rb + d;
-            if (R >= KNA) R -= KNA;
-            const int off = R * NB + c0 + l;
-            int rel = off - sp.x;
-            if (rel < 0) rel += Npar;
-            if ((rel < sp.y) | (rel == Npar - 1)) {
-                const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(pb + off);
-                const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + off);
-                ax0 += v.a.x * f.a; ay0 += v.a.y * f.a;
-                ax1 += v.b.x * f.b; ay1 += v.b.y * f.b;
+    const int amax = (nr + NA - 1) / NA;                              // aliases f1 + a*NA that can meet the support
+    constexpr int CELLS = NA * (k1L / 2), U = 4;
+    for (int base = 0; base < CELLS; base += U * k1Threads) {
+        T acc[U][4];
+#pragma unroll
+        for (int c = 0; c < U; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = T(0);
+        for (int ai = 0; ai < amax; ++ai) {
+            cxpair<T> v[U]; repair<T> f[U];
+#pragma unroll
+            for (int c = 0; c < U; ++c) {                             // U independent predicated loads in flight
+                const int idx = base + c * k1Threads + tid;
+                const int f1 = idx / (k1L / 2), l = 2 * (idx - f1 * (k1L / 2));
+                const int d = ((f1 - Rb) & (NA - 1)) + ai * NA;
+                int R = Rb + d;
+                if (R >= KNA) R -= KNA;
+                const int off = R * NB + c0 + l;
+                int rel = off - sp.x;
+                if (rel < 0) rel += Npar;
+                const bool in = (idx < CELLS) & (d < nr) & ((rel < sp.y) | (rel == Npar - 1));
+                v[c] = ld_pred<cxpair<T>>(pb + off, in);
+                f[c] = ld8_pred<repair<T>>(fb + off, in);
+            }
+#pragma unroll
+            for (int c = 0; c < U; ++c) {
+                acc[c][0] += v[c].a.x * f[c].a; acc[c][1] += v[c].a.y * f[c].a;
+                acc[c][2] += v[c].b.x * f[c].b; acc[c][3] += v[c].b.y * f[c].b;
             }
         }
-        s[f1 * LP + l] = mk<T>(ax0 * a.scale, ay0 * a.scale);
-        s[f1 * LP + l + 1] = mk<T>(ax1 * a.scale, ay1 * a.scale);
+#pragma unroll
+        for (int c = 0; c < U; ++c) {
+            const int idx = base + c * k1Threads + tid;
+            if (idx < CELLS) {
+                const int f1 = idx / (k1L / 2), l = 2 * (idx - f1 * (k1L / 2));
+                s[f1 * LP + l] = mk<T>(acc[c][0] * a.scale, acc[c][1] * a.scale);
+                s[f1 * LP + l + 1] = mk<T>(acc[c][2] * a.scale, acc[c][3] * a.scale);
+            }
+        }
     }
     __syncthreads();
     slab_fft_s<NA, false, +1, 1, k1LP, T>(s, k1L, twA);               // inverse DIF over f1: row p holds t1 = invA[p]
     cx<T>* yb = a.Y + (size_t)g * NA * NB + c0;
     for (int idx = tid; idx < NA * (k1L / 2); idx += nt) {
         const int p = idx / (k1L / 2), l = 2 * (idx - p * (k1L / 2));
-        const int t1 = invA[p], f2 = c0 + l;
+        const int t1 = __ldg(invA + p), f2 = c0 + l;
         cxpair<T> o;
         o.a = cmulc(s[p * LP + l], twn(hi, lo, a.w.lb, f2 * t1));
         o.b = cmulc(s[p * LP + l + 1], twn(hi, lo, a.w.lb, (f2 + 1) * t1));
@@ -114,38 +146,31 @@ template <typename T> struct RowMod1 {
     TwN<T> w;
     cx<T>* part; int Fc;                         // leaves: part[(g*nparts + cta)][Fc]
 };
-template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Threads, 2) k1d_row_mod(RowMod1<T> a) {
-    constexpr int LP = k1LP;
+// Shared-memory layout: line-major, line l at s + l*(NB+1) (odd pitch): both the staging (lanes along a line) and
+// the butterflies (lanes across lines) are bank-conflict free.
+template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Threads, 3) k1d_row_mod(RowMod1<T> a) {
+    constexpr int LS = NB + 1;
     cx<T>* s = dyn_smem<cx<T>>();
-    cx<T>* twB = s + (size_t)NB * LP;
-    cx<T>* hi = twB + NB;
-    cx<T>* lo = hi + a.w.nhi;
-    int* t1s = reinterpret_cast<int*>(lo + (1 << a.w.lb));
+    cx<T>* twB = s + (size_t)k1L * LS;
+    int* t1s = reinterpret_cast<int*>(twB + NB);
+    const cx<T>* hi = a.w.hi; const cx<T>* lo = a.w.lo;
     const int g = blockIdx.x, p0 = blockIdx.y * k1L;
     const int nl = min(k1L, a.NA - p0);
     const int tid = flat_tid(), nt = flat_nt();
     stage(twB, a.twB, NB);
-    stage(hi, a.w.hi, a.w.nhi);
-    stage(lo, a.w.lo, 1 << a.w.lb);
     if (tid < k1L) t1s[tid] = tid < nl ? a.invA[p0 + tid] : 0;
     cx<T>* yb = a.Y + ((size_t)g * a.NA + p0) * NB;
-    constexpr int half = NB / 2;
-    for (int idx = tid; idx < nl * half; idx += nt) {
-        const int l = idx / half, e = 2 * (idx - l * half);
-        const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(yb + (size_t)l * NB + e);
-        s[e * LP + l] = v.a; s[(e + 1) * LP + l] = v.b;
+    for (int idx = tid; idx < nl * NB; idx += nt) {
+        const int l = idx / NB, e = idx - l * NB;
+        s[l * LS + e] = yb[idx];
     }
     __syncthreads();
-    slab_fft_s<NB, false, +1, 1, k1LP, T, true>(s, nl, twB);          // inverse DIF + modulus: (|u|, 0), scrambled t2
-    slab_fft_s<NB, true, -1, 1, k1LP, T>(s, nl, twB);                 // forward DIT: natural f2'
+    slab_fft_s<NB, false, +1, LS, 1, T, true>(s, nl, twB);            // inverse DIF + modulus: (|u|, 0), scrambled t2
+    slab_fft_s<NB, true, -1, LS, 1, T>(s, nl, twB);                   // forward DIT: natural f2'
     if constexpr (!LEAF) {
-        for (int idx = tid; idx < nl * half; idx += nt) {
-            const int l = idx / half, e = 2 * (idx - l * half);
-            const int t1 = t1s[l];
-            cxpair<T> o;
-            o.a = cmul(s[e * LP + l], twn(hi, lo, a.w.lb, t1 * e));
-            o.b = cmul(s[(e + 1) * LP + l], twn(hi, lo, a.w.lb, t1 * (e + 1)));
-            *reinterpret_cast<cxpair<T>*>(yb + (size_t)l * NB + e) = o;
+        for (int idx = tid; idx < nl * NB; idx += nt) {
+            const int l = idx / NB, e = idx - l * NB;
+            yb[idx] = cmul(s[l * LS + e], twn(hi, lo, a.w.lb, t1s[l] * e));
         }
     } else {
         cx<T>* pb = a.part + ((size_t)g * gridDim.y + blockIdx.y) * a.Fc;
@@ -155,7 +180,7 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
             T ax = T(0), ay = T(0);
             for (int l = 0; l < nl; ++l) {
                 const cx<T> wv = twn(hi, lo, a.w.lb, (t1s[l] * f) & maskN);
-                const cx<T> v = s[e * LP + l];
+                const cx<T> v = s[l * LS + e];
                 ax += v.x * wv.x - v.y * wv.y; ay += v.x * wv.y + v.y * wv.x;
             }
             pb[f] = mk<T>(ax, ay);
@@ -169,11 +194,12 @@ template <typename T> struct ColFwd1 {
     int NB;
     const cx<T>* twA;
 };
-template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 2) k1d_col_fwd(ColFwd1<T> a) {
+template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 3) k1d_col_fwd(ColFwd1<T> a) {
     constexpr int LP = k1LP;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twA = s + (size_t)NA * LP;
-    const int g = blockIdx.x, c0 = blockIdx.y * k1L;
+    const int ncol = a.NB / k1L;
+    const int g = blockIdx.x / ncol, c0 = (blockIdx.x - g * ncol) * k1L;
     const int tid = flat_tid(), nt = flat_nt();
     stage(twA, a.twA, NA);
     const cx<T>* zb = a.Z + (size_t)g * NA * a.NB + c0;
@@ -193,51 +219,70 @@ template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 2) k1
 }
 
 // ------------------------------------------------------------------ low-pass tail on the lowest Fc bins
+// One launch serves every path of a batch chunk: the lines (one per path) are described by segments, one per
+// launch group (S0, each first-order group, each (j1, n2) second-order group).
+template <typename T> struct FinSeg {
+    long long src_off, ss_g, ss_part;      // X[f] = sum_{q<nparts} base[which][src_off + gl*ss_g + q*ss_part + f], f < Fc
+    const T* phi;                          // real low-pass on the length-N grid
+    const int* chan;                       // [NI] output channel of path i
+    int which, nparts, N, Fc, NI, line0;   // gl = line - line0 = b*NI + i
+};
 template <typename T> struct Finish1 {
-    const cx<T>* src; long long ss_g, ss_part; int nparts;   // X[f] = sum_part src[g*ss_g + part*ss_part + f], f < Fc
-    const T* phi;                                            // real low-pass on the length-N grid
-    int N, Fc;
-    T scale;                                                 // 1 / N
-    T* out; long long os_b; const int* chan; int NI;         // out[b*os_b + chan[i]*W + n - i0]
-    int G, i0, W;
+    const cx<T>* base[3];                  // U0_hat, U1_hat buffer, leaf partial sums
+    const FinSeg<T>* segs; int nseg, total;
+    T* out; long long os_b;                // out[b*os_b + chan[i]*W + n - i0]
+    int i0, W;
     const cx<T>* twM; const int* posM;
 };
+constexpr int k1FL = 8, k1FLP = k1FL | 1;  // lines per CTA of the finish kernel
 template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 2) k1d_finish(Finish1<T> a) {
-    constexpr int LP = k1LP;
+    constexpr int LP = k1FLP;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twM = s + (size_t)M * LP;
     int* posM = reinterpret_cast<int*>(twM + M);
-    const int g0 = blockIdx.x * k1L;
-    const int nl = min(k1L, a.G - g0);
+    int* segi = posM + M;
+    const int g0 = blockIdx.x * k1FL;
+    const int nl = min(k1FL, a.total - g0);
     const int tid = flat_tid(), nt = flat_nt();
     stage(twM, a.twM, M);
     stage(posM, a.posM, M);
-    const int N = a.N, Fc = a.Fc, nyq = N >> 1;
+    if (tid < nl) {
+        int sgi = 0;
+        while (sgi + 1 < a.nseg && a.segs[sgi + 1].line0 <= g0 + tid) ++sgi;
+        segi[tid] = sgi;
+    }
+    __syncthreads();
     for (int idx = tid; idx < nl * M; idx += nt) {
         const int l = idx / M, u = idx - l * M;
-        const cx<T>* __restrict__ xb = a.src + (long long)(g0 + l) * a.ss_g;
+        const FinSeg<T>& sg = a.segs[segi[l]];
+        const int N = sg.N, Fc = sg.Fc, nyq = N >> 1, nparts = sg.nparts;
+        const long long ssp = sg.ss_part;
+        const cx<T>* __restrict__ xb = a.base[sg.which] + sg.src_off + (long long)(g0 + l - sg.line0) * sg.ss_g;
+        const T* __restrict__ phi = sg.phi;
         T ax = T(0), ay = T(0);
         for (int f = u; f < Fc; f += M) {                    // bins f = u + aM on the non-negative side
             T vx = T(0), vy = T(0);
-            for (int q = 0; q < a.nparts; ++q) { const cx<T> v = xb[q * a.ss_part + f]; vx += v.x; vy += v.y; }
-            const T ph = a.phi[f];
+            for (int q = 0; q < nparts; ++q) { const cx<T> v = xb[q * ssp + f]; vx += v.x; vy += v.y; }
+            const T ph = phi[f];
             ax += vx * ph; ay += vy * ph;
         }
         for (int f = (M - u) & (M - 1); f < Fc; f += M) {    // bins N - f == u (mod M): conj(X[f]) * phi[N - f]
             if (f == 0 || f == nyq) continue;
             T vx = T(0), vy = T(0);
-            for (int q = 0; q < a.nparts; ++q) { const cx<T> v = xb[q * a.ss_part + f]; vx += v.x; vy += v.y; }
-            const T ph = a.phi[N - f];
+            for (int q = 0; q < nparts; ++q) { const cx<T> v = xb[q * ssp + f]; vx += v.x; vy += v.y; }
+            const T ph = phi[N - f];
             ax += vx * ph; ay -= vy * ph;
         }
-        s[u * LP + l] = mk<T>(ax * a.scale, ay * a.scale);
+        const T sc = T(1) / T(N);
+        s[u * LP + l] = mk<T>(ax * sc, ay * sc);
     }
     __syncthreads();
-    slab_fft_s<M, false, +1, 1, k1LP, T>(s, nl, twM);                 // inverse DIF: sample n at row posM[n]
+    slab_fft_s<M, false, +1, 1, k1FLP, T>(s, nl, twM);                // inverse DIF: sample n at row posM[n]
     for (int idx = tid; idx < nl * a.W; idx += nt) {
         const int l = idx / a.W, n = idx - l * a.W;
-        const int g = g0 + l, b = g / a.NI, i = g - b * a.NI;
-        a.out[(long long)b * a.os_b + (long long)a.chan[i] * a.W + n] = s[posM[a.i0 + n] * LP + l].x;
+        const FinSeg<T>& sg = a.segs[segi[l]];
+        const int gl = g0 + l - sg.line0, b = gl / sg.NI, i = gl - b * sg.NI;
+        a.out[(long long)b * a.os_b + (long long)sg.chan[i] * a.W + n] = s[posM[a.i0 + n] * LP + l].x;
     }
 }
 

@@ -103,8 +103,8 @@ inline void col_prod1d(const void* tables, const void* parent, long long ps_b, l
     a.scale = 1.0f / ((float)N * (float)a.k);
     a.twA = reinterpret_cast<const cx<float>*>(cb + t.twa); a.invA = reinterpret_cast<const int*>(cb + t.inva);
     a.w = twn_of(t, cb);
-    const size_t smem = ((size_t)t.sp.Na * k1LP + t.sp.Na + t.sp.nhi + t.sp.nlo) * sizeof(cx<float>) + (size_t)t.sp.Na * sizeof(int);
-    dim3 grid((unsigned)G, t.sp.Nb / k1L);
+    const size_t smem = ((size_t)t.sp.Na * k1LP + t.sp.Na) * sizeof(cx<float>);
+    dim3 grid((unsigned)(G * (t.sp.Nb / k1L)));
     launch("1d_col_prod:N" + std::to_string(N) + ":k" + std::to_string(a.k), algo_bytes, st,
            [&] { k.col_prod<<<grid, block1d(), smem, st>>>(a); });
 }
@@ -122,7 +122,7 @@ inline void row_mod1d(const void* tables, void* Y, long long G, int N, void* par
     a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb); a.invA = reinterpret_cast<const int*>(cb + t.inva);
     a.w = twn_of(t, cb);
     a.part = static_cast<cx<float>*>(part); a.Fc = Fc;
-    const size_t smem = ((size_t)t.sp.Nb * k1LP + t.sp.Nb + t.sp.nhi + t.sp.nlo) * sizeof(cx<float>) + k1L * sizeof(int);
+    const size_t smem = ((size_t)(t.sp.Nb + 1) * k1L + t.sp.Nb) * sizeof(cx<float>) + k1L * sizeof(int);
     dim3 grid((unsigned)G, ceil_div(t.sp.Na, k1L));
     launch(std::string(part ? "1d_row_mod_leaf:N" : "1d_row_mod:N") + std::to_string(N), algo_bytes, st,
            [&] { (part ? k.leaf : k.parent)<<<grid, block1d(), smem, st>>>(a); });
@@ -139,31 +139,29 @@ inline void col_fwd1d(const void* tables, const void* Z, void* out, long long G,
     a.Z = static_cast<const cx<float>*>(Z); a.out = static_cast<cx<float>*>(out); a.NB = t.sp.Nb;
     a.twA = reinterpret_cast<const cx<float>*>(cb + t.twa);
     const size_t smem = ((size_t)t.sp.Na * k1LP + t.sp.Na) * sizeof(cx<float>);
-    dim3 grid((unsigned)G, t.sp.Nb / k1L);
+    dim3 grid((unsigned)(G * (t.sp.Nb / k1L)));
     launch("1d_col_fwd:N" + std::to_string(N), algo_bytes, st, [&] { k.col_fwd<<<grid, block1d(), smem, st>>>(a); });
 }
 
-inline void finish1d(const void* fin_tables, const void* src, long long ss_g, long long ss_part, int nparts, const void* phi,
-                     int N, int Fc, int M, void* out, long long os_b, const void* chan_dev, int NI, long long G, int i0, int W,
-                     double algo_bytes, cudaStream_t st) {
-    if (G <= 0) return;
+inline void finish1d(const void* fin_tables, const void* base0, const void* base1, const void* base2, const void* segs_dev,
+                     int nseg, long long total_lines, int M, void* out, long long os_b, int i0, int W, double algo_bytes,
+                     cudaStream_t st) {
+    if (total_lines <= 0) return;
     enable1d_once();
     FinTables1d t(M);
-    if (N % M || Fc < 1 || Fc > N / 2 + 1 || i0 < 0 || i0 + W > M || NI < 1 || nparts < 1)
-        throw std::runtime_error("finish1d: bad sizes");
+    if (i0 < 0 || i0 + W > M || nseg < 1) throw std::runtime_error("finish1d: bad sizes");
     const unsigned char* cb = static_cast<const unsigned char*>(fin_tables);
     auto kern = kern1d_finish<float>(M);
     if (!kern) throw std::runtime_error("finish1d: no instance for M=" + std::to_string(M));
     Finish1<float> a{};
-    a.src = static_cast<const cx<float>*>(src); a.ss_g = ss_g; a.ss_part = ss_part; a.nparts = nparts;
-    a.phi = static_cast<const float*>(phi); a.N = N; a.Fc = Fc; a.scale = 1.0f / (float)N;
-    a.out = static_cast<float*>(out); a.os_b = os_b; a.chan = static_cast<const int*>(chan_dev); a.NI = NI;
-    a.G = (int)G; a.i0 = i0; a.W = W;
+    a.base[0] = static_cast<const cx<float>*>(base0); a.base[1] = static_cast<const cx<float>*>(base1);
+    a.base[2] = static_cast<const cx<float>*>(base2);
+    a.segs = static_cast<const FinSeg<float>*>(segs_dev); a.nseg = nseg; a.total = (int)total_lines;
+    a.out = static_cast<float*>(out); a.os_b = os_b; a.i0 = i0; a.W = W;
     a.twM = reinterpret_cast<const cx<float>*>(cb + t.tw); a.posM = reinterpret_cast<const int*>(cb + t.pos);
-    const size_t smem = ((size_t)M * k1LP + M) * sizeof(cx<float>) + (size_t)M * sizeof(int);
-    dim3 grid((unsigned)ceil_div((int)G, k1L));
-    launch("1d_finish:N" + std::to_string(N) + ":M" + std::to_string(M), algo_bytes, st,
-           [&] { kern<<<grid, block1d(), smem, st>>>(a); });
+    const size_t smem = ((size_t)M * k1FLP + M) * sizeof(cx<float>) + (size_t)(M + k1FL) * sizeof(int);
+    dim3 grid((unsigned)((total_lines + k1FL - 1) / k1FL));
+    launch("1d_finish:M" + std::to_string(M), algo_bytes, st, [&] { kern<<<grid, block1d(), smem, st>>>(a); });
 }
 
 }  // namespace sb

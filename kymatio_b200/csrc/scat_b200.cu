@@ -370,13 +370,14 @@ int scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int
                    void* stream) {
     return guarded([&] { col_fwd1d(tables_dev, z_dev, out_dev, G, N, algo_bytes, static_cast<cudaStream_t>(stream)); });
 }
-int scat1d_finish(const void* fin_tables_dev, const void* src_dev, int64_t ss_g, int64_t ss_part, int32_t nparts,
-                  const void* phi_dev, int32_t N, int32_t Fc, int32_t M, void* out_dev, int64_t os_b, const void* chan_dev,
-                  int32_t NI, int64_t G, int32_t i0, int32_t W, double algo_bytes, void* stream) {
+int scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1_dev, const void* part_dev,
+                  const void* segs_dev, int32_t nseg, int64_t total_lines, int32_t M, void* out_dev, int64_t os_b, int32_t i0,
+                  int32_t W, double algo_bytes, void* stream) {
     return guarded([&] {
-        finish1d(fin_tables_dev, src_dev, ss_g, ss_part, nparts, phi_dev, N, Fc, M, out_dev, os_b, chan_dev, NI, G, i0, W,
-                 algo_bytes, static_cast<cudaStream_t>(stream));
+        finish1d(fin_tables_dev, u0_dev, u1_dev, part_dev, segs_dev, nseg, total_lines, M, out_dev, os_b, i0, W, algo_bytes,
+                 static_cast<cudaStream_t>(stream));
     });
 }
+size_t scat1d_finseg_bytes(void) { return sizeof(FinSeg<float>); }
 
 }  // extern "C"

@@ -140,11 +140,16 @@ def schedule(Np, log2_stride, phi, psi1, psi2):
     return dict(M=M, K=1 + len(n1s) + len(pairs), groups=groups, order=order)
 
 
+_FINSEG = np.dtype([("src_off", "<i8"), ("ss_g", "<i8"), ("ss_part", "<i8"), ("phi", "<u8"), ("chan", "<u8"),
+                    ("which", "<i4"), ("nparts", "<i4"), ("N", "<i4"), ("Fc", "<i4"), ("NI", "<i4"), ("line0", "<i4")])
+
+
 class Engine1D:
     """One engine per (device, filter-buffer identity, Np, log2_stride)."""
 
     def __init__(self, Np, log2_stride, phi, psi1, psi2, device):
         self.lib = _lib.load()
+        assert self.lib.scat1d_finseg_bytes() == _FINSEG.itemsize
         self.device = torch.device(device)
         self.Np, self.ls = int(Np), int(log2_stride)
         if self.Np & (self.Np - 1):
@@ -161,6 +166,7 @@ class Engine1D:
             self.chan0 = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.tables.for_length(self.Np)        # validates Np
             self.groups = []
+            # per-signal workspace (complex elements): Y = largest group, U1 = every parent group, part = every leaf
             self.per_signal = dict(Y=0, U1=0, part=0)
             for g in sch["groups"]:
                 N1, NI = g["N1"], len(g["n1"])
@@ -171,11 +177,13 @@ class Engine1D:
                 gd.update(NI=NI, tab=self.tables.for_length(N1), **self._filter_arrays(filt, self.Np))
                 gd["chan_dev"] = torch.tensor(g["chan"], dtype=torch.int32, device=self.device)
                 gd["nparts"] = (_split(N1)[0] + 15) // 16
-                self.per_signal["Y"] = max(self.per_signal["Y"], NI * N1 * 8)
+                self.per_signal["Y"] = max(self.per_signal["Y"], NI * N1)
                 if g["children"]:
-                    self.per_signal["U1"] = max(self.per_signal["U1"], NI * N1 * 8)
+                    gd["u1_off"] = self.per_signal["U1"]
+                    self.per_signal["U1"] += NI * N1
                 else:
-                    self.per_signal["part"] = max(self.per_signal["part"], NI * gd["nparts"] * self.Fc[g["k1"]] * 8)
+                    gd["part_off"] = self.per_signal["part"]
+                    self.per_signal["part"] += NI * gd["nparts"] * self.Fc[g["k1"]]
                 kids = []
                 for c in g["children"]:
                     cd = dict(c)
@@ -185,11 +193,13 @@ class Engine1D:
                     cd.update(tab=self.tables.for_length(c["N2"]), **self._filter_arrays([f2] * NI, N1, same=True))
                     cd["chan_dev"] = torch.tensor(c["chan"], dtype=torch.int32, device=self.device)
                     cd["nparts"] = (_split(c["N2"])[0] + 15) // 16
-                    self.per_signal["Y"] = max(self.per_signal["Y"], NI * c["N2"] * 8)
-                    self.per_signal["part"] = max(self.per_signal["part"], NI * cd["nparts"] * self.Fc[c["level"]] * 8)
+                    self.per_signal["Y"] = max(self.per_signal["Y"], NI * c["N2"])
+                    cd["part_off"] = self.per_signal["part"]
+                    self.per_signal["part"] += NI * cd["nparts"] * self.Fc[c["level"]]
                     kids.append(cd)
                 gd["children"] = kids
                 self.groups.append(gd)
+            self._segs = {}
             torch.cuda.current_stream(self.device).synchronize()
 
     def _filter_arrays(self, filt, Npar, same=False):
@@ -204,10 +214,40 @@ class Engine1D:
             supp_dev=torch.tensor(supp, dtype=torch.int32, device=self.device).reshape(-1, 2).contiguous(),
             supp_len=[s[1] for s in supp])
 
+    def _segments(self, nb):
+        """Segment table of the finish launch for a chunk of nb signals (cached on the device)."""
+        hit = self._segs.get(nb)
+        if hit is not None:
+            return hit
+        rows, line, nbytes = [], 0, 0.0
+
+        def add(which, off, ss_g, ss_part, nparts, level, N, chan_dev, NI):
+            nonlocal line, nbytes
+            rows.append((off, ss_g, ss_part, self.phi_lv[level].data_ptr(), chan_dev.data_ptr(), which, nparts, N,
+                         self.Fc[level], NI, line))
+            line += nb * NI
+            nbytes += nb * NI * (nparts * self.Fc[level] * 8 + self.M * 4)
+
+        add(0, 0, self.Np, 0, 1, 0, self.Np, self.chan0, 1)
+        for g in self.groups:
+            NI, N1 = g["NI"], g["N1"]
+            if g["children"]:
+                add(1, nb * g["u1_off"], N1, 0, 1, g["k1"], N1, g["chan_dev"], NI)
+                for c in g["children"]:
+                    Fc = self.Fc[c["level"]]
+                    add(2, nb * c["part_off"], c["nparts"] * Fc, Fc, c["nparts"], c["level"], c["N2"], c["chan_dev"], NI)
+            else:
+                Fc = self.Fc[g["k1"]]
+                add(2, nb * g["part_off"], g["nparts"] * Fc, Fc, g["nparts"], g["k1"], N1, g["chan_dev"], NI)
+        arr = np.array(rows, dtype=_FINSEG)
+        dev = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+        hit = self._segs[nb] = (dev, len(rows), line, nbytes)
+        return hit
+
     # ------------------------------------------------------------------------------------------------
     def chunk_size(self, B):
         budget = int(os.environ.get("SCAT_B200_WS1D_MB", "6144")) << 20
-        per = max(1, sum(self.per_signal.values()))
+        per = max(1, 8 * sum(self.per_signal.values()))
         return max(1, min(B, budget // per))
 
     def forward(self, U0_hat):
@@ -222,42 +262,35 @@ class Engine1D:
         ps = self.per_signal
         with torch.cuda.device(dev):
             st = _stream(dev)
-            Y = torch.empty(max(8, Bc * ps["Y"]), dtype=torch.uint8, device=dev)
-            U1 = torch.empty(max(8, Bc * ps["U1"]), dtype=torch.uint8, device=dev)
-            part = torch.empty(max(8, Bc * ps["part"]), dtype=torch.uint8, device=dev)
+            Y = torch.empty(max(1, Bc * ps["Y"]) * 8, dtype=torch.uint8, device=dev)
+            U1 = torch.empty(max(1, Bc * ps["U1"]) * 8, dtype=torch.uint8, device=dev)
+            part = torch.empty(max(1, Bc * ps["part"]) * 8, dtype=torch.uint8, device=dev)
             yp, up, pp = Y.data_ptr(), U1.data_ptr(), part.data_ptr()
             for b0 in range(0, B, Bc):
                 nb = min(Bc, B - b0)
                 u0 = U0_hat.data_ptr() + b0 * Np * 8
-                op = out.data_ptr() + b0 * K * M * 4
-
-                def finish(src, ss_g, ss_part, nparts, level, N, chan_dev, NI, G):
-                    Fc = self.Fc[level]
-                    _lib.check(lib.scat1d_finish(self.fin_tab.data_ptr(), src, ss_g, ss_part, nparts,
-                                                 self.phi_lv[level].data_ptr(), N, Fc, M, op, K * M, chan_dev.data_ptr(),
-                                                 NI, G, 0, M, float(G) * (nparts * Fc * 8 + M * 4), st))
-
-                finish(u0, Np, 0, 1, 0, Np, self.chan0, 1, nb)
                 for g in self.groups:
                     NI, N1, G = g["NI"], g["N1"], nb * g["NI"]
                     tab = g["tab"].data_ptr()
                     _lib.check(lib.scat1d_col_prod(tab, u0, Np, 0, g["filt_dev"].data_ptr(), g["supp_dev"].data_ptr(), yp,
                                                    G, NI, Np, N1, float(nb) * 8 * (sum(g["supp_len"]) + NI * N1), st))
                     if g["children"]:
+                        u1 = up + nb * g["u1_off"] * 8
                         _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, None, 0, float(G) * N1 * 16, st))
-                        _lib.check(lib.scat1d_col_fwd(tab, yp, up, G, N1, float(G) * N1 * 16, st))
-                        finish(up, N1, 0, 1, g["k1"], N1, g["chan_dev"], NI, G)
+                        _lib.check(lib.scat1d_col_fwd(tab, yp, u1, G, N1, float(G) * N1 * 16, st))
                         for c in g["children"]:
                             N2, ctab = c["N2"], c["tab"].data_ptr()
                             Fc = self.Fc[c["level"]]
-                            _lib.check(lib.scat1d_col_prod(ctab, up, NI * N1, N1, c["filt_dev"].data_ptr(),
+                            _lib.check(lib.scat1d_col_prod(ctab, u1, NI * N1, N1, c["filt_dev"].data_ptr(),
                                                            c["supp_dev"].data_ptr(), yp, G, NI, N1, N2,
                                                            float(nb) * 8 * (sum(c["supp_len"]) + NI * N2), st))
-                            _lib.check(lib.scat1d_row_mod(ctab, yp, G, N2, pp, Fc,
+                            _lib.check(lib.scat1d_row_mod(ctab, yp, G, N2, pp + nb * c["part_off"] * 8, Fc,
                                                           float(G) * 8 * (N2 + c["nparts"] * Fc), st))
-                            finish(pp, c["nparts"] * Fc, Fc, c["nparts"], c["level"], N2, c["chan_dev"], NI, G)
                     else:
                         Fc = self.Fc[g["k1"]]
-                        _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, pp, Fc, float(G) * 8 * (N1 + g["nparts"] * Fc), st))
-                        finish(pp, g["nparts"] * Fc, Fc, g["nparts"], g["k1"], N1, g["chan_dev"], NI, G)
+                        _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, pp + nb * g["part_off"] * 8, Fc,
+                                                      float(G) * 8 * (N1 + g["nparts"] * Fc), st))
+                segs, nseg, lines, nbytes = self._segments(nb)
+                _lib.check(lib.scat1d_finish(self.fin_tab.data_ptr(), u0, up, pp, segs.data_ptr(), nseg, lines, M,
+                                             out.data_ptr() + b0 * K * M * 4, K * M, 0, M, nbytes, st))
         return out

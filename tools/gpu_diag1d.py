@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from kymatio_b200 import _lib  # noqa: E402
-from kymatio_b200.engine1d import _Tables, _split, _stream, circular_support  # noqa: E402
+from kymatio_b200.engine1d import _FINSEG, _Tables, _split, _stream, circular_support  # noqa: E402
 
 dev = torch.device("cuda:0")
 lib = _lib.load()
@@ -68,11 +68,15 @@ def run(N, k, NI, B, M, full_support=False):
     chan = torch.arange(NI, dtype=torch.int32, device=dev) + 1
     S = torch.zeros(B, K, M, device=dev)
     ft = tabs.for_lowpass(M)
-    _lib.check(lib.scat1d_finish(ft.data_ptr(), part.data_ptr(), nparts * Fc, Fc, nparts, phi.data_ptr(), N, Fc, M,
-                                 S.data_ptr(), K * M, chan.data_ptr(), NI, G, 0, M, 0.0, st))
+    rows = [(0, nparts * Fc, Fc, phi.data_ptr(), chan.data_ptr(), 2, nparts, N, Fc, NI, 0)]
+    segs = torch.from_numpy(np.array(rows, dtype=_FINSEG).view(np.uint8).copy()).to(dev)
+    _lib.check(lib.scat1d_finish(ft.data_ptr(), None, out.data_ptr(), part.data_ptr(), segs.data_ptr(), 1, G, M,
+                                 S.data_ptr(), K * M, 0, M, 0.0, st))
     S2 = torch.zeros(B, K, M, device=dev)
-    _lib.check(lib.scat1d_finish(ft.data_ptr(), out.data_ptr(), N, 0, 1, phi.data_ptr(), N, Fc, M,
-                                 S2.data_ptr(), K * M, chan.data_ptr(), NI, G, 0, M, 0.0, st))
+    rows2 = [(0, N, 0, phi.data_ptr(), chan.data_ptr(), 1, 1, N, Fc, NI, 0)]
+    segs2 = torch.from_numpy(np.array(rows2, dtype=_FINSEG).view(np.uint8).copy()).to(dev)
+    _lib.check(lib.scat1d_finish(ft.data_ptr(), None, out.data_ptr(), part.data_ptr(), segs2.data_ptr(), 1, G, M,
+                                 S2.data_ptr(), K * M, 0, M, 0.0, st))
     torch.cuda.synchronize()
     low = (U1 * phi).reshape(B, NI, N // M, M).mean(2)
     ref = torch.fft.ifft(low).real
