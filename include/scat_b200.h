@@ -182,6 +182,24 @@ int  scat_modulus_rotation(const void* x_dev, const void* prev_dev, void* out_de
 int  scat_compute_integrals(const void* x_dev, void* out_f64_dev, int64_t B, int64_t n, const void* powers_f32_dev,
                             int32_t P, int32_t dtype, void* stream);
 
+/* fused 3-D path (kymatio/scattering3d/core/scattering3d.py:24-73), float32, power-of-two volumes ---------
+ * One band (l, j) = cdgmm3d + ifft + modulus_rotation over its nm = 2l+1 filters + compute_integrals (+ rfft for
+ * parents) runs as: col_prod (filter product + inverse transform along M, all m in one launch) -> plane (2-D inverse
+ * of every (N, O) plane in shared memory, sum_m |.|^2 in registers, sqrt, voxel sums of U^q added to
+ * integ[b*istride + ioff + p] (float64 atomics), and for parents the 2-D forward of (U, 0)) -> col_fwd (forward
+ * along M).  u_dev / out_dev: (B, M, N, O) complex natural-order spectra; filt_dev: (nm, M, N, O) complex;
+ * y_dev: (B*nm, M, N, O) complex scratch; spec_dev: (B, M, N, O) complex scratch or NULL for a leaf band. */
+int    scat3d_supported(int32_t M, int32_t N, int32_t O);
+size_t scat3d_tables_bytes(int32_t M, int32_t N, int32_t O);
+int    scat3d_tables_init(void* tables_dev, int32_t M, int32_t N, int32_t O, void* stream);
+int    scat3d_col_prod(const void* tables_dev, const void* u_dev, const void* filt_dev, void* y_dev, int64_t B, int32_t nm,
+                       int32_t M, int32_t N, int32_t O, void* stream);
+int    scat3d_plane(const void* tables_dev, const void* y_dev, void* spec_dev, void* integ_f64_dev, int64_t istride,
+                    int32_t ioff, const void* powers_f32_dev, int32_t P, int64_t B, int32_t nm, int32_t M, int32_t N,
+                    int32_t O, void* stream);
+int    scat3d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t O,
+                      void* stream);
+
 /* adjoints for the autograd graph ------------------------------------------------
  * filter multiply with the filters broadcast over the batch: out[b][f][i] = a[b][i] * w[f][i] (w real);
  * adjoint = 1 computes ga[b][i] = sum_f a[b][f][i] * w[f][i]  (backward of cdgmm, backend/torch_backend.py:205-206) */

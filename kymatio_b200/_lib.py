@@ -87,6 +87,15 @@ SIGNATURES = {
     "scat_modulus_rotation": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_compute_integrals": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int32,
                                           _c.c_int32, _c.c_void_p]),
+    "scat3d_supported": (_c.c_int, [_c.c_int32, _c.c_int32, _c.c_int32]),
+    "scat3d_tables_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32, _c.c_int32]),
+    "scat3d_tables_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat3d_col_prod": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,
+                                   _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat3d_plane": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p,
+                                _c.c_int32, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat3d_col_fwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,
+                                  _c.c_void_p]),
     "scat_cdgmm_bcast": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int64,
                                     _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_subsample_fourier2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,

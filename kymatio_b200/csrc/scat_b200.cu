@@ -4,6 +4,7 @@
 #include "plan2d.cuh"
 #include "prims.cuh"
 #include "plan1d.cuh"
+#include "plan3d.cuh"
 
 using namespace sb;
 
@@ -379,5 +380,29 @@ int scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1
     });
 }
 size_t scat1d_finseg_bytes(void) { return sizeof(FinSeg<float>); }
+
+// ---------------------------------------------------------------- fused 3-D kernels (engine3d.py drives the cascade)
+int scat3d_supported(int32_t M, int32_t N, int32_t O) { return fused3d_supported(M, N, O) ? 1 : 0; }
+size_t scat3d_tables_bytes(int32_t M, int32_t N, int32_t O) {
+    try { return Tables3d(M, N, O).bytes; } catch (const std::exception& e) { last_error() = e.what(); return 0; }
+}
+int scat3d_tables_init(void* tables_dev, int32_t M, int32_t N, int32_t O, void* stream) {
+    return guarded([&] { tables3d_init(tables_dev, M, N, O, static_cast<cudaStream_t>(stream)); });
+}
+int scat3d_col_prod(const void* tables_dev, const void* u_dev, const void* filt_dev, void* y_dev, int64_t B, int32_t nm,
+                    int32_t M, int32_t N, int32_t O, void* stream) {
+    return guarded([&] { col_prod3d(tables_dev, u_dev, filt_dev, y_dev, B, nm, M, N, O, static_cast<cudaStream_t>(stream)); });
+}
+int scat3d_plane(const void* tables_dev, const void* y_dev, void* spec_dev, void* integ_f64_dev, int64_t istride, int32_t ioff,
+                 const void* powers_f32_dev, int32_t P, int64_t B, int32_t nm, int32_t M, int32_t N, int32_t O, void* stream) {
+    return guarded([&] {
+        plane3d(tables_dev, y_dev, spec_dev, integ_f64_dev, istride, ioff, powers_f32_dev, P, B, nm, M, N, O,
+                static_cast<cudaStream_t>(stream));
+    });
+}
+int scat3d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t O,
+                   void* stream) {
+    return guarded([&] { col_fwd3d(tables_dev, z_dev, out_dev, B, M, N, O, static_cast<cudaStream_t>(stream)); });
+}
 
 }  // extern "C"

@@ -526,6 +526,39 @@ def _fusable1d(U_0, backend_, filters, log2_stride, average_local):
         [p["j"] for p in filters[1]] + [0])) >= 16
 
 
+_engines3d = {}
+
+
+def _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend_, averaging):
+    """Same signature and return value as kymatio/scattering3d/core/scattering3d.py:1-75, or None when the
+    configuration is outside the fused kernels (the caller then runs the reference core on the eager primitives)."""
+    from .engine3d import Engine3D, Unsupported
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5):
+        return None
+    if any((not f.is_cuda) or f.dtype != torch.float32 or not f.is_contiguous() for f in filters[:L + 1]):
+        return None
+    # the frontend passes `averaging` as a closure over itself (scattering3d/frontend/torch_frontend.py:70-71)
+    powers = None
+    for cell in (getattr(averaging, "__closure__", None) or ()):
+        owner = cell.cell_contents
+        if hasattr(owner, "integral_powers") and getattr(owner, "method", "integral") == "integral":
+            powers = [float(q) for q in owner.integral_powers]
+    if not powers or len(powers) > 8 or max_order not in (1, 2):
+        return None
+    M, N, O = x.shape[1:4]
+    key = (x.device.index, M, N, O)
+    eng = _engines3d.get(key)
+    if eng is None:
+        try:
+            eng = _engines3d[key] = Engine3D(M, N, O, x.device)
+        except Unsupported:
+            _engines3d[key] = eng = False
+    if not eng:
+        return None
+    U0_hat = backend_.rfft(x)
+    return eng.forward(U0_hat, filters, bool(rotation_covariant), int(L), int(J), int(max_order), powers)
+
+
 def install(fused=True):
     """Register the backend module and (optionally) the fused core dispatcher. Idempotent."""
     import kymatio.scattering2d.frontend.torch_frontend as tf2d   # the unmodified reference
@@ -579,6 +612,23 @@ def install(fused=True):
     else:
         bf1d.scattering1d = reference_core1d
 
+    import kymatio.scattering3d.frontend.torch_frontend as tf3d
+    if "scattering3d" not in _originals:
+        _originals["scattering3d"] = tf3d.scattering3d
+    reference_core3d = _originals["scattering3d"]
+    if fused:
+        def dispatch3d(x, filters, rotation_covariant, L, J, max_order, backend, averaging):
+            if getattr(backend, "name", None) == NAME:
+                S = _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend, averaging)
+                if S is not None:
+                    return S
+            return reference_core3d(x, filters=filters, rotation_covariant=rotation_covariant, L=L, J=J,
+                                    max_order=max_order, backend=backend, averaging=averaging)
+        dispatch3d.__wrapped__ = reference_core3d
+        tf3d.scattering3d = dispatch3d
+    else:
+        tf3d.scattering3d = reference_core3d
+
     if fused:
         def dispatch(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type="array"):
             if getattr(backend_, "name", None) == NAME:
@@ -598,3 +648,6 @@ def uninstall():
     if "scattering1d" in _originals:
         import kymatio.scattering1d.frontend.base_frontend as bf1d
         bf1d.scattering1d = _originals["scattering1d"]
+    if "scattering3d" in _originals:
+        import kymatio.scattering3d.frontend.torch_frontend as tf3d
+        tf3d.scattering3d = _originals["scattering3d"]

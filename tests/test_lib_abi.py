@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "scat_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(scat_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(scat(?:1d|3d)?_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_and_binding_agree():
