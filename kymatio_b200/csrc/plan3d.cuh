@@ -9,25 +9,25 @@ namespace sb {
 
 inline bool fused3d_supported(int M, int N, int O) {
     auto p2 = [](int v) { return v >= 8 && (v & (v - 1)) == 0; };
-    return p2(M) && p2(N) && M <= 256 && N == O && N <= 128 && kern3d_col_prod<float>(M) && kern3d_plane<float>(N, O);
+    return p2(M) && p2(N) && M <= 256 && N == O && N >= 16 && N <= 128 && kern3d_col_prod<float>(M) && kern3d_plane<float>(N, O);
 }
 
-// [twM | twN | twO]
+// [twM | twN | twO | twO/2]
 struct Tables3d {
-    int n[3]; size_t tw[3], bytes;
+    int n[4]; size_t tw[4], bytes;
     Tables3d(int M, int N, int O) {
         if (!fused3d_supported(M, N, O))
-            throw std::runtime_error("fused 3-D kernels need power-of-two sizes with M in [8,256] and N == O in [8,128]");
-        n[0] = M; n[1] = N; n[2] = O;
+            throw std::runtime_error("fused 3-D kernels need power-of-two sizes with M in [8,256] and N == O in [16,128]");
+        n[0] = M; n[1] = N; n[2] = O; n[3] = O / 2;
         size_t off = 0;
-        for (int a = 0; a < 3; ++a) { tw[a] = off; off = align_up(off + (size_t)n[a] * sizeof(cx<float>), 256); }
+        for (int a = 0; a < 4; ++a) { tw[a] = off; off = align_up(off + (size_t)n[a] * sizeof(cx<float>), 256); }
         bytes = off;
     }
 };
 inline void tables3d_init(void* dev, int M, int N, int O, cudaStream_t st) {
     Tables3d t(M, N, O);
     std::vector<unsigned char> h(t.bytes, 0);
-    for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < 4; ++a) {
         auto tw = twiddle_table<float>(t.n[a]);
         memcpy(h.data() + t.tw[a], tw.data(), (size_t)t.n[a] * sizeof(cx<float>));
     }
@@ -36,7 +36,7 @@ inline void tables3d_init(void* dev, int M, int N, int O, cudaStream_t st) {
 }
 inline void enable3d_once() {
     static bool done = false;
-    if (!done) { kern3d_enable_smem(); kern1d_enable_smem(); done = true; }
+    if (!done) { kern3d_enable_smem(); done = true; }
 }
 
 inline void col_prod3d(const void* tables, const void* U, const void* filt, void* Y, long long B, int nm, int M, int N, int O,
@@ -47,13 +47,13 @@ inline void col_prod3d(const void* tables, const void* U, const void* filt, void
     const unsigned char* cb = static_cast<const unsigned char*>(tables);
     ColProd3<float> a{};
     a.U = static_cast<const cx<float>*>(U); a.filt = static_cast<const cx<float>*>(filt); a.Y = static_cast<cx<float>*>(Y);
-    a.B = (int)B; a.nm = nm; a.NO = N * O; a.scale = 1.0f / ((float)M * (float)N * (float)O);
-    a.twM = reinterpret_cast<const cx<float>*>(cb + t.tw[0]);
+    a.B = (int)B; a.nm = nm; a.NO = N * O; a.O = O; a.scale = 1.0f / ((float)M * (float)N * (float)O);
+    a.twM = reinterpret_cast<const cx<float>*>(cb + t.tw[0]); a.twO = reinterpret_cast<const cx<float>*>(cb + t.tw[2]);
     const size_t smem = ((size_t)M * k1LP + M) * sizeof(cx<float>);
     const size_t vol = (size_t)M * N * O * sizeof(cx<float>);
-    dim3 grid((unsigned)(B * nm * (a.NO / k1L)));
+    dim3 grid((unsigned)(B * (a.NO / k1L)));
     auto kern = kern3d_col_prod<float>(M);
-    launch("3d_col_prod:nm" + std::to_string(nm), (double)B * nm * 2.0 * vol + (double)nm * vol, st,
+    launch("3d_col_prod:nm" + std::to_string(nm), (double)B * (nm + 1.0) * vol + (double)nm * vol, st,
            [&] { kern<<<grid, block1d(), smem, st>>>(a); });
 }
 
@@ -68,30 +68,29 @@ inline void plane3d(const void* tables, const void* Y, void* spec, void* integ, 
     a.Y = static_cast<const cx<float>*>(Y); a.spec = static_cast<cx<float>*>(spec);
     a.integ = static_cast<double*>(integ); a.powers = static_cast<const float*>(powers); a.P = P;
     a.istride = istride; a.ioff = ioff; a.nm = nm; a.M = M;
-    a.twN = reinterpret_cast<const cx<float>*>(cb + t.tw[1]); a.twO = reinterpret_cast<const cx<float>*>(cb + t.tw[2]);
-    const size_t smem = ((size_t)N * (O + 1) + N + O) * sizeof(cx<float>);
+    a.twN = reinterpret_cast<const cx<float>*>(cb + t.tw[1]); a.twH = reinterpret_cast<const cx<float>*>(cb + t.tw[3]);
+    const size_t smem = ((size_t)N * (O / 2 + 1) + N + O / 2) * sizeof(cx<float>) + 8 * 32 * sizeof(double);
     const size_t vol = (size_t)M * N * O * sizeof(cx<float>);
-    dim3 grid((unsigned)(B * M));
+    dim3 grid((unsigned)(B * M * 2));
     auto kern = kern3d_plane<float>(N, O);
     launch(std::string(spec ? "3d_plane_parent:nm" : "3d_plane_leaf:nm") + std::to_string(nm),
-           (double)B * (nm + (spec ? 1.0 : 0.0)) * vol, st, [&] { kern<<<grid, k3Threads, smem, st>>>(a); });
+           (double)B * (nm + (spec ? 1.0 : 0.0)) * vol, st, [&] { kern<<<grid, plane_threads(N * O / 2), smem, st>>>(a); });
 }
 
-// forward transform along M of scrambled-M plane spectra: k1d_col_fwd with NA = M, NB = N*O
+// parents: radix-2 DIT along O + forward transform along M of the half-plane spectra (in place allowed)
 inline void col_fwd3d(const void* tables, const void* Z, void* out, long long B, int M, int N, int O, cudaStream_t st) {
     if (B <= 0) return;
     enable3d_once();
     Tables3d t(M, N, O);
     const unsigned char* cb = static_cast<const unsigned char*>(tables);
-    auto k = kern1d_cols<float>(M);
-    if (!k.col_fwd) throw std::runtime_error("col_fwd3d: no instance for M=" + std::to_string(M));
-    ColFwd1<float> a{};
-    a.Z = static_cast<const cx<float>*>(Z); a.out = static_cast<cx<float>*>(out); a.NB = N * O;
-    a.twA = reinterpret_cast<const cx<float>*>(cb + t.tw[0]);
+    auto kern = kern3d_col_fwd<float>(M);
+    ColFwd3<float> a{};
+    a.Z = static_cast<const cx<float>*>(Z); a.out = static_cast<cx<float>*>(out); a.B = (int)B; a.NO = N * O; a.O = O;
+    a.twM = reinterpret_cast<const cx<float>*>(cb + t.tw[0]); a.twO = reinterpret_cast<const cx<float>*>(cb + t.tw[2]);
     const size_t smem = ((size_t)M * k1LP + M) * sizeof(cx<float>);
     const size_t vol = (size_t)M * N * O * sizeof(cx<float>);
-    dim3 grid((unsigned)(B * (a.NB / k1L)));
-    launch("3d_col_fwd", (double)B * 2.0 * vol, st, [&] { k.col_fwd<<<grid, block1d(), smem, st>>>(a); });
+    dim3 grid((unsigned)(B * (a.NO / k1L)));
+    launch("3d_col_fwd", (double)B * 2.0 * vol, st, [&] { kern<<<grid, block1d(), smem, st>>>(a); });
 }
 
 }  // namespace sb

@@ -5,7 +5,7 @@
 namespace sb {
 
 #define SB_M3_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256)
-#define SB_P3_SIZES(X) X(8) X(16) X(32) X(64) X(128)
+#define SB_P3_SIZES(X) X(16) X(32) X(64) X(128)
 
 template <typename T> void (*kern3d_col_prod(int M))(ColProd3<T>) {
 #define SB_CASE(N) if (M == N) return k3d_col_prod<T, N>;
@@ -13,23 +13,29 @@ template <typename T> void (*kern3d_col_prod(int M))(ColProd3<T>) {
 #undef SB_CASE
     return nullptr;
 }
+template <typename T> void (*kern3d_col_fwd(int M))(ColFwd3<T>) {
+#define SB_CASE(N) if (M == N) return k3d_col_fwd<T, N>;
+    SB_M3_SIZES(SB_CASE)
+#undef SB_CASE
+    return nullptr;
+}
 template <typename T> void (*kern3d_plane(int N, int O))(Plane3<T>) {
-#define SB_CASE(S) if (N == S && O == S) return k3d_plane<T, S, S>;
+#define SB_CASE(S) if (N == S && O == S) return k3d_plane<T, S, S / 2>;
     SB_P3_SIZES(SB_CASE)
 #undef SB_CASE
     return nullptr;
 }
 void kern3d_enable_smem() {
-#define SB_EN(N) enable_big_smem(k3d_col_prod<float, N>);
+#define SB_EN(N) enable_big_smem(k3d_col_prod<float, N>); enable_big_smem(k3d_col_fwd<float, N>);
     SB_M3_SIZES(SB_EN)
 #undef SB_EN
-    // the plane kernel also has a small static array: leave room for it below the 227 KB limit
-#define SB_EN(S) SB_CUDA(cudaFuncSetAttribute(k3d_plane<float, S, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define SB_EN(S) enable_big_smem(k3d_plane<float, S, S / 2>);
     SB_P3_SIZES(SB_EN)
 #undef SB_EN
 }
 
 template void (*kern3d_col_prod<float>(int))(ColProd3<float>);
 template void (*kern3d_plane<float>(int, int))(Plane3<float>);
+template void (*kern3d_col_fwd<float>(int))(ColFwd3<float>);
 
 }  // namespace sb
