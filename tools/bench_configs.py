@@ -58,14 +58,14 @@ with torch.no_grad():
         Sr = Scattering1D(8, 2 ** 16, Q=(8, 1), backend="torch").cuda()
         Sb = Scattering1D(8, 2 ** 16, Q=(8, 1), backend="torch_b200").cuda()
         report("C3 1D J=8 Q=(8,1) N=2^16", "signals/s", B, timeit(lambda: Sr(x), n=3), timeit(lambda: Sb(x), n=3),
-               "torch_b200 1D is the eager per-primitive path; reduced batch 32")
+               "fused 1-D path; reduced batch 32 (see tools/bench1d.py for batch 256)")
     if "c4" in which:
         B = 2
         x = torch.randn(B, 128, 128, 128, device="cuda")
         Sr = HarmonicScattering3D(2, (128, 128, 128), L=2, backend="torch").cuda()
         Sb = HarmonicScattering3D(2, (128, 128, 128), L=2, backend="torch_b200").cuda()
         report("C4 3D J=2 L=2 128^3", "volumes/s", B, timeit(lambda: Sr(x), n=2, warm=1), timeit(lambda: Sb(x), n=2, warm=1),
-               "torch_b200 3D is the eager per-primitive path; reduced batch 2")
+               "fused 3-D path; reduced batch 2 (see tools/bench3d.py for batch 16)")
 if "c5" in which:
     B = 64
     Sr, Sb = Scattering2D(4, (224, 224), backend="torch").cuda(), Scattering2D(4, (224, 224), backend="torch_b200").cuda()
@@ -74,7 +74,7 @@ if "c5" in which:
         x = torch.randn(B, 224, 224, device="cuda", requires_grad=True)
         S(x).sum().backward()
     report("C5 2D J=4 L=8 224x224 forward+backward", "images/s", B, timeit(lambda: fb(Sr), n=2, warm=1),
-           timeit(lambda: fb(Sb), n=2, warm=1), "backward of torch_b200 is the recomputed eager graph; reduced batch 64")
+           timeit(lambda: fb(Sb), n=2, warm=1), "backward: fused second-order tiles + recomputed first-order graph; reduced batch 64")
     with torch.no_grad():
         x = torch.randn(B, 224, 224, device="cuda")
         report("C5 2D J=4 L=8 224x224 forward only", "images/s", B, timeit(lambda: Sr(x), n=2, warm=1), timeit(lambda: Sb(x), n=10))
