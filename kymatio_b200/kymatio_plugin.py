@@ -39,9 +39,16 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+NOT_DIFFERENTIABLE = ("The torch_b200 backend does not propagate gradients through this path yet (2-D scattering is "
+                      "differentiable; 1-D, 3-D and the eager primitives are forward-only, like kymatio's torch_skcuda "
+                      "backend). Call it under torch.no_grad() or use backend='torch' for gradients.")
+
+
 def _cuda_check(x):
     if not x.is_cuda:
         raise TypeError("The torch_b200 backend needs CUDA tensors. Use the torch backend for CPU tensors.")
+    if x.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError(NOT_DIFFERENTIABLE)        # never hand back a silently detached result
 
 
 def _dtype_code(x):
@@ -535,6 +542,8 @@ def _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend
     from .engine3d import Engine3D, Unsupported
     if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5):
         return None
+    if x.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError(NOT_DIFFERENTIABLE)
     if any((not f.is_cuda) or f.dtype != torch.float32 or not f.is_contiguous() for f in filters[:L + 1]):
         return None
     # the frontend passes `averaging` as a closure over itself (scattering3d/frontend/torch_frontend.py:70-71)

@@ -136,3 +136,14 @@ def test_fused1d_falls_back_outside_scope(plugin):
     assert len(y) == len(ref)
     for a, b in zip(y, ref):
         assert np.abs(a["coef"].cpu().numpy() - b["coef"]).max() <= 1e-4 * np.abs(b["coef"]).max() + 1e-7
+
+
+def test_1d_gradient_request_fails_loudly(plugin):
+    # forward-only path: never return a silently detached tensor
+    from kymatio.torch import Scattering1D
+    S = Scattering1D(J=4, shape=1024, Q=2, backend="torch_b200").cuda()
+    x = torch.randn(2, 1024, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="does not propagate gradients"):
+        S(x)
+    with torch.no_grad():
+        assert S(x).shape[0] == 2

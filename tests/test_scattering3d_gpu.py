@@ -119,3 +119,11 @@ def test_fused3d_matches_eager_primitives(plugin):
     finally:
         plugin.install(fused=True)
     assert ((y - ye).abs() / ye.abs().clamp_min(1e-30)).max().item() < 1e-4
+
+
+def test_3d_gradient_request_fails_loudly(plugin):
+    from kymatio.torch import HarmonicScattering3D
+    S = HarmonicScattering3D(J=1, shape=(16, 16, 16), L=1, backend="torch_b200").cuda()
+    x = torch.randn(1, 16, 16, 16, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="does not propagate gradients"):
+        S(x)
