@@ -292,6 +292,14 @@ def run_b200_arm(args):
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     top = kern["rows"][0]
     achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same batch only)
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["label"])
+        if t and int(t["batch"]) == B:
+            traffic = float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -305,7 +313,7 @@ def run_b200_arm(args):
                 "note": f"pinned host in/out, {nchunk} chunks pipelined on {len(streams)} streams, wall clock, max over ranks"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "kernel": top["label"],
+                     "frac": achieved / hbm_peak, "traffic": traffic, "kernel": top["label"],
                      "kernel_share_of_step": top["ms"] / kern["total_ms"], "peak_source": peak_src,
                      "step_pass_model": {"bytes_per_image": PASS_MODEL_BYTES_PER_IMAGE,
                                          "achieved": value / world * PASS_MODEL_BYTES_PER_IMAGE / 1e9,

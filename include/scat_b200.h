@@ -214,6 +214,16 @@ int  scat_modulus_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_
 int  scat_pad2d_bwd(const void* gout_dev, void* gx_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
                     int32_t left, int32_t right, int32_t dtype, void* stream);
 
+/* adjoints of the 1-D / 3-D eager primitives (gradients through backend='torch_b200' Scattering1D / HarmonicScattering3D):
+ * periodisation -> replicate / k; sqrt(prev^2 + |x|^2) -> (x, prev) g / out (gprev_dev, prev_dev may be NULL);
+ * integrals -> sum_p g[b][p] q_p x^(q_p - 1).  scat_cdgmm with b_is_complex = 2 multiplies by conj(b) (adjoint of cdgmm3d). */
+int  scat_subsample_fourier1d_bwd(const void* gout_dev, void* gin_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
+                                  void* stream);
+int  scat_modulus_rotation_bwd(const void* x_dev, const void* prev_dev, const void* out_dev, const void* g_dev, void* gx_dev,
+                               void* gprev_dev, int64_t n, int32_t dtype, void* stream);
+int  scat_compute_integrals_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t B, int64_t n,
+                                const void* powers_f32_dev, int32_t P, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,12 @@ SIGNATURES = {
                                     _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_subsample_fourier2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,
                                                 _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_subsample_fourier1d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,
+                                                _c.c_void_p]),
+    "scat_modulus_rotation_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                             _c.c_int64, _c.c_int32, _c.c_void_p]),
+    "scat_compute_integrals_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p,
+                                              _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_modulus_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_pad2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int32] * 7 + [_c.c_void_p]),
 }

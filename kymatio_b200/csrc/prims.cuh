@@ -31,7 +31,7 @@ __global__ void kp_cdgmm(const cx<T>* __restrict__ A, const T* __restrict__ B, c
     const cx<T> a = A[i];
     if (b_complex) {
         const cx<T> w = reinterpret_cast<const cx<T>*>(B)[j];
-        out[i] = cmul(a, w);
+        out[i] = b_complex == 2 ? cmulc(a, w) : cmul(a, w);       // 2: multiply by conj(B) (adjoint of the complex product)
     } else {
         const T w = B[j];
         out[i] = mk<T>(a.x * w, a.y * w);
@@ -141,6 +141,44 @@ __global__ void kp_pad2d_bwd(const T* __restrict__ gout, T* __restrict__ gx, int
     const size_t b = blockIdx.z;
     if (c >= P1) return;
     atomicAdd(&gx[(b * M + reflect_idx(r - top, M)) * N + reflect_idx(c - left, N)], gout[(b * P0 + r) * P1 + c]);
+}
+
+// adjoint of the 1-D Fourier periodisation: gin[g][t] = gout[g][t mod (n/k)] / k
+template <typename T>
+__global__ void kp_periodize1d_bwd(const cx<T>* __restrict__ gout, cx<T>* __restrict__ gin, int n, int k) {
+    const int m = n / k;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = blockIdx.y;
+    if (t >= n) return;
+    gin[g * n + t] = scal(gout[g * m + t % m], T(1) / T(k));
+}
+// adjoint of out = sqrt(prev^2 + |x|^2): gx = x g / out, gprev = prev g / out (0 where out = 0); prev / gprev may be null
+template <typename T>
+__global__ void kp_modrot_bwd(const cx<T>* __restrict__ x, const T* __restrict__ prev, const T* __restrict__ out,
+                              const T* __restrict__ g, cx<T>* __restrict__ gx, T* __restrict__ gprev, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T o = out[i];
+    const T s = o > T(0) ? g[i] / o : T(0);
+    const cx<T> v = x[i];
+    gx[i] = mk<T>(v.x * s, v.y * s);
+    if (gprev) gprev[i] = prev[i] * s;
+}
+// adjoint of the integrals out[b][p] = sum_i x[b][i]^q_p: gx[b][i] = sum_p g[b][p] q_p x^(q_p - 1)
+template <typename T>
+__global__ void kp_integrals_bwd(const T* __restrict__ x, const T* __restrict__ g, T* __restrict__ gx, size_t n,
+                                 const float* __restrict__ powers, int P) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t b = blockIdx.y;
+    if (i >= n) return;
+    const T v = x[b * n + i];
+    T acc = T(0);
+    for (int p = 0; p < P; ++p) {
+        const T q = T(powers[p]);
+        const T d = q == T(1) ? T(1) : q == T(2) ? T(2) * v : (v > T(0) ? q * pow(v, q - T(1)) : T(0));
+        acc += g[b * P + p] * d;
+    }
+    gx[b * n + i] = acc;
 }
 
 inline unsigned blocks_for(size_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }

@@ -405,4 +405,43 @@ int scat3d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int
     return guarded([&] { col_fwd3d(tables_dev, z_dev, out_dev, B, M, N, O, static_cast<cudaStream_t>(stream)); });
 }
 
+// ---------------------------------------------------------------- adjoints of the 1-D / 3-D eager primitives
+int scat_subsample_fourier1d_bwd(const void* gout_dev, void* gin_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
+                                 void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (k < 1 || N % k) throw std::runtime_error("subsample_fourier: k must divide the length");
+        if (G <= 0) return;
+        dim3 grid(ceil_div(N, 256), (unsigned)G);
+        SB_DISPATCH(dtype, launch("prim_periodize1d_bwd", (double)G * N * sizeof(cx<T>), st, [&] {
+            kp_periodize1d_bwd<T><<<grid, 256, 0, st>>>(static_cast<const cx<T>*>(gout_dev), static_cast<cx<T>*>(gin_dev), N, k);
+        }));
+    });
+}
+int scat_modulus_rotation_bwd(const void* x_dev, const void* prev_dev, const void* out_dev, const void* g_dev, void* gx_dev,
+                              void* gprev_dev, int64_t n, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (n <= 0) return;
+        SB_DISPATCH(dtype, launch("prim_modulus_rotation_bwd", (double)n * 8 * sizeof(T), st, [&] {
+            kp_modrot_bwd<T><<<blocks_for((size_t)n), 256, 0, st>>>(
+                static_cast<const cx<T>*>(x_dev), static_cast<const T*>(prev_dev), static_cast<const T*>(out_dev),
+                static_cast<const T*>(g_dev), static_cast<cx<T>*>(gx_dev), static_cast<T*>(gprev_dev), (size_t)n);
+        }));
+    });
+}
+int scat_compute_integrals_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t B, int64_t n,
+                               const void* powers_f32_dev, int32_t P, int32_t dtype, void* stream) {
+    return guarded([&] {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (B <= 0 || n <= 0) return;
+        dim3 grid(blocks_for((size_t)n), (unsigned)B);
+        SB_DISPATCH(dtype, launch("prim_integrals_bwd", (double)B * n * 2 * sizeof(T), st, [&] {
+            kp_integrals_bwd<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x_dev), static_cast<const T*>(g_dev),
+                                                      static_cast<T*>(gx_dev), (size_t)n,
+                                                      static_cast<const float*>(powers_f32_dev), P);
+        }));
+    });
+}
+
 }  // extern "C"

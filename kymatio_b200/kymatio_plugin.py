@@ -39,15 +39,19 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-NOT_DIFFERENTIABLE = ("The torch_b200 backend does not propagate gradients through this path yet (2-D scattering is "
-                      "differentiable; 1-D, 3-D and the eager primitives are forward-only, like kymatio's torch_skcuda "
-                      "backend). Call it under torch.no_grad() or use backend='torch' for gradients.")
+NOT_DIFFERENTIABLE = ("The torch_b200 backend does not propagate gradients through this primitive (the fused 2-D path and "
+                      "the 1-D / 3-D backends are differentiable; the 2-D eager primitives are forward-only, like "
+                      "kymatio's torch_skcuda backend). Call it under torch.no_grad() or use install(fused=True).")
 
 
-def _cuda_check(x):
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _cuda_check(x, differentiable=False):
     if not x.is_cuda:
         raise TypeError("The torch_b200 backend needs CUDA tensors. Use the torch backend for CPU tensors.")
-    if x.requires_grad and torch.is_grad_enabled():
+    if not differentiable and _wants_grad(x):
         raise RuntimeError(NOT_DIFFERENTIABLE)        # never hand back a silently detached result
 
 
@@ -148,7 +152,7 @@ class TorchB200Backend2D:
         return out
 
     @classmethod
-    def cdgmm(cls, A, B):
+    def _cdgmm_checks(cls, A, B):
         # kymatio/backend/torch_backend.py:181-219
         if not cls._is_real(B):
             cls.complex_contiguous_check(B)
@@ -168,7 +172,11 @@ class TorchB200Backend2D:
         if B.device.type == "cpu":
             if A.device.type == "cuda":
                 raise TypeError("Input must be on CPU.")
-            _cuda_check(A)
+
+    @classmethod
+    def cdgmm(cls, A, B):
+        cls._cdgmm_checks(A, B)
+        _cuda_check(A)
         n = B.numel() // B.shape[-1]
         out = torch.empty_like(A)
         with torch.cuda.device(A.device):
@@ -280,7 +288,66 @@ class _Fft1dTables:
         return buf
 
 
-class TorchB200Backend1D(TorchB200Backend2D):
+class _DifferentiableEager:
+    """Routes the generic primitives through kymatio_b200.ops_eager (kernel + hand-written adjoint) whenever a gradient
+    is requested; otherwise the plain forward kernels of TorchB200Backend2D run."""
+
+    @classmethod
+    def _n_total(cls, x):
+        return x.shape[-2]
+
+    @classmethod
+    def modulus(cls, x):
+        if not _wants_grad(x):
+            return super().modulus(x)
+        from . import ops_eager
+        cls.complex_contiguous_check(x)
+        _cuda_check(x, True)
+        return ops_eager.modulus(x)
+
+    @classmethod
+    def cdgmm(cls, A, B):
+        if not _wants_grad(A):
+            return super().cdgmm(A, B)
+        from . import ops_eager
+        cls._cdgmm_checks(A, B)
+        _cuda_check(A, True)
+        return ops_eager.Cdgmm.apply(A, B)
+
+    @classmethod
+    def _dfft(cls, x, inverse):
+        from . import ops_eager
+        _cuda_check(x, True)
+        return ops_eager.FftN.apply(x, inverse, cls._fft, cls._n_total(x))
+
+    @classmethod
+    def rfft(cls, x):
+        if not _wants_grad(x):
+            return super().rfft(x)
+        from . import ops_eager
+        cls.contiguous_check(x)
+        cls.real_check(x)
+        return cls._dfft(ops_eager.FromReal.apply(x), False)
+
+    @classmethod
+    def ifft(cls, x):
+        if not _wants_grad(x):
+            return super().ifft(x)
+        cls.contiguous_check(x)
+        cls.complex_check(x)
+        return cls._dfft(x, True)
+
+    @classmethod
+    def irfft(cls, x):
+        if not _wants_grad(x):
+            return super().irfft(x)
+        from . import ops_eager
+        cls.contiguous_check(x)
+        cls.complex_check(x)
+        return ops_eager.RealPart.apply(cls._dfft(x, True))
+
+
+class TorchB200Backend1D(_DifferentiableEager, TorchB200Backend2D):
     """Same generic primitives (checks, modulus, cdgmm) plus the 1-D specific ones."""
     Pad = None
 
@@ -288,6 +355,10 @@ class TorchB200Backend1D(TorchB200Backend2D):
     def subsample_fourier(cls, x, k):
         # kymatio/scattering1d/backend/torch_backend.py:19-48
         cls.complex_check(x)
+        if _wants_grad(x):
+            from . import ops_eager
+            _cuda_check(x, True)
+            return ops_eager.SubsampleFourier1d.apply(x, int(k))
         _cuda_check(x)
         x = x.contiguous()
         N = x.shape[-2]
@@ -304,6 +375,10 @@ class TorchB200Backend1D(TorchB200Backend2D):
             raise ValueError("torch_b200 implements reflect padding only.")
         if (pad_left >= x.shape[-1]) or (pad_right >= x.shape[-1]):
             raise ValueError("Indefinite padding size (larger than tensor).")
+        if _wants_grad(x):
+            from . import ops_eager
+            _cuda_check(x, True)
+            return ops_eager.Pad1d.apply(x, int(pad_left), int(pad_right))[..., None]
         _cuda_check(x)
         x = x.contiguous()
         N = x.shape[-1]
@@ -332,6 +407,8 @@ class TorchB200Backend1D(TorchB200Backend2D):
     def cfft(cls, x):
         cls.contiguous_check(x)
         cls.complex_check(x)
+        if _wants_grad(x):
+            return cls._dfft(x, False)
         _cuda_check(x)
         return cls._fft(x, False)
 
@@ -389,7 +466,7 @@ class _Fft3dTables:
         return buf
 
 
-class TorchB200Backend3D(TorchB200Backend2D):
+class TorchB200Backend3D(_DifferentiableEager, TorchB200Backend2D):
     Pad = None
 
     @staticmethod
@@ -410,12 +487,20 @@ class TorchB200Backend3D(TorchB200Backend2D):
         return out
 
     @classmethod
+    def _n_total(cls, x):
+        return x.shape[-4] * x.shape[-3] * x.shape[-2]
+
+    @classmethod
     def cdgmm3d(cls, A, B):
         return cls.cdgmm(A, B)
 
     @staticmethod
     def modulus_rotation(x, module=None):
         # torch_backend.py:102-124
+        if _wants_grad(x, module):
+            from . import ops_eager
+            _cuda_check(x, True)
+            return ops_eager.ModulusRotation.apply(x, module)
         _cuda_check(x)
         x = x.contiguous()
         out = torch.empty(x.shape[:-1] + (1,), dtype=x.dtype, device=x.device)
@@ -428,6 +513,10 @@ class TorchB200Backend3D(TorchB200Backend2D):
     @staticmethod
     def compute_integrals(input_array, integral_powers):
         # torch_backend.py:127-151 (the result takes torch's default dtype there, which is kept)
+        if _wants_grad(input_array):
+            from . import ops_eager
+            _cuda_check(input_array, True)
+            return ops_eager.ComputeIntegrals.apply(input_array, tuple(float(q) for q in integral_powers))
         _cuda_check(input_array)
         x = input_array.contiguous()
         B = x.shape[0]
@@ -523,6 +612,8 @@ def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
 def _fusable1d(U_0, backend_, filters, log2_stride, average_local):
     if getattr(backend_, "name", None) != NAME or not average_local:
         return False
+    if _wants_grad(U_0):
+        return False                      # gradients: the unchanged core drives the differentiable eager primitives
     if not (torch.is_tensor(U_0) and U_0.is_cuda and U_0.dtype == torch.float32 and U_0.dim() == 4):
         return False
     if filters[0]["levels"][0].dtype != torch.float32 or not filters[0]["levels"][0].is_cuda:
@@ -542,8 +633,8 @@ def _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend
     from .engine3d import Engine3D, Unsupported
     if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5):
         return None
-    if x.requires_grad and torch.is_grad_enabled():
-        raise RuntimeError(NOT_DIFFERENTIABLE)
+    if _wants_grad(x):
+        return None                       # gradients: the unchanged core drives the differentiable eager primitives
     if any((not f.is_cuda) or f.dtype != torch.float32 or not f.is_contiguous() for f in filters[:L + 1]):
         return None
     # the frontend passes `averaging` as a closure over itself (scattering3d/frontend/torch_frontend.py:70-71)

@@ -170,3 +170,11 @@ def test_fft_against_torch(plugin, shape):
         be.ifft(x)
     with pytest.raises(RuntimeError):
         be.ifft(z[::2])
+
+
+def test_2d_eager_primitives_refuse_gradients(plugin):
+    """The 2-D eager primitives are forward-only (gradients come from the fused path): asking for a gradient
+    through them raises instead of returning a silently detached tensor."""
+    x = torch.randn(2, 8, 8, 2, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="does not propagate gradients"):
+        plugin.backend2d.modulus(x)
