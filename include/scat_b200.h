@@ -154,6 +154,13 @@ int    scat1d_row_mod(const void* tables_dev, void* y_dev, int64_t G, int32_t N,
 /* second half of rfft: natural-order spectrum (G, N) out */
 int    scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t G, int32_t N, double algo_bytes,
                       void* stream);
+/* whole path in ONE launch for short transforms (N <= scat1d_tile_max()): product + periodise, inverse, modulus, forward
+ * all in one CTA's shared memory; writes the natural-order spectrum to spec_dev (G, N) when non-NULL (parents) and/or
+ * the Fc lowest bins to part_dev (G, Fc) when non-NULL (leaves: one "partial" per path for scat1d_finish) */
+int    scat1d_tile_max(void);
+int    scat1d_tile(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
+                   const void* supp_dev, void* spec_dev, void* part_dev, int32_t Fc, int64_t G, int32_t NI, int32_t Npar,
+                   int32_t N, double algo_bytes, void* stream);
 /* cdgmm(phi) -> subsample_fourier(N/M) -> irfft -> unpad[i0:i0+W] (core/scattering1d.py:72-77,101-105 and
  * frontend/base_frontend.py:137-139) for every path of a batch chunk in ONE launch.  Line (= path) `line` belongs to
  * the last segment with line0 <= line; with gl = line - line0 = b*NI + i its spectrum is

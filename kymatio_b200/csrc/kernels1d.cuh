@@ -218,6 +218,101 @@ template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 3) k1
     }
 }
 
+// ------------------------------------------------------------------ whole path in one CTA (N <= 8192)
+// Short paths fit one CTA's shared memory as the [NA][NB] matrix (pitch NB+1): product + periodise, four-step inverse
+// (columns, twiddle, rows with the modulus fused), four-step forward (rows, twiddle, columns) and the natural-order
+// spectrum is read straight out of shared memory - no Y round trip through HBM and no pruned column DFT.
+template <typename T> struct Tile1 {
+    const cx<T>* parent; long long ps_b, ps_i;
+    const T* const* filt; const int2* supp;
+    cx<T>* spec;                                 // parents: [G][N] natural-order spectrum; else nullptr
+    cx<T>* part; int Fc;                         // leaves: part[g][Fc] (the Fc lowest bins); else nullptr
+    int NI, Npar, k;
+    T scale;
+    const cx<T>* twA; const cx<T>* twB; const int* invA;
+    TwN<T> w;
+};
+template <typename T, int NA, int NB> __global__ void __launch_bounds__(k1Threads, 3) k1d_tile(Tile1<T> a) {
+    constexpr int W = NB + 1, N = NA * NB;
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* twA = s + (size_t)NA * W;
+    cx<T>* twB = twA + NA;
+    const cx<T>* hi = a.w.hi; const cx<T>* lo = a.w.lo;
+    const int* __restrict__ invA = a.invA;
+    const int g = blockIdx.x;
+    const int i = g % a.NI, b = g / a.NI;
+    const int tid = flat_tid(), nt = flat_nt();
+    stage(twA, a.twA, NA);
+    stage(twB, a.twB, NB);
+    const cx<T>* __restrict__ pb = a.parent + (long long)b * a.ps_b + (long long)i * a.ps_i;
+    const T* __restrict__ fb = a.filt[i];
+    const int2 sp = a.supp[i];
+    const int KNA = a.k * NA, Npar = a.Npar;
+    const int Rb = sp.x / NB;
+    const int nr = min(KNA, (sp.x - Rb * NB + sp.y + NB - 1) / NB);
+    const int amax = (nr + NA - 1) / NA;
+    constexpr int CELLS = NA * (NB / 2), U = 4;
+    for (int base = 0; base < CELLS; base += U * k1Threads) {
+        T acc[U][4];
+#pragma unroll
+        for (int c = 0; c < U; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = T(0);
+        for (int ai = 0; ai < amax; ++ai) {
+            cxpair<T> v[U]; repair<T> f[U];
+#pragma unroll
+            for (int c = 0; c < U; ++c) {
+                const int idx = base + c * k1Threads + tid;
+                const int f1 = idx / (NB / 2), l = 2 * (idx - f1 * (NB / 2));
+                const int d = ((f1 - Rb) & (NA - 1)) + ai * NA;
+                int R = Rb + d;
+                if (R >= KNA) R -= KNA;
+                const int off = R * NB + l;
+                int rel = off - sp.x;
+                if (rel < 0) rel += Npar;
+                const bool in = (idx < CELLS) & (d < nr) & ((rel < sp.y) | (rel == Npar - 1));
+                v[c] = ld_pred<cxpair<T>>(pb + off, in);
+                f[c] = ld8_pred<repair<T>>(fb + off, in);
+            }
+#pragma unroll
+            for (int c = 0; c < U; ++c) {
+                acc[c][0] += v[c].a.x * f[c].a; acc[c][1] += v[c].a.y * f[c].a;
+                acc[c][2] += v[c].b.x * f[c].b; acc[c][3] += v[c].b.y * f[c].b;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < U; ++c) {
+            const int idx = base + c * k1Threads + tid;
+            if (idx < CELLS) {
+                const int f1 = idx / (NB / 2), l = 2 * (idx - f1 * (NB / 2));
+                s[f1 * W + l] = mk<T>(acc[c][0] * a.scale, acc[c][1] * a.scale);
+                s[f1 * W + l + 1] = mk<T>(acc[c][2] * a.scale, acc[c][3] * a.scale);
+            }
+        }
+    }
+    __syncthreads();
+    slab_fft_s<NA, false, +1, 1, W, T>(s, NB, twA);                    // inverse over f1 (columns): row p holds t1 = invA[p]
+    for (int idx = tid; idx < N; idx += nt) {
+        const int p = idx / NB, e = idx - p * NB;
+        s[p * W + e] = cmulc(s[p * W + e], twn(hi, lo, a.w.lb, e * __ldg(invA + p)));
+    }
+    __syncthreads();
+    slab_fft_s<NB, false, +1, W, 1, T, true>(s, NA, twB);              // inverse over f2 (rows) + modulus
+    slab_fft_s<NB, true, -1, W, 1, T>(s, NA, twB);                     // forward over t2 (rows): natural f2'
+    for (int idx = tid; idx < N; idx += nt) {
+        const int p = idx / NB, e = idx - p * NB;
+        s[p * W + e] = cmul(s[p * W + e], twn(hi, lo, a.w.lb, e * __ldg(invA + p)));
+    }
+    __syncthreads();
+    slab_fft_s<NA, true, -1, 1, W, T>(s, NB, twA);                     // forward over t1 (columns): natural f1'
+    if (a.spec) {
+        cx<T>* ob = a.spec + (size_t)g * N;
+        for (int idx = tid; idx < N; idx += nt) { const int f1 = idx / NB, e = idx - f1 * NB; ob[idx] = s[f1 * W + e]; }
+    }
+    if (a.part) {
+        cx<T>* pb2 = a.part + (size_t)g * a.Fc;
+        for (int f = tid; f < a.Fc; f += nt) { const int f1 = f / NB, e = f - f1 * NB; pb2[f] = s[f1 * W + e]; }
+    }
+}
+
 // ------------------------------------------------------------------ low-pass tail on the lowest Fc bins
 // One launch serves every path of a batch chunk: the lines (one per path) are described by segments, one per
 // launch group (S0, each first-order group, each (j1, n2) second-order group).
@@ -298,6 +393,8 @@ template <typename T> struct KernRow1d {
 template <typename T> Kern1d<T> kern1d_cols(int NA);                 // nullptr entries when NA is not compiled
 template <typename T> KernRow1d<T> kern1d_rows(int NB);
 template <typename T> void (*kern1d_finish(int M))(Finish1<T>);
+template <typename T> void (*kern1d_tile(int NA, int NB))(Tile1<T>);
+constexpr int k1TileMaxN = 8192;
 void kern1d_enable_smem();
 
 }  // namespace sb

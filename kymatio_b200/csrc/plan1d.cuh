@@ -143,6 +143,32 @@ inline void col_fwd1d(const void* tables, const void* Z, void* out, long long G,
     launch("1d_col_fwd:N" + std::to_string(N), algo_bytes, st, [&] { k.col_fwd<<<grid, block1d(), smem, st>>>(a); });
 }
 
+inline void tile1d(const void* tables, const void* parent, long long ps_b, long long ps_i, const void* filt_dev,
+                   const void* supp_dev, void* spec, void* part, int Fc, long long G, int NI, int Npar, int N,
+                   double algo_bytes, cudaStream_t st) {
+    if (G <= 0) return;
+    enable1d_once();
+    Tables1d t(N);
+    if (Npar % N || NI < 1 || N > k1TileMaxN) throw std::runtime_error("tile1d: bad sizes");
+    if (part && (Fc < 1 || Fc > N / 2 + 1)) throw std::runtime_error("tile1d: Fc out of range");
+    const unsigned char* cb = static_cast<const unsigned char*>(tables);
+    auto kern = kern1d_tile<float>(t.sp.Na, t.sp.Nb);
+    if (!kern) throw std::runtime_error("tile1d: no instance for N=" + std::to_string(N));
+    Tile1<float> a{};
+    a.parent = static_cast<const cx<float>*>(parent); a.ps_b = ps_b; a.ps_i = ps_i;
+    a.filt = static_cast<const float* const*>(filt_dev); a.supp = static_cast<const int2*>(supp_dev);
+    a.spec = static_cast<cx<float>*>(spec); a.part = static_cast<cx<float>*>(part); a.Fc = Fc;
+    a.NI = NI; a.Npar = Npar; a.k = Npar / N;
+    a.scale = 1.0f / ((float)N * (float)a.k);
+    a.twA = reinterpret_cast<const cx<float>*>(cb + t.twa); a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb);
+    a.invA = reinterpret_cast<const int*>(cb + t.inva);
+    a.w = twn_of(t, cb);
+    const size_t smem = ((size_t)t.sp.Na * (t.sp.Nb + 1) + t.sp.Na + t.sp.Nb) * sizeof(cx<float>);
+    dim3 grid((unsigned)G);
+    launch(std::string(spec ? "1d_tile_parent:N" : "1d_tile_leaf:N") + std::to_string(N) + ":k" + std::to_string(a.k), algo_bytes,
+           st, [&] { kern<<<grid, block1d(), smem, st>>>(a); });
+}
+
 inline void finish1d(const void* fin_tables, const void* base0, const void* base1, const void* base2, const void* segs_dev,
                      int nseg, long long total_lines, int M, void* out, long long os_b, int i0, int W, double algo_bytes,
                      cudaStream_t st) {

@@ -29,7 +29,17 @@ template <typename T> void (*kern1d_finish(int M))(Finish1<T>) {
 #undef SB_CASE
     return nullptr;
 }
+#define SB_TILE1_SIZES(X) X(1, 16) X(2, 16) X(4, 16) X(8, 16) X(16, 16) X(16, 32) X(32, 32) X(32, 64) X(64, 64) X(64, 128)
+template <typename T> void (*kern1d_tile(int NA, int NB))(Tile1<T>) {
+#define SB_CASE(A, B) if (NA == A && NB == B) return k1d_tile<T, A, B>;
+    SB_TILE1_SIZES(SB_CASE)
+#undef SB_CASE
+    return nullptr;
+}
 void kern1d_enable_smem() {
+#define SB_EN(A, B) enable_big_smem(k1d_tile<float, A, B>);
+    SB_TILE1_SIZES(SB_EN)
+#undef SB_EN
 #define SB_EN(N) enable_big_smem(k1d_col_prod<float, N>); enable_big_smem(k1d_col_fwd<float, N>);
     SB_NA_SIZES(SB_EN)
 #undef SB_EN
@@ -44,5 +54,6 @@ void kern1d_enable_smem() {
 template Kern1d<float> kern1d_cols<float>(int);
 template KernRow1d<float> kern1d_rows<float>(int);
 template void (*kern1d_finish<float>(int))(Finish1<float>);
+template void (*kern1d_tile<float>(int, int))(Tile1<float>);
 
 }  // namespace sb

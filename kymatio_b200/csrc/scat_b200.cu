@@ -371,6 +371,15 @@ int scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int
                    void* stream) {
     return guarded([&] { col_fwd1d(tables_dev, z_dev, out_dev, G, N, algo_bytes, static_cast<cudaStream_t>(stream)); });
 }
+int scat1d_tile_max(void) { return k1TileMaxN; }
+int scat1d_tile(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
+                const void* supp_dev, void* spec_dev, void* part_dev, int32_t Fc, int64_t G, int32_t NI, int32_t Npar,
+                int32_t N, double algo_bytes, void* stream) {
+    return guarded([&] {
+        tile1d(tables_dev, parent_dev, ps_b, ps_i, filt_ptrs_dev, supp_dev, spec_dev, part_dev, Fc, G, NI, Npar, N, algo_bytes,
+               static_cast<cudaStream_t>(stream));
+    });
+}
 int scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1_dev, const void* part_dev,
                   const void* segs_dev, int32_t nseg, int64_t total_lines, int32_t M, void* out_dev, int64_t os_b, int32_t i0,
                   int32_t W, double algo_bytes, void* stream) {

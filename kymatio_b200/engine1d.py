@@ -157,6 +157,8 @@ class Engine1D:
         sch = schedule(self.Np, self.ls, phi, psi1, psi2)
         self.M, self.K, self.order = sch["M"], sch["K"], sch["order"]
         self.tables = _Tables(self.device)
+        # transforms up to this length run as ONE launch with the whole path in shared memory (scat1d_tile)
+        self.tile_max = self.lib.scat1d_tile_max() if os.environ.get("SCAT_B200_1D_TILE", "1") != "0" else 0
         with torch.cuda.device(self.device):
             self.fin_tab = self.tables.for_lowpass(self.M)
             self._keep = []                        # tensors the device arrays point into
@@ -176,8 +178,10 @@ class Engine1D:
                 gd = dict(g)
                 gd.update(NI=NI, tab=self.tables.for_length(N1), **self._filter_arrays(filt, self.Np))
                 gd["chan_dev"] = torch.tensor(g["chan"], dtype=torch.int32, device=self.device)
-                gd["nparts"] = (_split(N1)[0] + 15) // 16
-                self.per_signal["Y"] = max(self.per_signal["Y"], NI * N1)
+                gd["tile"] = N1 <= self.tile_max
+                gd["nparts"] = 1 if gd["tile"] else (_split(N1)[0] + 15) // 16
+                if not gd["tile"]:
+                    self.per_signal["Y"] = max(self.per_signal["Y"], NI * N1)
                 if g["children"]:
                     gd["u1_off"] = self.per_signal["U1"]
                     self.per_signal["U1"] += NI * N1
@@ -192,8 +196,10 @@ class Engine1D:
                     f2 = psi2[c["n2"]]["levels"][g["k1"]].reshape(-1)
                     cd.update(tab=self.tables.for_length(c["N2"]), **self._filter_arrays([f2] * NI, N1, same=True))
                     cd["chan_dev"] = torch.tensor(c["chan"], dtype=torch.int32, device=self.device)
-                    cd["nparts"] = (_split(c["N2"])[0] + 15) // 16
-                    self.per_signal["Y"] = max(self.per_signal["Y"], NI * c["N2"])
+                    cd["tile"] = c["N2"] <= self.tile_max
+                    cd["nparts"] = 1 if cd["tile"] else (_split(c["N2"])[0] + 15) // 16
+                    if not cd["tile"]:
+                        self.per_signal["Y"] = max(self.per_signal["Y"], NI * c["N2"])
                     cd["part_off"] = self.per_signal["part"]
                     self.per_signal["part"] += NI * cd["nparts"] * self.Fc[c["level"]]
                     kids.append(cd)
@@ -272,24 +278,39 @@ class Engine1D:
                 for g in self.groups:
                     NI, N1, G = g["NI"], g["N1"], nb * g["NI"]
                     tab = g["tab"].data_ptr()
-                    _lib.check(lib.scat1d_col_prod(tab, u0, Np, 0, g["filt_dev"].data_ptr(), g["supp_dev"].data_ptr(), yp,
-                                                   G, NI, Np, N1, float(nb) * 8 * (sum(g["supp_len"]) + NI * N1), st))
-                    if g["children"]:
-                        u1 = up + nb * g["u1_off"] * 8
-                        _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, None, 0, float(G) * N1 * 16, st))
-                        _lib.check(lib.scat1d_col_fwd(tab, yp, u1, G, N1, float(G) * N1 * 16, st))
-                        for c in g["children"]:
-                            N2, ctab = c["N2"], c["tab"].data_ptr()
-                            Fc = self.Fc[c["level"]]
+                    rd1 = float(nb) * 8 * sum(g["supp_len"])           # algorithmic reads of the parent spectrum
+                    u1 = up + nb * g.get("u1_off", 0) * 8
+                    if g["tile"]:
+                        Fc = self.Fc[g["k1"]]
+                        leaf = not g["children"]
+                        _lib.check(lib.scat1d_tile(tab, u0, Np, 0, g["filt_dev"].data_ptr(), g["supp_dev"].data_ptr(),
+                                                   None if leaf else u1, pp + nb * g["part_off"] * 8 if leaf else None, Fc,
+                                                   G, NI, Np, N1, rd1 + float(G) * 8 * (Fc if leaf else N1), st))
+                    else:
+                        _lib.check(lib.scat1d_col_prod(tab, u0, Np, 0, g["filt_dev"].data_ptr(), g["supp_dev"].data_ptr(),
+                                                       yp, G, NI, Np, N1, rd1 + float(G) * 8 * N1, st))
+                        if g["children"]:
+                            _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, None, 0, float(G) * N1 * 16, st))
+                            _lib.check(lib.scat1d_col_fwd(tab, yp, u1, G, N1, float(G) * N1 * 16, st))
+                        else:
+                            Fc = self.Fc[g["k1"]]
+                            _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, pp + nb * g["part_off"] * 8, Fc,
+                                                          float(G) * 8 * (N1 + g["nparts"] * Fc), st))
+                    for c in g["children"]:
+                        N2, ctab = c["N2"], c["tab"].data_ptr()
+                        Fc = self.Fc[c["level"]]
+                        rd2 = float(nb) * 8 * sum(c["supp_len"])
+                        cpart = pp + nb * c["part_off"] * 8
+                        if c["tile"]:
+                            _lib.check(lib.scat1d_tile(ctab, u1, NI * N1, N1, c["filt_dev"].data_ptr(),
+                                                       c["supp_dev"].data_ptr(), None, cpart, Fc, G, NI, N1, N2,
+                                                       rd2 + float(G) * 8 * Fc, st))
+                        else:
                             _lib.check(lib.scat1d_col_prod(ctab, u1, NI * N1, N1, c["filt_dev"].data_ptr(),
                                                            c["supp_dev"].data_ptr(), yp, G, NI, N1, N2,
-                                                           float(nb) * 8 * (sum(c["supp_len"]) + NI * N2), st))
-                            _lib.check(lib.scat1d_row_mod(ctab, yp, G, N2, pp + nb * c["part_off"] * 8, Fc,
+                                                           rd2 + float(G) * 8 * N2, st))
+                            _lib.check(lib.scat1d_row_mod(ctab, yp, G, N2, cpart, Fc,
                                                           float(G) * 8 * (N2 + c["nparts"] * Fc), st))
-                    else:
-                        Fc = self.Fc[g["k1"]]
-                        _lib.check(lib.scat1d_row_mod(tab, yp, G, N1, pp + nb * g["part_off"] * 8, Fc,
-                                                      float(G) * 8 * (N1 + g["nparts"] * Fc), st))
                 segs, nseg, lines, nbytes = self._segments(nb)
                 _lib.check(lib.scat1d_finish(self.fin_tab.data_ptr(), u0, up, pp, segs.data_ptr(), nseg, lines, M,
                                              out.data_ptr() + b0 * K * M * 4, K * M, 0, M, nbytes, st))

@@ -99,10 +99,35 @@ def test_fused1d_vs_reference_numpy_float64(plugin, kw):
     y = S(torch.from_numpy(x).float().cuda())
     labels = {r["label"].split(":")[0] for r in _lib.timing_report()}
     _lib.timing_enable(False)
-    assert {"1d_col_prod", "1d_finish"} <= labels, labels
+    assert "1d_finish" in labels and labels & {"1d_col_prod", "1d_tile_leaf", "1d_tile_parent"}, labels
     ref = ScatteringNumPy1D(**kw)(x)
     assert tuple(y.shape) == ref.shape
     assert_parity(y.cpu().numpy(), ref, channel_axis=-2, what=str(kw))
+
+
+def test_fused1d_streaming_and_tile_paths_agree(plugin, monkeypatch):
+    """Short transforms run as one whole-path launch (scat1d_tile); SCAT_B200_1D_TILE=0 forces the three-pass streaming
+    kernels for the same paths: both must give the reference's coefficients."""
+    from kymatio.torch import Scattering1D
+    from kymatio.scattering1d.frontend.numpy_frontend import ScatteringNumPy1D
+    from kymatio_b200 import _lib
+    x = np.random.RandomState(9).randn(2, 4096)
+    ref = ScatteringNumPy1D(J=6, shape=4096, Q=(8, 1))(x)
+    xt = torch.from_numpy(x).float().cuda()
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SCAT_B200_1D_TILE", flag)
+        plugin._engines1d.clear()
+        S = Scattering1D(J=6, shape=4096, Q=(8, 1), backend="torch_b200").cuda()
+        _lib.timing_enable(True)
+        y = S(xt)
+        labels = {r["label"].split(":")[0] for r in _lib.timing_report()}
+        _lib.timing_enable(False)
+        assert ("1d_tile_leaf" in labels) == (flag == "1") and ("1d_row_mod_leaf" in labels) == (flag == "0"), labels
+        assert_parity(y.cpu().numpy(), ref, channel_axis=-2, what="tile=" + flag)
+        outs.append(y)
+    plugin._engines1d.clear()
+    assert (outs[0] - outs[1]).abs().max() <= 2e-6 * outs[0].abs().max()
 
 
 @pytest.mark.parametrize("out_type", ["list", "dict"])
