@@ -154,6 +154,9 @@ int    scat1d_row_mod(const void* tables_dev, void* y_dev, int64_t G, int32_t N,
 /* second half of rfft: natural-order spectrum (G, N) out */
 int    scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t G, int32_t N, double algo_bytes,
                       void* stream);
+/* U_hat = rfft(x) of the padded real signals x_dev (G, N) (core/scattering1d.py:41; the real -> complex copy of
+ * scattering1d/backend/torch_backend.py:109-113 stays in shared memory); z_dev: (G, N) complex scratch, may alias out_dev */
+int    scat1d_rfft(const void* tables_dev, const void* x_dev, void* z_dev, void* out_dev, int64_t G, int32_t N, void* stream);
 /* whole path in ONE launch for short transforms (N <= scat1d_tile_max()): product + periodise, inverse, modulus, forward
  * all in one CTA's shared memory; writes the natural-order spectrum to spec_dev (G, N) when non-NULL (parents) and/or
  * the Fc lowest bins to part_dev (G, Fc) when non-NULL (leaves: one "partial" per path for scat1d_finish) */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "scat1d_row_mod": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_double,
                                   _c.c_void_p]),
     "scat1d_col_fwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_double, _c.c_void_p]),
+    "scat1d_rfft": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat1d_tile_max": (_c.c_int, []),
     "scat1d_tile": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_double,

@@ -188,11 +188,46 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
     }
 }
 
+// ------------------------------------------------------------------ rfft of the padded input, first half
+// U0_hat = rfft(U_0) (core/scattering1d.py:41): rows t1 (natural order) of the real padded signal x[t1 + NA*t2] are staged
+// at the scrambled positions of t2, transformed forward (DIT, natural f2' out) and twiddled; k1d_col_fwd (posA != null)
+// finishes the transform.  The real -> complex copy of the reference (torch_backend.py:109-113) never touches HBM.
+template <typename T> struct RowReal1 {
+    const T* x; cx<T>* Z;                        // x: [G][N] real; Z: [G][NA][NB]
+    int NA;
+    const cx<T>* twB; const int* posB;
+    TwN<T> w;
+};
+template <typename T, int NB> __global__ void __launch_bounds__(k1Threads, 3) k1d_row_real(RowReal1<T> a) {
+    constexpr int LS = NB + 1;
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* twB = s + (size_t)k1L * LS;
+    const cx<T>* hi = a.w.hi; const cx<T>* lo = a.w.lo;
+    const int g = blockIdx.x, p0 = blockIdx.y * k1L;
+    const int nl = min(k1L, a.NA - p0);
+    const int tid = flat_tid(), nt = flat_nt();
+    stage(twB, a.twB, NB);
+    const T* __restrict__ xb = a.x + (size_t)g * a.NA * NB + p0;
+    for (int idx = tid; idx < NB * k1L; idx += nt) {
+        const int t2 = idx / k1L, l = idx - t2 * k1L;                 // 16 consecutive samples per t2: 64-byte segments
+        if (l < nl) s[l * LS + __ldg(a.posB + t2)] = mk<T>(xb[(size_t)t2 * a.NA + l], T(0));
+    }
+    __syncthreads();
+    slab_fft_s<NB, true, -1, LS, 1, T>(s, nl, twB);                   // forward DIT over t2: natural f2'
+    cx<T>* zb = a.Z + ((size_t)g * a.NA + p0) * NB;
+    for (int idx = tid; idx < nl * NB; idx += nt) {
+        const int l = idx / NB, e = idx - l * NB;
+        zb[idx] = cmul(s[l * LS + e], twn(hi, lo, a.w.lb, (p0 + l) * e));
+    }
+}
+
 // ------------------------------------------------------------------ P3: column forward, natural-order spectrum out
 template <typename T> struct ColFwd1 {
     const cx<T>* Z; cx<T>* out;                  // [G][NA][NB] both; out = natural-order spectrum
     int NB;
     const cx<T>* twA;
+    const int* posA;                             // non-null: the rows of Z are in NATURAL t1 order (first transform of a real
+                                                 // signal, k1d_row_real): row t1 is staged at its scrambled position posA[t1]
 };
 template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 3) k1d_col_fwd(ColFwd1<T> a) {
     constexpr int LP = k1LP;
@@ -207,7 +242,8 @@ template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 3) k1
     for (int idx = tid; idx < NA * (k1L / 2); idx += nt) {
         const int p = idx / (k1L / 2), l = 2 * (idx - p * (k1L / 2));
         const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(zb + (size_t)p * a.NB + l);
-        s[p * LP + l] = v.a; s[p * LP + l + 1] = v.b;
+        const int sp = a.posA ? __ldg(a.posA + p) : p;
+        s[sp * LP + l] = v.a; s[sp * LP + l + 1] = v.b;
     }
     __syncthreads();
     slab_fft_s<NA, true, -1, 1, k1LP, T>(s, k1L, twA);                // forward DIT over t1 (scrambled in, natural out)
@@ -389,6 +425,7 @@ template <typename T> struct Kern1d {
 template <typename T> struct KernRow1d {
     void (*parent)(RowMod1<T>);
     void (*leaf)(RowMod1<T>);
+    void (*real)(RowReal1<T>);
 };
 template <typename T> Kern1d<T> kern1d_cols(int NA);                 // nullptr entries when NA is not compiled
 template <typename T> KernRow1d<T> kern1d_rows(int NB);

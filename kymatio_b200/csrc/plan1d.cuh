@@ -19,15 +19,16 @@ inline Split1d split1d(int N) {
     return s;
 }
 
-// [twA | twB | hi | lo | invA]
+// [twA | twB | hi | lo | invA | posA | posB]
 struct Tables1d {
-    Split1d sp; size_t twa, twb, hi, lo, inva, bytes;
+    Split1d sp; size_t twa, twb, hi, lo, inva, posa, posb, bytes;
     explicit Tables1d(int N) : sp(split1d(N)) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
         twa = take((size_t)sp.Na * sizeof(cx<float>)); twb = take((size_t)sp.Nb * sizeof(cx<float>));
         hi = take((size_t)sp.nhi * sizeof(cx<float>)); lo = take((size_t)sp.nlo * sizeof(cx<float>));
         inva = take((size_t)sp.Na * sizeof(int));
+        posa = take((size_t)sp.Na * sizeof(int)); posb = take((size_t)sp.Nb * sizeof(int));
         bytes = off;
     }
 };
@@ -43,10 +44,16 @@ inline void tables1d_init(void* dev, int N, cudaStream_t st) {
     for (int a = 0; a < t.sp.nhi; ++a) { long double x = tau * (long double)((long long)a << t.sp.lb); hi[a].x = (float)cosl(x); hi[a].y = (float)sinl(x); }
     for (int b = 0; b < t.sp.nlo; ++b) { long double x = tau * (long double)b; lo[b].x = (float)cosl(x); lo[b].y = (float)sinl(x); }
     int* inva = reinterpret_cast<int*>(h.data() + t.inva);
+    int* posa = reinterpret_cast<int*>(h.data() + t.posa);
+    int* posb = reinterpret_cast<int*>(h.data() + t.posb);
     if (t.sp.Na > 1) {
         auto pos = scramble_table(ct_plan1(t.sp.Na));
-        for (int f = 0; f < t.sp.Na; ++f) inva[pos[f]] = f;
-    } else inva[0] = 0;
+        for (int f = 0; f < t.sp.Na; ++f) { inva[pos[f]] = f; posa[f] = pos[f]; }
+    } else { inva[0] = 0; posa[0] = 0; }
+    {
+        auto pos = scramble_table(ct_plan1(t.sp.Nb));
+        for (int f = 0; f < t.sp.Nb; ++f) posb[f] = pos[f];
+    }
     SB_CUDA(cudaMemcpyAsync(dev, h.data(), t.bytes, cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaStreamSynchronize(st));
 }
@@ -141,6 +148,31 @@ inline void col_fwd1d(const void* tables, const void* Z, void* out, long long G,
     const size_t smem = ((size_t)t.sp.Na * k1LP + t.sp.Na) * sizeof(cx<float>);
     dim3 grid((unsigned)(G * (t.sp.Nb / k1L)));
     launch("1d_col_fwd:N" + std::to_string(N), algo_bytes, st, [&] { k.col_fwd<<<grid, block1d(), smem, st>>>(a); });
+}
+
+// U_hat = fft(x) for real x (G, N): k1d_row_real then k1d_col_fwd with scrambled row staging; Z is a (G, N) complex scratch
+// (may alias out)
+inline void rfft1d(const void* tables, const void* x, void* Z, void* out, long long G, int N, cudaStream_t st) {
+    if (G <= 0) return;
+    enable1d_once();
+    Tables1d t(N);
+    const unsigned char* cb = static_cast<const unsigned char*>(tables);
+    auto kr = kern1d_rows<float>(t.sp.Nb);
+    auto kc = kern1d_cols<float>(t.sp.Na);
+    if (!kr.real || !kc.col_fwd) throw std::runtime_error("rfft1d: no instance for N=" + std::to_string(N));
+    RowReal1<float> a{};
+    a.x = static_cast<const float*>(x); a.Z = static_cast<cx<float>*>(Z); a.NA = t.sp.Na;
+    a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb); a.posB = reinterpret_cast<const int*>(cb + t.posb);
+    a.w = twn_of(t, cb);
+    const size_t smem_r = ((size_t)(t.sp.Nb + 1) * k1L + t.sp.Nb) * sizeof(cx<float>);
+    dim3 grid_r((unsigned)G, ceil_div(t.sp.Na, k1L));
+    launch("1d_row_real:N" + std::to_string(N), (double)G * N * 12.0, st, [&] { kr.real<<<grid_r, block1d(), smem_r, st>>>(a); });
+    ColFwd1<float> c{};
+    c.Z = static_cast<const cx<float>*>(Z); c.out = static_cast<cx<float>*>(out); c.NB = t.sp.Nb;
+    c.twA = reinterpret_cast<const cx<float>*>(cb + t.twa); c.posA = reinterpret_cast<const int*>(cb + t.posa);
+    const size_t smem_c = ((size_t)t.sp.Na * k1LP + t.sp.Na) * sizeof(cx<float>);
+    dim3 grid_c((unsigned)(G * (t.sp.Nb / k1L)));
+    launch("1d_col_fwd0:N" + std::to_string(N), (double)G * N * 16.0, st, [&] { kc.col_fwd<<<grid_c, block1d(), smem_c, st>>>(c); });
 }
 
 inline void tile1d(const void* tables, const void* parent, long long ps_b, long long ps_i, const void* filt_dev,

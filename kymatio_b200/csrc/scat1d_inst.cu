@@ -17,8 +17,8 @@ template <typename T> Kern1d<T> kern1d_cols(int NA) {
     return k;
 }
 template <typename T> KernRow1d<T> kern1d_rows(int NB) {
-    KernRow1d<T> k{nullptr, nullptr};
-#define SB_CASE(N) if (NB == N) { k.parent = k1d_row_mod<T, N, false>; k.leaf = k1d_row_mod<T, N, true>; }
+    KernRow1d<T> k{nullptr, nullptr, nullptr};
+#define SB_CASE(N) if (NB == N) { k.parent = k1d_row_mod<T, N, false>; k.leaf = k1d_row_mod<T, N, true>; k.real = k1d_row_real<T, N>; }
     SB_NB_SIZES(SB_CASE)
 #undef SB_CASE
     return k;
@@ -43,7 +43,8 @@ void kern1d_enable_smem() {
 #define SB_EN(N) enable_big_smem(k1d_col_prod<float, N>); enable_big_smem(k1d_col_fwd<float, N>);
     SB_NA_SIZES(SB_EN)
 #undef SB_EN
-#define SB_EN(N) enable_big_smem(k1d_row_mod<float, N, false>); enable_big_smem(k1d_row_mod<float, N, true>);
+#define SB_EN(N) enable_big_smem(k1d_row_mod<float, N, false>); enable_big_smem(k1d_row_mod<float, N, true>); \
+                 enable_big_smem(k1d_row_real<float, N>);
     SB_NB_SIZES(SB_EN)
 #undef SB_EN
 #define SB_EN(N) enable_big_smem(k1d_finish<float, N>);

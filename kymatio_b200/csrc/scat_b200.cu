@@ -371,6 +371,9 @@ int scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int
                    void* stream) {
     return guarded([&] { col_fwd1d(tables_dev, z_dev, out_dev, G, N, algo_bytes, static_cast<cudaStream_t>(stream)); });
 }
+int scat1d_rfft(const void* tables_dev, const void* x_dev, void* z_dev, void* out_dev, int64_t G, int32_t N, void* stream) {
+    return guarded([&] { rfft1d(tables_dev, x_dev, z_dev, out_dev, G, N, static_cast<cudaStream_t>(stream)); });
+}
 int scat1d_tile_max(void) { return k1TileMaxN; }
 int scat1d_tile(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
                 const void* supp_dev, void* spec_dev, void* part_dev, int32_t Fc, int64_t G, int32_t NI, int32_t Npar,

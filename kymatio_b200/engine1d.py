@@ -256,6 +256,16 @@ class Engine1D:
         per = max(1, 8 * sum(self.per_signal.values()))
         return max(1, min(B, budget // per))
 
+    def rfft(self, U0):
+        """U0: (B, Np) float32 padded real signals -> (B, Np, 2) natural-order spectrum (core/scattering1d.py:41)."""
+        B = U0.shape[0]
+        out = torch.empty((B, self.Np, 2), dtype=torch.float32, device=self.device)
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.scat1d_rfft(self.tables.for_length(self.Np).data_ptr(), U0.data_ptr(), out.data_ptr(),
+                                                out.data_ptr(), B, self.Np, _stream(self.device)))
+        return out
+
     def forward(self, U0_hat):
         """U0_hat: (B, Np, 2) float32 natural-order spectrum of the padded signals -> (B, K, M) float32:
         every channel's low-passed, subsampled (stride 2^log2_stride) signal BEFORE unpadding."""

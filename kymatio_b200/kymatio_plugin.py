@@ -596,8 +596,7 @@ def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
         if len(_engines1d) > 16:
             _engines1d.clear()
         eng = _engines1d[key] = Engine1D(Np, log2_stride, phi, psi1, psi2, U_0.device)
-    U0_hat = backend_.rfft(U_0)                                   # (B, 1, Np, 2), this library's four-step FFT
-    S = eng.forward(U0_hat.reshape(-1, Np, 2))
+    S = eng.forward(eng.rfft(U_0.reshape(-1, Np).contiguous()))
     B = S.shape[0]
     for kind, n1, n2, ch in eng.order:
         coef = S[:, ch].reshape(B, 1, eng.M, 1)

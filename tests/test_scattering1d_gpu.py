@@ -190,3 +190,19 @@ def test_1d_gradients_match_reference_autograd(plugin, kw):
     assert err < 1e-4, float(err)
     with torch.no_grad():                                      # the no-grad call still takes the fused schedule
         assert (Sb(x) - yb.detach()).abs().max() <= 1e-5 * yb.detach().abs().max()
+
+
+def test_jtfs_through_eager_primitives(plugin):
+    """Joint time-frequency scattering (out of the fused scope) still runs through backend='torch_b200':
+    the unchanged core (kymatio/scattering1d/core/timefrequency_scattering.py) drives this library's eager primitives
+    plus the reshape helpers (pad_frequency, swap_time_frequency, ...)."""
+    from kymatio.torch import TimeFrequencyScattering
+    from kymatio.numpy import TimeFrequencyScattering as TimeFrequencyScatteringNumPy
+    kw = dict(J=5, J_fr=3, Q=4, shape=1024, format="time")
+    x = np.random.RandomState(2).randn(2, 1024)
+    S = TimeFrequencyScattering(backend="torch_b200", **kw).cuda()
+    with torch.no_grad():
+        y = S(torch.from_numpy(x).float().cuda())
+    ref = TimeFrequencyScatteringNumPy(**kw)(x)
+    assert tuple(y.shape) == ref.shape
+    assert np.abs(y.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()

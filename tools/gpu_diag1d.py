@@ -97,7 +97,21 @@ def run(N, k, NI, B, M, full_support=False):
     return max(e1, e2, e3, e4) < 2e-5
 
 
+def run_rfft(N, B=3):
+    torch.manual_seed(N)
+    x = torch.randn(B, N, device=dev)
+    out = torch.empty(B, N, 2, device=dev)
+    _lib.check(lib.scat1d_rfft(tabs.for_length(N).data_ptr(), x.data_ptr(), out.data_ptr(), out.data_ptr(), B, N, _stream(dev)))
+    torch.cuda.synchronize()
+    ref = torch.view_as_real(torch.fft.fft(x))
+    e = rel(out, ref)
+    print(f"rfft N={N:7d}: {e:.2e}", "OK" if e < 2e-6 else "FAIL", flush=True)
+    return e < 2e-6
+
+
 ok = True
+for N in (16, 64, 512, 2048, 8192, 65536, 131072, 262144):
+    ok &= run_rfft(N)
 for (N, k, NI, B, M, full) in [(16, 1, 1, 2, 8, True), (32, 2, 2, 3, 16, True), (64, 1, 3, 2, 32, False),
                                (128, 4, 2, 2, 32, False), (256, 2, 3, 3, 64, False), (512, 1, 2, 2, 128, True),
                                (1024, 8, 3, 2, 256, False), (2048, 2, 2, 2, 512, False), (4096, 1, 2, 2, 512, False),
