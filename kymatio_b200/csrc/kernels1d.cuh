@@ -70,7 +70,7 @@ template <typename T> struct ColProd1 {
     const cx<T>* twA; const int* invA;           // length-NA twiddles; invA[p] = t1 held at scrambled row p
     TwN<T> w;
 };
-template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 3) k1d_col_prod(ColProd1<T> a) {
+template <typename T, int NA> __global__ void __launch_bounds__(k1Threads, 4) k1d_col_prod(ColProd1<T> a) {
     constexpr int LP = k1LP;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twA = s + (size_t)NA * LP;
@@ -148,7 +148,7 @@ template <typename T> struct RowMod1 {
 };
 // Shared-memory layout: line-major, line l at s + l*(NB+1) (odd pitch): both the staging (lanes along a line) and
 // the butterflies (lanes across lines) are bank-conflict free.
-template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Threads, 3) k1d_row_mod(RowMod1<T> a) {
+template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Threads, NB >= 512 ? 3 : 4) k1d_row_mod(RowMod1<T> a) {
     constexpr int LS = NB + 1;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twB = s + (size_t)k1L * LS;
@@ -198,7 +198,7 @@ template <typename T> struct RowReal1 {
     const cx<T>* twB; const int* posB;
     TwN<T> w;
 };
-template <typename T, int NB> __global__ void __launch_bounds__(k1Threads, 3) k1d_row_real(RowReal1<T> a) {
+template <typename T, int NB> __global__ void __launch_bounds__(k1Threads, NB >= 512 ? 3 : 4) k1d_row_real(RowReal1<T> a) {
     constexpr int LS = NB + 1;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twB = s + (size_t)k1L * LS;
@@ -268,7 +268,7 @@ template <typename T> struct Tile1 {
     const cx<T>* twA; const cx<T>* twB; const int* invA;
     TwN<T> w;
 };
-template <typename T, int NA, int NB> __global__ void __launch_bounds__(k1Threads, 3) k1d_tile(Tile1<T> a) {
+template <typename T, int NA, int NB> __global__ void __launch_bounds__(k1Threads, 4) k1d_tile(Tile1<T> a) {
     constexpr int W = NB + 1, N = NA * NB;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twA = s + (size_t)NA * W;
@@ -366,7 +366,7 @@ template <typename T> struct Finish1 {
     const cx<T>* twM; const int* posM;
 };
 constexpr int k1FL = 8, k1FLP = k1FL | 1;  // lines per CTA of the finish kernel
-template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 2) k1d_finish(Finish1<T> a) {
+template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k1d_finish(Finish1<T> a) {
     constexpr int LP = k1FLP;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twM = s + (size_t)M * LP;
