@@ -42,7 +42,7 @@ template <typename T> struct ColProd3 {
 };
 // slab column l < 8 <-> o0 + l, column 8 + l <-> o0 + O/2 + l (same n); grid = (NO/16 column groups) x B, b fastest so
 // that the CTAs sharing a filter slab run together
-template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k3d_col_prod(ColProd3<T> a) {
+template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 4) k3d_col_prod(ColProd3<T> a) {
     constexpr int LP = k1LP, CPT = (M * 4 + k1Threads - 1) / k1Threads;     // cells (row, column pair) per thread
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)M * LP;
@@ -100,7 +100,7 @@ template <typename T> struct ColFwd3 {
     int B, NO, O;
     const cx<T>* twM; const cx<T>* twO;
 };
-template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k3d_col_fwd(ColFwd3<T> a) {
+template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 4) k3d_col_fwd(ColFwd3<T> a) {
     constexpr int LP = k1LP;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)M * LP;
@@ -131,6 +131,70 @@ template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k3d
     }
 }
 
+// Inverse DIF transform of LINES lines (same layout conventions as slab_fft_s) whose LAST pass does not store its
+// outputs: |v|^2 of output j of the thread's n-th butterfly is added to acc[n*R + j].  The work-item -> thread mapping is
+// the fixed one of slab_fft_s (item = tid + n*NT), so a thread owns the same spatial positions for every field it
+// processes; acc_store_sqrt() later writes (sqrt(acc), 0) back to exactly those positions.  Everything is compile-time
+// so that acc stays in registers.
+template <int N> struct LastPass {
+    static constexpr int NP = ct_plan1(N).npass;
+    static constexpr int R = ct_plan1(N).radix[NP - 1];
+    static_assert(ct_plan1(N).blen[NP - 1] == R && ct_is_pow2(R), "last pass must be an untwiddled power-of-two butterfly");
+};
+template <int N, int LINES, int NT> constexpr int acc_iters() { return ((N / LastPass<N>::R) * LINES + NT - 1) / NT; }
+template <int N, int LINES, int NT> constexpr int acc_size() { return acc_iters<N, LINES, NT>() * LastPass<N>::R; }
+
+template <int N, int SIGN, int LS, int ES, int LINES, int NT, typename T>
+__device__ __forceinline__ void slab_fft_acc(cx<T>* s, const cx<T>* tw, T (&acc)[acc_size<N, LINES, NT>()]) {
+    constexpr int NP = LastPass<N>::NP, R = LastPass<N>::R;
+    const int tid = flat_tid();
+    static_for<0, NP - 1>([&](auto p_) {
+        constexpr int p = decltype(p_)::value;
+        constexpr int r = ct_plan1(N).radix[p], m = ct_plan1(N).blen[p];
+        constexpr int q = m / r, nbf = N / r, tws = N / m;
+        constexpr int items = nbf * LINES;
+        for (int it = tid; it < items; it += NT) {
+            const int bf = it / LINES, line = it - bf * LINES;
+            const int blk = bf / q, i = bf - blk * q;
+            butterfly_s<r, false, SIGN, q, ES, false, T>(s + line * LS + (blk * m + i) * ES, i * tws, tw);
+        }
+        __syncthreads();
+    });
+    constexpr int items = (N / R) * LINES;
+    static_for<0, acc_iters<N, LINES, NT>()>([&](auto n_) {
+        constexpr int n = decltype(n_)::value;
+        const int it = tid + n * NT;
+        if (it < items) {
+            const int bf = it / LINES, line = it - bf * LINES;
+            const cx<T>* p0 = s + line * LS + bf * R * ES;
+            cx<T> v[R];
+            static_for<0, R>([&](auto k_) { constexpr int k = decltype(k_)::value; v[k] = p0[k * ES]; });
+            dif_pow2<R, SIGN, T>(v);
+            static_for<0, R>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                acc[n * R + k] += v[k].x * v[k].x + v[k].y * v[k].y;
+            });
+        }
+    });
+    __syncthreads();
+}
+// write (sqrt(acc), 0) to the positions slab_fft_acc accumulated from
+template <int N, int LS, int ES, int LINES, int NT, typename T>
+__device__ __forceinline__ void acc_store_sqrt(cx<T>* s, const T (&acc)[acc_size<N, LINES, NT>()]) {
+    constexpr int R = LastPass<N>::R;
+    constexpr int items = (N / R) * LINES;
+    const int tid = flat_tid();
+    static_for<0, acc_iters<N, LINES, NT>()>([&](auto n_) {
+        constexpr int n = decltype(n_)::value;
+        const int it = tid + n * NT;
+        if (it < items) {
+            const int bf = it / LINES, line = it - bf * LINES;
+            cx<T>* p0 = s + line * LS + bf * R * ES;
+            static_for<0, R>([&](auto k_) { constexpr int k = decltype(k_)::value; p0[k * ES] = mk<T>(sqrt(acc[n * R + k]), T(0)); });
+        }
+    });
+}
+
 // ------------------------------------------------------------------ plane pass: 2-D inverse, rotation modulus, integrals, 2-D forward
 template <typename T> struct Plane3 {
     const cx<T>* Y;        // [B*nm][M][N][O]
@@ -145,7 +209,8 @@ template <typename T> struct Plane3 {
 template <typename T, int N, int OH> __global__ void __launch_bounds__(plane_threads(N * OH), plane_ctas(N * OH)) k3d_plane(Plane3<T> a) {
     constexpr int W = OH + 1, O = 2 * OH;                          // odd pitch: both passes are conflict-free
     constexpr int TH = plane_threads(N * OH);
-    constexpr int EPT = (N * OH + TH - 1) / TH;
+    constexpr int EPT = acc_size<N, OH, TH>();                     // accumulators per thread (outputs of its last-pass butterflies)
+    constexpr int ACC_R = LastPass<N>::R, ACC_ITEMS = (N / ACC_R) * OH;
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twN = s + (size_t)N * W;
     cx<T>* twH = twN + N;
@@ -176,13 +241,7 @@ template <typename T, int N, int OH> __global__ void __launch_bounds__(plane_thr
         }
         __syncthreads();
         slab_fft_s<OH, false, +1, W, 1, T>(s, N, twH);            // rows (along o): N lines
-        slab_fft_s<N, false, +1, 1, W, T>(s, OH, twN);            // columns (along n): OH lines
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int idx = tid + k * TH;
-            if (idx < N * OH) { const int n = idx / OH, o = idx - n * OH; const cx<T> v = s[n * W + o]; acc[k] += v.x * v.x + v.y * v.y; }
-        }
-        __syncthreads();
+        slab_fft_acc<N, +1, 1, W, OH, TH, T>(s, twN, acc);        // columns (along n): |.|^2 of the last pass stays in registers
     }
     // U = sqrt(sum_m |.|^2)  (== the reference's nested sqrt(prev^2 + |x|^2)); voxel sums of U^q
     for (int q = 0; q < a.P; ++q) {
@@ -190,8 +249,7 @@ template <typename T, int N, int OH> __global__ void __launch_bounds__(plane_thr
         T part = T(0);
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
-            const int idx = tid + k * TH;
-            if (idx < N * OH) {
+            if (tid + (k / ACC_R) * TH < ACC_ITEMS) {
                 const T m2 = acc[k], u = sqrt(m2);
                 part += pw == 1.f ? u : pw == 2.f ? m2 : pw == 0.5f ? sqrt(u) : (u > T(0) ? pow(u, T(pw)) : (pw == 0.f ? T(1) : T(0)));
             }
@@ -209,11 +267,7 @@ template <typename T, int N, int OH> __global__ void __launch_bounds__(plane_thr
         }
     }
     if (a.spec) {
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int idx = tid + k * TH;
-            if (idx < N * OH) { const int n = idx / OH, o = idx - n * OH; s[n * W + o] = mk<T>(sqrt(acc[k]), T(0)); }
-        }
+        acc_store_sqrt<N, 1, W, OH, TH, T>(s, acc);
         __syncthreads();
         slab_fft_s<N, true, -1, 1, W, T>(s, OH, twN);             // columns first (transpose of the inverse order)
         slab_fft_s<OH, true, -1, W, 1, T>(s, N, twH);
