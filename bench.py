@@ -92,6 +92,33 @@ def cpu_baseline_single(sample):
             "sample": f"{sample} images 256x256 fp32, numpy backend, 1 process, {dt:.1f} s"}
 
 
+def reference_torch_gpu_baseline(dev, batch=64, steps=3):
+    """The reference's own torch GPU backend (cuFFT + ATen, kymatio/scattering2d/backend/torch_backend.py) on the same
+    device and config, reduced batch - a reported baseline beside the numpy CPU one (north_star); None if the reference
+    is not installed under baseline/_ref."""
+    if _import_reference() is None:
+        return None
+    import torch
+    try:
+        from kymatio.scattering2d.frontend.torch_frontend import ScatteringTorch2D
+        S = ScatteringTorch2D(J, SHAPE, L=L, backend="torch").to(dev)
+        x = torch.randn(batch, *SHAPE, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            S(x)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                S(x)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": batch / ms * 1e3, "unit": UNIT, "batch": batch, "ms_per_step": ms,
+                "what": "unmodified kymatio Scattering2D(backend='torch') on the same B200, inputs resident in HBM"}
+    except Exception as e:                                     # a baseline must never break the measured arm
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -323,6 +350,7 @@ def run_b200_arm(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
+        line["reference_torch_gpu"] = reference_torch_gpu_baseline(dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
