@@ -202,6 +202,10 @@ int  scat_compute_integrals(const void* x_dev, void* out_f64_dev, int64_t B, int
 int    scat3d_supported(int32_t M, int32_t N, int32_t O);
 size_t scat3d_tables_bytes(int32_t M, int32_t N, int32_t O);
 int    scat3d_tables_init(void* tables_dev, int32_t M, int32_t N, int32_t O, void* stream);
+/* U0_hat = rfft(x) of real volumes x_dev (B, M, N, O) -> out_dev (B, M, N, O) complex natural-order spectrum
+ * (core/scattering3d.py:24; replaces the zero-imaginary copy + fftn of scattering3d/backend/torch_backend.py:81-87) */
+int    scat3d_rfft(const void* tables_dev, const void* x_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t O,
+                   void* stream);
 int    scat3d_col_prod(const void* tables_dev, const void* u_dev, const void* filt_dev, void* y_dev, int64_t B, int32_t nm,
                        int32_t M, int32_t N, int32_t O, void* stream);
 int    scat3d_plane(const void* tables_dev, const void* y_dev, void* spec_dev, void* integ_f64_dev, int64_t istride,

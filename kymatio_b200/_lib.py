@@ -95,6 +95,8 @@ SIGNATURES = {
     "scat3d_supported": (_c.c_int, [_c.c_int32, _c.c_int32, _c.c_int32]),
     "scat3d_tables_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32, _c.c_int32]),
     "scat3d_tables_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat3d_rfft": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32,
+                               _c.c_void_p]),
     "scat3d_col_prod": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32,
                                    _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat3d_plane": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p,

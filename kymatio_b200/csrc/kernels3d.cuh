@@ -99,6 +99,7 @@ template <typename T> struct ColFwd3 {
     const cx<T>* Z; cx<T>* out;    // [B][M (scrambled)][N][O] half-plane spectra -> natural-order spectrum (may alias)
     int B, NO, O;
     const cx<T>* twM; const cx<T>* twO;
+    const int* posM;               // non-null: the M rows of Z are in NATURAL order (k3d_plane_real): row m is staged at posM[m]
 };
 template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 4) k3d_col_fwd(ColFwd3<T> a) {
     constexpr int LP = k1LP;
@@ -119,8 +120,9 @@ template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 4) k3d
         const cxpair<T> d = *reinterpret_cast<const cxpair<T>*>(zb + (size_t)p * a.NO + OH + l);
         // radix-2 DIT stage along o (forward sign): X[f] = E[f] + w^f D[f], X[f + O/2] = E[f] - w^f D[f]
         const cx<T> t0 = cmul(d.a, ldg_cx(a.twO + o0 + l)), t1 = cmul(d.b, ldg_cx(a.twO + o0 + l + 1));
-        s[p * LP + l] = e.a + t0; s[p * LP + l + 1] = e.b + t1;
-        s[p * LP + 8 + l] = e.a - t0; s[p * LP + 8 + l + 1] = e.b - t1;
+        const int sp = a.posM ? __ldg(a.posM + p) : p;
+        s[sp * LP + l] = e.a + t0; s[sp * LP + l + 1] = e.b + t1;
+        s[sp * LP + 8 + l] = e.a - t0; s[sp * LP + 8 + l + 1] = e.b - t1;
     }
     __syncthreads();
     slab_fft_s<M, true, -1, 1, k1LP, T>(s, k1L, tw);
@@ -280,9 +282,45 @@ template <typename T, int N, int OH> __global__ void __launch_bounds__(plane_thr
     }
 }
 
+// ------------------------------------------------------------------ rfft of the input volume, plane half
+// U0_hat = rfft(x) (core/scattering3d.py:24): half h of plane (b, m) holds the REAL samples x[b][m][n][2 o' + h], staged at
+// the scrambled positions of (n, o') so that the forward DIT passes leave natural-order half spectra; k3d_col_fwd
+// (posM != null) applies the radix-2 DIT stage along O and the transform along M.
+template <typename T> struct PlaneReal3 {
+    const T* x; cx<T>* spec;       // x: [B][M][N][O] real; spec: [B][M][N][O] half-plane spectra
+    int M;
+    const cx<T>* twN; const cx<T>* twH; const int* posN; const int* posH;
+};
+template <typename T, int N, int OH> __global__ void __launch_bounds__(plane_threads(N * OH), plane_ctas(N * OH)) k3d_plane_real(PlaneReal3<T> a) {
+    constexpr int W = OH + 1, O = 2 * OH;
+    constexpr int TH = plane_threads(N * OH);
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* twN = s + (size_t)N * W;
+    cx<T>* twH = twN + N;
+    const int h = blockIdx.x & 1, bp = blockIdx.x >> 1;
+    const int tid = flat_tid();
+    stage(twN, a.twN, N);
+    stage(twH, a.twH, OH);
+    const T* __restrict__ xb = a.x + (size_t)bp * N * O + h;
+    for (int idx = tid; idx < N * OH; idx += TH) {
+        const int n = idx / OH, o = idx - n * OH;
+        s[__ldg(a.posN + n) * W + __ldg(a.posH + o)] = mk<T>(xb[(size_t)n * O + 2 * o], T(0));
+    }
+    __syncthreads();
+    slab_fft_s<N, true, -1, 1, W, T>(s, OH, twN);
+    slab_fft_s<OH, true, -1, W, 1, T>(s, N, twH);
+    cx<T>* ob = a.spec + (size_t)bp * N * O + h * OH;
+    for (int idx = tid; idx < N * OH / 2; idx += TH) {
+        const int e = 2 * idx, n = e / OH, o = e - n * OH;
+        cxpair<T> v; v.a = s[n * W + o]; v.b = s[n * W + o + 1];
+        *reinterpret_cast<cxpair<T>*>(ob + (size_t)n * O + o) = v;
+    }
+}
+
 template <typename T> void (*kern3d_col_prod(int M))(ColProd3<T>);
 template <typename T> void (*kern3d_col_fwd(int M))(ColFwd3<T>);
 template <typename T> void (*kern3d_plane(int N, int O))(Plane3<T>);
+template <typename T> void (*kern3d_plane_real(int N, int O))(PlaneReal3<T>);
 void kern3d_enable_smem();
 
 }  // namespace sb

@@ -12,15 +12,17 @@ inline bool fused3d_supported(int M, int N, int O) {
     return p2(M) && p2(N) && M <= 256 && N == O && N >= 16 && N <= 128 && kern3d_col_prod<float>(M) && kern3d_plane<float>(N, O);
 }
 
-// [twM | twN | twO | twO/2]
+// [twM | twN | twO | twO/2 | posM | posN | posO/2]
 struct Tables3d {
-    int n[4]; size_t tw[4], bytes;
+    int n[4]; size_t tw[4], pos[3], bytes;
     Tables3d(int M, int N, int O) {
         if (!fused3d_supported(M, N, O))
             throw std::runtime_error("fused 3-D kernels need power-of-two sizes with M in [8,256] and N == O in [16,128]");
         n[0] = M; n[1] = N; n[2] = O; n[3] = O / 2;
         size_t off = 0;
         for (int a = 0; a < 4; ++a) { tw[a] = off; off = align_up(off + (size_t)n[a] * sizeof(cx<float>), 256); }
+        const int pn[3] = {M, N, O / 2};
+        for (int a = 0; a < 3; ++a) { pos[a] = off; off = align_up(off + (size_t)pn[a] * sizeof(int), 256); }
         bytes = off;
     }
 };
@@ -30,6 +32,11 @@ inline void tables3d_init(void* dev, int M, int N, int O, cudaStream_t st) {
     for (int a = 0; a < 4; ++a) {
         auto tw = twiddle_table<float>(t.n[a]);
         memcpy(h.data() + t.tw[a], tw.data(), (size_t)t.n[a] * sizeof(cx<float>));
+    }
+    const int pn[3] = {M, N, O / 2};
+    for (int a = 0; a < 3; ++a) {
+        auto pos = scramble_table(ct_plan1(pn[a]));
+        memcpy(h.data() + t.pos[a], pos.data(), (size_t)pn[a] * sizeof(int));
     }
     SB_CUDA(cudaMemcpyAsync(dev, h.data(), t.bytes, cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaStreamSynchronize(st));
@@ -91,6 +98,31 @@ inline void col_fwd3d(const void* tables, const void* Z, void* out, long long B,
     const size_t vol = (size_t)M * N * O * sizeof(cx<float>);
     dim3 grid((unsigned)(B * (a.NO / k1L)));
     launch("3d_col_fwd", (double)B * 2.0 * vol, st, [&] { kern<<<grid, block1d(), smem, st>>>(a); });
+}
+
+// U0_hat = rfft(x) for real volumes x (B, M, N, O): half-plane forward transforms, then radix-2 along O + transform along M
+inline void rfft3d(const void* tables, const void* x, void* out, long long B, int M, int N, int O, cudaStream_t st) {
+    if (B <= 0) return;
+    enable3d_once();
+    Tables3d t(M, N, O);
+    const unsigned char* cb = static_cast<const unsigned char*>(tables);
+    auto kp = kern3d_plane_real<float>(N, O);
+    auto kc = kern3d_col_fwd<float>(M);
+    PlaneReal3<float> a{};
+    a.x = static_cast<const float*>(x); a.spec = static_cast<cx<float>*>(out); a.M = M;
+    a.twN = reinterpret_cast<const cx<float>*>(cb + t.tw[1]); a.twH = reinterpret_cast<const cx<float>*>(cb + t.tw[3]);
+    a.posN = reinterpret_cast<const int*>(cb + t.pos[1]); a.posH = reinterpret_cast<const int*>(cb + t.pos[2]);
+    const size_t smem_p = ((size_t)N * (O / 2 + 1) + N + O / 2) * sizeof(cx<float>);
+    const size_t vol = (size_t)M * N * O * sizeof(cx<float>);
+    dim3 grid_p((unsigned)(B * M * 2));
+    launch("3d_plane_real", (double)B * 1.5 * vol, st, [&] { kp<<<grid_p, plane_threads(N * O / 2), smem_p, st>>>(a); });
+    ColFwd3<float> c{};
+    c.Z = static_cast<const cx<float>*>(out); c.out = static_cast<cx<float>*>(out); c.B = (int)B; c.NO = N * O; c.O = O;
+    c.twM = reinterpret_cast<const cx<float>*>(cb + t.tw[0]); c.twO = reinterpret_cast<const cx<float>*>(cb + t.tw[2]);
+    c.posM = reinterpret_cast<const int*>(cb + t.pos[0]);
+    const size_t smem_c = ((size_t)M * k1LP + M) * sizeof(cx<float>);
+    dim3 grid_c((unsigned)(B * (c.NO / k1L)));
+    launch("3d_col_fwd0", (double)B * 2.0 * vol, st, [&] { kc<<<grid_c, block1d(), smem_c, st>>>(c); });
 }
 
 }  // namespace sb

@@ -25,11 +25,17 @@ template <typename T> void (*kern3d_plane(int N, int O))(Plane3<T>) {
 #undef SB_CASE
     return nullptr;
 }
+template <typename T> void (*kern3d_plane_real(int N, int O))(PlaneReal3<T>) {
+#define SB_CASE(S) if (N == S && O == S) return k3d_plane_real<T, S, S / 2>;
+    SB_P3_SIZES(SB_CASE)
+#undef SB_CASE
+    return nullptr;
+}
 void kern3d_enable_smem() {
 #define SB_EN(N) enable_big_smem(k3d_col_prod<float, N>); enable_big_smem(k3d_col_fwd<float, N>);
     SB_M3_SIZES(SB_EN)
 #undef SB_EN
-#define SB_EN(S) enable_big_smem(k3d_plane<float, S, S / 2>);
+#define SB_EN(S) enable_big_smem(k3d_plane<float, S, S / 2>); enable_big_smem(k3d_plane_real<float, S, S / 2>);
     SB_P3_SIZES(SB_EN)
 #undef SB_EN
 }
@@ -37,5 +43,6 @@ void kern3d_enable_smem() {
 template void (*kern3d_col_prod<float>(int))(ColProd3<float>);
 template void (*kern3d_plane<float>(int, int))(Plane3<float>);
 template void (*kern3d_col_fwd<float>(int))(ColFwd3<float>);
+template void (*kern3d_plane_real<float>(int, int))(PlaneReal3<float>);
 
 }  // namespace sb

@@ -401,6 +401,10 @@ size_t scat3d_tables_bytes(int32_t M, int32_t N, int32_t O) {
 int scat3d_tables_init(void* tables_dev, int32_t M, int32_t N, int32_t O, void* stream) {
     return guarded([&] { tables3d_init(tables_dev, M, N, O, static_cast<cudaStream_t>(stream)); });
 }
+int scat3d_rfft(const void* tables_dev, const void* x_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t O,
+                void* stream) {
+    return guarded([&] { rfft3d(tables_dev, x_dev, out_dev, B, M, N, O, static_cast<cudaStream_t>(stream)); });
+}
 int scat3d_col_prod(const void* tables_dev, const void* u_dev, const void* filt_dev, void* y_dev, int64_t B, int32_t nm,
                     int32_t M, int32_t N, int32_t O, void* stream) {
     return guarded([&] { col_prod3d(tables_dev, u_dev, filt_dev, y_dev, B, nm, M, N, O, static_cast<cudaStream_t>(stream)); });

@@ -48,6 +48,16 @@ class Engine3D:
             self.tab = torch.empty(self.lib.scat3d_tables_bytes(*self.shape), dtype=torch.uint8, device=self.device)
             _lib.check(self.lib.scat3d_tables_init(self.tab.data_ptr(), *self.shape, _stream(self.device)))
 
+    def rfft(self, x):
+        """x: (B, M, N, O) float32 real volumes -> (B, M, N, O, 2) natural-order spectrum (core/scattering3d.py:24)."""
+        M, N, O = self.shape
+        out = torch.empty((x.shape[0], M, N, O, 2), dtype=torch.float32, device=self.device)
+        if x.shape[0]:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.scat3d_rfft(self.tab.data_ptr(), x.data_ptr(), out.data_ptr(), x.shape[0], M, N, O,
+                                                _stream(self.device)))
+        return out
+
     def forward(self, U0_hat, filters, rotation_covariant, L, J, max_order, powers):
         """U0_hat: (B, M, N, O, 2) float32 spectrum of the input volumes; filters[l]: (J+1, 2l+1, M, N, O, 2).
         Returns (B, n_j, L+1, P) float32 in the reference's layout."""

@@ -654,7 +654,7 @@ def _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend
             _engines3d[key] = eng = False
     if not eng:
         return None
-    U0_hat = backend_.rfft(x)
+    U0_hat = eng.rfft(x.reshape(x.shape[:4]).contiguous())
     return eng.forward(U0_hat, filters, bool(rotation_covariant), int(L), int(J), int(max_order), powers)
 
 
