@@ -48,3 +48,33 @@ def test_plan_geometry_without_gpu():
     assert lib.scat_plan2d_info(h, *[ctypes.byref(x) for x in v]) == 0
     assert [x.value for x in v] == [272, 272, 32, 32, 217]
     lib.scat_plan2d_destroy(h)
+
+
+def test_host_only_entry_points():
+    """Entry points that need no device: the finish-segment record layout shared with engine1d.py, the N = Na*Nb split
+    and the support predicates of the fused 1-D / 3-D kernels."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libscat_b200.so not built")
+    from kymatio_b200.engine1d import _FINSEG
+    lib = _lib.load()
+    assert lib.scat1d_finseg_bytes() == _FINSEG.itemsize == 64
+    na, nb = ctypes.c_int32(), ctypes.c_int32()
+    for n in range(4, 19):
+        assert lib.scat1d_split(1 << n, ctypes.byref(na), ctypes.byref(nb)) == 0
+        assert na.value * nb.value == 1 << n and nb.value >= 16 and nb.value >= na.value
+    assert lib.scat1d_split(1 << 19, ctypes.byref(na), ctypes.byref(nb)) != 0 and lib.scat_last_error()
+    assert lib.scat1d_split(1000, ctypes.byref(na), ctypes.byref(nb)) != 0
+    assert lib.scat1d_tile_max() == 8192
+    assert lib.scat3d_supported(128, 128, 128) == 1 and lib.scat3d_supported(64, 32, 32) == 1
+    assert lib.scat3d_supported(12, 16, 20) == 0 and lib.scat3d_supported(32, 32, 16) == 0
+    assert lib.scat1d_tables_bytes(1 << 17) > 0 and lib.scat1d_fin_tables_bytes(512) > 0
+    assert lib.scat1d_fin_tables_bytes(4096) == 0 and lib.scat_last_error()
+
+
+def test_engine3d_band_layout_matches_oracle_order():
+    # n_j axis: first the J+1 first-order scales, then the (j1, j2 > j1) pairs in loop order (core/scattering3d.py:62-73)
+    from kymatio_b200.engine3d import band_layout
+    first, second, n = band_layout(L=2, J=2, max_order=2)
+    assert first == {0: 0, 1: 1, 2: 2} and second == {(0, 1): 3, (0, 2): 4, (1, 2): 5} and n == 6
+    first, second, n = band_layout(L=3, J=3, max_order=1)
+    assert n == 4 and second == {}
