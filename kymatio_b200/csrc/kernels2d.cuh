@@ -100,7 +100,7 @@ constexpr int kSLines = 16;           // lines per CTA in the static variants
 constexpr int kSLP = kSLines | 1;     // odd shared-memory pitch
 // launch bounds of the slab kernels: static instances run 16 lines x <= 18 butterflies (<= 288 threads)
 // and are compiled for three CTAs per SM (<= 75 registers); generic ones may use up to kMaxThreads
-#define SB_SLAB_BOUNDS(NS) __launch_bounds__((NS) > 0 ? 288 : kMaxThreads, (NS) > 0 ? 3 : 1)
+#define SB_SLAB_BOUNDS(NS) __launch_bounds__((NS) > 0 ? 288 : kMaxThreads, (NS) > 0 ? 4 : 1)
 
 template <typename T> struct alignas(2 * sizeof(cx<T>)) cxpair { cx<T> a, b; };
 template <typename T> struct alignas(2 * sizeof(T)) repair { T a, b; };
