@@ -648,7 +648,7 @@ private:
     std::vector<bool> tile_ok_;
     std::vector<size_t> tile_smem_;
     bool force_stream_ = false;
-    int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 576);
+    int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 608);
     int num_sms_ = 148;
     bool use_mma_ = env_int("SCAT_B200_NO_MMA", 0) == 0;
     size_t l2_sub_bytes_ = (size_t)env_int("SCAT_B200_L2_SUB_MB", 0) << 20;   // 0 disables sub-batching
