@@ -51,8 +51,10 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     const size_t o_g0 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
     const size_t o_g1 = take(sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
     const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
-    const size_t o_gs = take(sizeof(T) * (size_t)a.o0p * a.o1p);     // backward: staged output-plane gradient
-    const size_t o_xr = take(sizeof(int2) * (size_t)a.n1);           // backward: nonzero output range of each G1 row
+    // backward only (the forward kernel must not pay for them: 68 x 68 tiles fit three per SM without)
+    const bool bwd = a.gparent != nullptr;
+    const size_t o_gs = take(bwd ? sizeof(T) * (size_t)a.o0p * a.o1p : 0);   // staged output-plane gradient
+    const size_t o_xr = take(bwd ? sizeof(int2) * (size_t)a.n1 : 0);         // nonzero output range of each G1 row
     if (L) {
 #ifdef __CUDA_ARCH__
         unsigned char* base = dyn_smem<unsigned char>();
