@@ -226,8 +226,11 @@ public:
     void forward(const void* x, void* out, void* ws, size_t ws_bytes, int64_t batch, cudaStream_t st) override {
         if (!bound_) throw std::runtime_error("filters are not bound to the plan");
         if (batch <= 0) return;
-        const int64_t chunk = std::min<int64_t>(batch, (int64_t)(ws_bytes / per_img_));
+        int64_t chunk = std::min<int64_t>(batch, (int64_t)(ws_bytes / per_img_));
         if (chunk < 1) throw std::runtime_error("workspace too small");
+        // images per pass over the kernel sequence: small enough that the first-order spectra of a chunk stay in the
+        // 126 MB L2 between the kernel that writes them and the kernels that read them (SCAT_B200_CHUNK overrides)
+        if (chunk_cap_ > 0) chunk = std::min<int64_t>(chunk, chunk_cap_);
         const size_t in_img = d_.pre_pad ? (size_t)P0_ * P1_ : (size_t)d_.M * d_.N;
         const size_t out_img = (size_t)K_ * o0_ * o1_;
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
@@ -649,6 +652,7 @@ private:
     std::vector<size_t> tile_smem_;
     bool force_stream_ = false;
     int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 608);
+    int chunk_cap_ = env_int("SCAT_B200_CHUNK", 0);
     int num_sms_ = 148;
     bool use_mma_ = env_int("SCAT_B200_NO_MMA", 0) == 0;
     size_t l2_sub_bytes_ = (size_t)env_int("SCAT_B200_L2_SUB_MB", 0) << 20;   // 0 disables sub-batching
