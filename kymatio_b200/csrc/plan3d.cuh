@@ -8,8 +8,8 @@
 namespace sb {
 
 inline bool fused3d_supported(int M, int N, int O) {
-    auto p2 = [](int v) { return v >= 8 && (v & (v - 1)) == 0; };
-    return p2(M) && p2(N) && M <= 256 && N == O && N >= 16 && N <= 128 && kern3d_col_prod<float>(M) && kern3d_plane<float>(N, O);
+    return M >= 8 && N >= 16 && O >= 16 && O % 16 == 0 && kern3d_col_prod<float>(M) && kern3d_col_fwd<float>(M) &&
+           kern3d_plane<float>(N, O) && kern3d_plane_real<float>(N, O);
 }
 
 // [twM | twN | twO | twO/2 | posM | posN | posO/2]
@@ -17,7 +17,7 @@ struct Tables3d {
     int n[4]; size_t tw[4], pos[3], bytes;
     Tables3d(int M, int N, int O) {
         if (!fused3d_supported(M, N, O))
-            throw std::runtime_error("fused 3-D kernels need power-of-two sizes with M in [8,256] and N == O in [16,128]");
+            throw std::runtime_error("no fused 3-D kernel instance for this volume shape (see scat3d_inst.cu)");
         n[0] = M; n[1] = N; n[2] = O; n[3] = O / 2;
         size_t off = 0;
         for (int a = 0; a < 4; ++a) { tw[a] = off; off = align_up(off + (size_t)n[a] * sizeof(cx<float>), 256); }

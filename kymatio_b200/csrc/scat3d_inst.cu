@@ -4,8 +4,9 @@
 
 namespace sb {
 
-#define SB_M3_SIZES(X) X(8) X(16) X(32) X(64) X(128) X(256)
-#define SB_P3_SIZES(X) X(16) X(32) X(64) X(128)
+#define SB_M3_SIZES(X) X(8) X(16) X(32) X(64) X(96) X(128) X(192) X(256)
+// planes (N, O): N a power of two (the |.|^2 accumulation hooks the last, untwiddled power-of-two pass), O % 16 == 0
+#define SB_P3_SIZES(X) X(16, 16) X(32, 32) X(64, 64) X(128, 128) X(128, 96) X(64, 96) X(64, 48)
 
 template <typename T> void (*kern3d_col_prod(int M))(ColProd3<T>) {
 #define SB_CASE(N) if (M == N) return k3d_col_prod<T, N>;
@@ -20,13 +21,13 @@ template <typename T> void (*kern3d_col_fwd(int M))(ColFwd3<T>) {
     return nullptr;
 }
 template <typename T> void (*kern3d_plane(int N, int O))(Plane3<T>) {
-#define SB_CASE(S) if (N == S && O == S) return k3d_plane<T, S, S / 2>;
+#define SB_CASE(A, B) if (N == A && O == B) return k3d_plane<T, A, B / 2>;
     SB_P3_SIZES(SB_CASE)
 #undef SB_CASE
     return nullptr;
 }
 template <typename T> void (*kern3d_plane_real(int N, int O))(PlaneReal3<T>) {
-#define SB_CASE(S) if (N == S && O == S) return k3d_plane_real<T, S, S / 2>;
+#define SB_CASE(A, B) if (N == A && O == B) return k3d_plane_real<T, A, B / 2>;
     SB_P3_SIZES(SB_CASE)
 #undef SB_CASE
     return nullptr;
@@ -35,7 +36,7 @@ void kern3d_enable_smem() {
 #define SB_EN(N) enable_big_smem(k3d_col_prod<float, N>); enable_big_smem(k3d_col_fwd<float, N>);
     SB_M3_SIZES(SB_EN)
 #undef SB_EN
-#define SB_EN(S) enable_big_smem(k3d_plane<float, S, S / 2>); enable_big_smem(k3d_plane_real<float, S, S / 2>);
+#define SB_EN(A, B) enable_big_smem(k3d_plane<float, A, B / 2>); enable_big_smem(k3d_plane_real<float, A, B / 2>);
     SB_P3_SIZES(SB_EN)
 #undef SB_EN
 }

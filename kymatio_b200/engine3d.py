@@ -43,7 +43,7 @@ class Engine3D:
         self.device = torch.device(device)
         self.shape = (int(M), int(N), int(O))
         if not self.lib.scat3d_supported(*self.shape):
-            raise Unsupported("fused 3-D kernels need power-of-two volumes (M <= 256, N == O <= 128)")
+            raise Unsupported("no fused 3-D kernel instance for this volume shape")
         with torch.cuda.device(self.device):
             self.tab = torch.empty(self.lib.scat3d_tables_bytes(*self.shape), dtype=torch.uint8, device=self.device)
             _lib.check(self.lib.scat3d_tables_init(self.tab.data_ptr(), *self.shape, _stream(self.device)))

@@ -84,6 +84,7 @@ FUSED_CASES = [
     dict(J=2, shape=(32, 32, 32), L=1, max_order=1),
     dict(J=2, shape=(16, 16, 16), L=2, rotation_covariant=False),
     dict(J=2, shape=(64, 64, 64), L=1, integral_powers=(0.5, 1.0, 2.0, 3.0)),
+    dict(J=1, shape=(96, 64, 48), L=1),                      # non-power-of-two instance (radix-3 factors along M and O)
 ]
 
 
@@ -142,7 +143,7 @@ def test_3d_gradients_match_reference_autograd(plugin, kw):
     assert err < 1e-3, float(err)
 
 
-@pytest.mark.parametrize("shape", [(16, 16, 16), (8, 32, 32), (64, 16, 16), (128, 128, 128)])
+@pytest.mark.parametrize("shape", [(16, 16, 16), (8, 32, 32), (64, 16, 16), (128, 128, 128), (96, 64, 48), (192, 128, 96)])
 def test_fused3d_rfft_against_torch(plugin, shape):
     """U0_hat of the fused path (half-plane forward transforms + radix-2 along O + transform along M)."""
     from kymatio_b200.engine3d import Engine3D
