@@ -116,3 +116,33 @@ def test_oracle3d_reference_fixture(ref, golden_dir):
         order_0 = ref_s.shape[1] - y.shape[1]
         ref_s = ref_s[:, order_0:]
     assert np.abs(y - ref_s).sum() / np.abs(ref_s).sum() < 1e-5
+
+
+LIVE_1D = [dict(J=6, shape=4096, Q=(8, 2)), dict(J=5, shape=3000, Q=(6, 1), stride=8), dict(J=7, shape=8192, Q=12, T=32),
+           dict(J=4, shape=777, Q=3, max_order=1), dict(J=5, shape=2048, Q=(4, 1), oversampling=1)]
+
+
+@pytest.mark.parametrize("kw", LIVE_1D)
+def test_oracle1d_vs_live_reference(ref, kw):
+    """The restatement against the reference itself run here (numpy frontend, float64) on configurations the committed
+    goldens do not cover: stride, T, oversampling, odd lengths, max_order=1."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S = ref[0](**kw)
+    x = np.random.RandomState(3).randn(2, kw["shape"])
+    y = _run1d(S, x)
+    want = S(x)
+    assert y.shape == want.shape
+    assert np.abs(y - want).max() <= 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("kw", [dict(J=2, shape=(16, 16, 16), L=2, rotation_covariant=False),
+                                dict(J=2, shape=(12, 10, 14), L=1, max_order=1, integral_powers=(0.5, 1.0, 2.0, 3.0))])
+def test_oracle3d_vs_live_reference(ref, kw):
+    S = ref[1](**kw)
+    x = np.random.RandomState(4).randn(2, *kw["shape"])
+    y = o3.scattering3d(x, S.filters, S.L, S.J, S.integral_powers, S.max_order, S.rotation_covariant)
+    want = S(x)
+    assert y.shape == want.shape
+    assert np.abs(y - want).max() <= 1e-5 * np.abs(want).max()       # the reference casts its integrals to float32
