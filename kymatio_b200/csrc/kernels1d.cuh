@@ -25,9 +25,15 @@
 //   k1d_col_fwd   (P3)  16 adjacent columns f2', all p: forward DIT over t1 -> f1' (natural), store the
 //                       natural-order spectrum U1_hat[NB*f1' + f2'];
 //   k1d_finish          low-pass tail  cdgmm(phi) -> subsample_fourier -> irfft -> unpad  on the Fc lowest bins
-//                       (Hermitian symmetry of the spectrum of a real field supplies the negative ones):
-//                       fold onto M bins, inverse DIF of length M in shared memory (16 paths per CTA),
-//                       write samples [i0, i0+W) of the real part into the channel row of the output.
+//                       (Hermitian symmetry of the spectrum of a real field supplies the negative ones): ONE launch per
+//                       batch chunk for every path (segment table), fold onto M bins, inverse DIF of length M in shared
+//                       memory (8 paths per CTA), real part of samples [i0, i0+W) into the channel row of the output;
+//   k1d_tile            transforms up to 8192 points: the WHOLE path (product, four-step inverse, modulus, four-step
+//                       forward) in one CTA's shared memory - no Y round trip, no pruned DFT;
+//   k1d_row_real        U0_hat = rfft(U_0) from the REAL padded signal (rows staged at scrambled positions), finished by
+//                       k1d_col_fwd with scrambled row staging.
+// All slab kernels are compiled for four CTAs per SM (<= 64 registers); the two-level twiddle table exp(-2 pi i j / N) =
+// hi[j >> lb] * lo[j & mask] is read through the read-only path (L1 resident).
 #pragma once
 #include "kernels2d.cuh"
 
