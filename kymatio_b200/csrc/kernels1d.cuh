@@ -399,6 +399,7 @@ template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k1d
         T ax = T(0), ay = T(0);
         for (int f = u; f < Fc; f += M) {                    // bins f = u + aM on the non-negative side
             T vx = T(0), vy = T(0);
+#pragma unroll 4
             for (int q = 0; q < nparts; ++q) { const cx<T> v = xb[q * ssp + f]; vx += v.x; vy += v.y; }
             const T ph = phi[f];
             ax += vx * ph; ay += vy * ph;
@@ -406,6 +407,7 @@ template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k1d
         for (int f = (M - u) & (M - 1); f < Fc; f += M) {    // bins N - f == u (mod M): conj(X[f]) * phi[N - f]
             if (f == 0 || f == nyq) continue;
             T vx = T(0), vy = T(0);
+#pragma unroll 4
             for (int q = 0; q < nparts; ++q) { const cx<T> v = xb[q * ssp + f]; vx += v.x; vy += v.y; }
             const T ph = phi[N - f];
             ax += vx * ph; ay -= vy * ph;
