@@ -94,6 +94,7 @@ int  scat_plan2d_order2_backward(scat_plan2d* plan, int32_t j1, const void* u1_d
  * backend object. */
 
 /* natural-order complex 2-D FFT on (G, n0, n1, 2): tables -> const_dev (caller-owned), then exec.
+ * inverse: 0 = forward, 1 = inverse normalised by 1/(n0 n1), 2 = inverse without normalisation (adjoint of the forward).
  * replaces torch.fft.fft2 / ifft2 at kymatio/scattering2d/backend/torch_backend.py:10-12,134-155 */
 size_t scat_fft2d_const_bytes(int32_t n0, int32_t n1, int32_t dtype);
 int  scat_fft2d_init(void* const_dev, int32_t n0, int32_t n1, int32_t dtype, void* stream);

@@ -210,10 +210,12 @@ template <typename T> void fft2d_init(void* const_dev, int n0, int n1, cudaStrea
     SB_CUDA(cudaStreamSynchronize(st));
 }
 
-// in/out: (G, n0, n1) complex, natural order both sides; inverse is 1/(n0 n1)-normalised
-// (torch.fft.fft2 / ifft2 conventions, kymatio/scattering2d/backend/torch_backend.py:10-12)
+// in/out: (G, n0, n1) complex, natural order both sides; mode 0 = forward, 1 = inverse 1/(n0 n1)-normalised
+// (torch.fft.fft2 / ifft2 conventions, kymatio/scattering2d/backend/torch_backend.py:10-12), 2 = inverse without the
+// normalisation (the adjoint of the forward transform, used by the autograd graph)
 template <typename T>
-void fft2d_exec(const void* const_dev, const void* in, void* out, int64_t G, int n0, int n1, bool inverse, cudaStream_t st) {
+void fft2d_exec(const void* const_dev, const void* in, void* out, int64_t G, int n0, int n1, int mode, cudaStream_t st) {
+    const bool inverse = mode != 0;
     Fft2dTables<T> t(n0, n1);
     const unsigned char* cb = static_cast<const unsigned char*>(const_dev);
     const SlabCfg rc = slab_cfg(t.p1, n0, sizeof(cx<T>), sizeof(int));
@@ -236,7 +238,7 @@ void fft2d_exec(const void* const_dev, const void* in, void* out, int64_t G, int
     dim3 gc((unsigned)G, ceil_div(n1, cc.lines));
     launch(inverse ? "prim_colpass_inv" : "prim_colpass_fwd", 2.0 * G * n0 * n1 * sizeof(cx<T>), st,
            [&] { (inverse ? kc.col_inv : kc.col_fwd)<<<gc, cc.block, cc.smem, st>>>(ca); });
-    if (inverse) {
+    if (mode == 1) {
         const size_t n = (size_t)G * n0 * n1;
         launch("prim_scale", 2.0 * n * sizeof(cx<T>), st,
                [&] { kp_scale<T><<<blocks_for(n), 256, 0, st>>>(static_cast<cx<T>*>(out), n, T(1) / (T(n0) * T(n1))); });

@@ -131,7 +131,7 @@ int scat_fft2d_exec(const void* const_dev, const void* in_dev, void* out_dev, in
     return guarded([&] {
         static bool enabled = false;
         if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
-        SB_DISPATCH(dtype, fft2d_exec<T>(const_dev, in_dev, out_dev, G, n0, n1, inverse != 0, static_cast<cudaStream_t>(stream)));
+        SB_DISPATCH(dtype, fft2d_exec<T>(const_dev, in_dev, out_dev, G, n0, n1, inverse, static_cast<cudaStream_t>(stream)));
     });
 }
 int scat_pad2d(const void* x_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,

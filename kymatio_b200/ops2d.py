@@ -64,7 +64,7 @@ class Fft2(torch.autograd.Function):
         N = g.shape[-3] * g.shape[-2]
         if ctx.inverse:                      # y = (1/N) F^H x  ->  gx = (1/N) F g
             return _fft2_raw(g, False) / N, None
-        return _fft2_raw(g, True) * N, None  # y = F x        ->  gx = F^H g = N ifft(g)
+        return _fft2_raw(g, 2), None         # y = F x        ->  gx = F^H g (unnormalised inverse, mode 2)
 
 
 class Modulus(torch.autograd.Function):
@@ -188,7 +188,8 @@ class Order2(torch.autograd.Function):
 
 
 def _to_complex(x):
-    return torch.stack([x, torch.zeros_like(x)], dim=-1)
+    from .ops_eager import FromReal          # kernel + adjoint (real part); no zero tensor, no stack copy
+    return FromReal.apply(x.contiguous()[..., None])
 
 
 def _low(U, phi_level, k):
