@@ -62,6 +62,8 @@ class Fft2(torch.autograd.Function):
     def backward(ctx, g):
         g = g.contiguous()
         N = g.shape[-3] * g.shape[-2]
+        if int(ctx.inverse) == 2:            # y = F^H x        ->  gx = F g
+            return _fft2_raw(g, False), None
         if ctx.inverse:                      # y = (1/N) F^H x  ->  gx = (1/N) F g
             return _fft2_raw(g, False) / N, None
         return _fft2_raw(g, 2), None         # y = F x        ->  gx = F^H g (unnormalised inverse, mode 2)
@@ -225,9 +227,12 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=Non
     S0 = _low(U0, phi[0], 2 ** J)[:, None]
     S1, S2 = [], []
     for j1 in range(J):
-        V = FilterBank.apply(U0, psi[j1][0])
+        # the 1/N of the inverse transform is folded into the (small) filter tensor: the transform itself then runs
+        # unnormalised in both directions of the graph, without a scaling pass over the full-size fields
+        n_j1 = (U0.shape[1] >> j1) * (U0.shape[2] >> j1)
+        V = FilterBank.apply(U0, psi[j1][0] * (1.0 / n_j1))
         V = Periodize.apply(V.reshape((B * L,) + tuple(V.shape[2:])), 2 ** j1)
-        A = Modulus.apply(Fft2.apply(V, True))
+        A = Modulus.apply(Fft2.apply(V, 2))
         U1 = Fft2.apply(_to_complex(A), False)
         s1 = _low(U1, phi[j1], 2 ** (J - j1))
         S1.append(s1.reshape((B, L) + tuple(s1.shape[1:])))
