@@ -1,5 +1,6 @@
 """Differentiable versions of the eager 1-D / 3-D backend primitives: every ``torch.autograd.Function`` pairs a
-forward kernel of this library with its hand-written adjoint.  torch only records the tape.
+forward kernel of this library with its hand-written adjoint.  torch records the tape (and applies
+the scalar 1/N or N of the FFT adjoints).
 
 Used by ``kymatio_plugin`` when a gradient is requested through ``backend='torch_b200'`` Scattering1D /
 HarmonicScattering3D: the unchanged reference core then drives these ops (the fused forward-only schedules of
