@@ -12,3 +12,15 @@ def test_fft_core_on_cpu(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     sys.stdout.write(res.stdout[-2000:])
     assert res.returncode == 0 and "ALL OK" in res.stdout
+
+
+def test_fourstep_1d_path_on_cpu(tmp_path):
+    """The index maps / twiddles / scrambled pairing of the fused 1-D kernels (kernels1d.cuh), emulated on the host with
+    the same butterflies, against a long-double O(N^2) evaluation of fft(|ifft(X)|)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fourstep_test")
+    src = os.path.join(root, "tests", "cpu", "fourstep_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, src], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    sys.stdout.write(res.stdout[-2000:])
+    assert res.returncode == 0 and "ALL OK" in res.stdout
