@@ -24,3 +24,15 @@ def test_fourstep_1d_path_on_cpu(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     sys.stdout.write(res.stdout[-2000:])
     assert res.returncode == 0 and "ALL OK" in res.stdout
+
+
+def test_halfplane_3d_transform_on_cpu(tmp_path):
+    """The two-pass 3-D transform of kernels3d.cuh (radix-2 along O inside the M-axis kernels, half-plane 2-D transforms,
+    scrambled spatial positions), emulated on the host with the same butterflies, against O(N^2) DFTs."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "halfplane3d_test")
+    src = os.path.join(root, "tests", "cpu", "halfplane3d_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, src], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    sys.stdout.write(res.stdout[-2000:])
+    assert res.returncode == 0 and "ALL OK" in res.stdout
