@@ -206,3 +206,16 @@ def test_jtfs_through_eager_primitives(plugin):
     ref = TimeFrequencyScatteringNumPy(**kw)(x)
     assert tuple(y.shape) == ref.shape
     assert np.abs(y.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_fused1d_batch_shapes(plugin):
+    """Leading batch axes are flattened by the frontend and restored on output (reshape_input / reshape_output); a single
+    un-batched signal works too."""
+    from kymatio.torch import Scattering1D
+    S = Scattering1D(J=4, shape=1024, Q=(4, 1), backend="torch_b200").cuda()
+    x = torch.randn(2, 3, 1024, device="cuda")
+    y = S(x)
+    flat = S(x.reshape(6, 1024))
+    assert y.shape[:2] == (2, 3) and torch.equal(y.reshape(flat.shape), flat)
+    one = S(x[0, 0])
+    assert one.shape == flat.shape[1:] and torch.allclose(one, flat[0], rtol=0, atol=1e-6 * float(flat.abs().max()))

@@ -152,3 +152,15 @@ def test_fused3d_rfft_against_torch(plugin, shape):
     got = eng.rfft(x)
     ref = torch.view_as_real(torch.fft.fftn(x, dim=(-3, -2, -1)))
     assert (got - ref).abs().max() <= 3e-6 * ref.abs().max() * np.log2(np.prod(shape))
+
+
+def test_fused3d_batch_shapes(plugin):
+    from kymatio.torch import HarmonicScattering3D
+    S = HarmonicScattering3D(J=1, shape=(16, 16, 16), L=1, backend="torch_b200").cuda()
+    x = torch.randn(2, 2, 16, 16, 16, device="cuda")
+    y = S(x)
+    flat = S(x.reshape(4, 16, 16, 16))
+    assert y.shape[:2] == (2, 2)
+    assert ((y.reshape(flat.shape) - flat).abs() / flat.abs().clamp_min(1e-30)).max().item() < 1e-5   # float64 atomics
+    one = S(x[0, 0])
+    assert ((one - flat[0]).abs() / flat[0].abs().clamp_min(1e-30)).max().item() < 1e-5
