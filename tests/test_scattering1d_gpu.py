@@ -219,3 +219,31 @@ def test_fused1d_batch_shapes(plugin):
     assert y.shape[:2] == (2, 3) and torch.equal(y.reshape(flat.shape), flat)
     one = S(x[0, 0])
     assert one.shape == flat.shape[1:] and torch.allclose(one, flat[0], rtol=0, atol=1e-6 * float(flat.abs().max()))
+
+
+def test_fused1d_streams_rebinding_and_float64(plugin):
+    from kymatio.torch import Scattering1D
+    from kymatio.scattering1d.frontend.numpy_frontend import ScatteringNumPy1D
+    kw = dict(J=4, shape=1024, Q=(4, 1))
+    x = np.random.RandomState(6).randn(3, 1024)
+    ref = ScatteringNumPy1D(**kw)(x)
+    S = Scattering1D(backend="torch_b200", **kw).cuda()
+    xt = torch.from_numpy(x).float().cuda()
+    y0 = S(xt)
+    # a side stream: launches go to torch's current stream, workspaces are stream-ordered
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        y1 = S(xt)
+    side.synchronize()
+    assert torch.equal(y0, y1)
+    # moving the module re-creates its buffers: the engine is re-bound (keyed on the buffers' identity)
+    S = S.cpu().cuda()
+    assert torch.equal(S(xt), y0)
+    assert_parity(y0.cpu().numpy(), ref, channel_axis=-2, what="1d fused")
+    # float64 modules are outside the fused kernels: the unchanged core drives the eager float64 primitives
+    Sd = Scattering1D(backend="torch_b200", **kw).cuda().double()
+    yd = Sd(torch.from_numpy(x).cuda())
+    assert yd.dtype == torch.float64
+    # (the module's filters were rounded to float32 at registration, kymatio/scattering1d/frontend/torch_frontend.py:36-40)
+    assert np.abs(yd.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
