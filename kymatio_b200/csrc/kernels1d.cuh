@@ -159,6 +159,7 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* twB = s + (size_t)k1L * LS;
     int* t1s = reinterpret_cast<int*>(twB + NB);
+    int* lk = t1s + k1L;                                              // leaves: row holding the k-th term of the progression
     const cx<T>* hi = a.w.hi; const cx<T>* lo = a.w.lo;
     const int g = blockIdx.x, p0 = blockIdx.y * k1L;
     const int nl = min(k1L, a.NA - p0);
@@ -171,6 +172,12 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
         s[l * LS + e] = yb[idx];
     }
     __syncthreads();
+    // the rows of one CTA hold t1 = base + stride*k, k < nl (DIF digit structure of the NA-point column transform; checked
+    // on the host when the tables are built): the leaf's pruned column DFT then needs one twiddle and a power ladder per bin
+    int base = t1s[0];
+    for (int l = 1; l < nl; ++l) base = min(base, t1s[l]);
+    const int stride = max(1, a.NA / k1L);
+    if (LEAF && tid < nl) lk[(t1s[tid] - base) / stride] = tid;
     slab_fft_s<NB, false, +1, LS, 1, T, true>(s, nl, twB);            // inverse DIF + modulus: (|u|, 0), scrambled t2
     slab_fft_s<NB, true, -1, LS, 1, T>(s, nl, twB);                   // forward DIT: natural f2'
     if constexpr (!LEAF) {
@@ -182,14 +189,24 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
         cx<T>* pb = a.part + ((size_t)g * gridDim.y + blockIdx.y) * a.Fc;
         const int maskN = a.N - 1;
         for (int f = tid; f < a.Fc; f += nt) {
+            // X[f] += w_N^{base f} sum_k (w_N^{stride f})^k R[row_k][f mod NB]
             const int e = f & (NB - 1);
+            const cx<T> z1 = twn(hi, lo, a.w.lb, (stride * f) & maskN);
+            const cx<T> z2 = cmul(z1, z1), z4 = cmul(z2, z2), z8 = cmul(z4, z4);
             T ax = T(0), ay = T(0);
-            for (int l = 0; l < nl; ++l) {
-                const cx<T> wv = twn(hi, lo, a.w.lb, (t1s[l] * f) & maskN);
-                const cx<T> v = s[l * LS + e];
-                ax += v.x * wv.x - v.y * wv.y; ay += v.x * wv.y + v.y * wv.x;
-            }
-            pb[f] = mk<T>(ax, ay);
+            static_for<0, k1L>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                if (k < nl) {
+                    cx<T> pk = mk<T>(T(1), T(0));
+                    if constexpr (k & 1) pk = z1;
+                    if constexpr (k & 2) pk = (k & 1) ? cmul(pk, z2) : z2;
+                    if constexpr (k & 4) pk = (k & 3) ? cmul(pk, z4) : z4;
+                    if constexpr (k & 8) pk = (k & 7) ? cmul(pk, z8) : z8;
+                    const cx<T> v = s[lk[k] * LS + e];
+                    ax += v.x * pk.x - v.y * pk.y; ay += v.x * pk.y + v.y * pk.x;
+                }
+            });
+            pb[f] = cmul(mk<T>(ax, ay), twn(hi, lo, a.w.lb, (base * f) & maskN));
         }
     }
 }

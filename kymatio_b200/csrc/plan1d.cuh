@@ -50,6 +50,18 @@ inline void tables1d_init(void* dev, int N, cudaStream_t st) {
         auto pos = scramble_table(ct_plan1(t.sp.Na));
         for (int f = 0; f < t.sp.Na; ++f) { inva[pos[f]] = f; posa[f] = pos[f]; }
     } else { inva[0] = 0; posa[0] = 0; }
+    // k1d_row_mod<LEAF> relies on: the k1L consecutive scrambled rows of one CTA hold t1 = base + (Na/k1L)*k, k < k1L
+    for (int p0 = 0; p0 + k1L <= t.sp.Na; p0 += k1L) {
+        int base = inva[p0];
+        for (int l = 1; l < k1L; ++l) base = std::min(base, inva[p0 + l]);
+        unsigned seen = 0;
+        for (int l = 0; l < k1L; ++l) {
+            const int d = inva[p0 + l] - base, st = t.sp.Na / k1L;
+            if (d % st || d / st >= k1L) throw std::runtime_error("row blocks of the column transform are not arithmetic progressions");
+            seen |= 1u << (d / st);
+        }
+        if (seen != (1u << k1L) - 1u) throw std::runtime_error("row blocks of the column transform are not arithmetic progressions");
+    }
     {
         auto pos = scramble_table(ct_plan1(t.sp.Nb));
         for (int f = 0; f < t.sp.Nb; ++f) posb[f] = pos[f];
@@ -129,7 +141,7 @@ inline void row_mod1d(const void* tables, void* Y, long long G, int N, void* par
     a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb); a.invA = reinterpret_cast<const int*>(cb + t.inva);
     a.w = twn_of(t, cb);
     a.part = static_cast<cx<float>*>(part); a.Fc = Fc;
-    const size_t smem = ((size_t)(t.sp.Nb + 1) * k1L + t.sp.Nb) * sizeof(cx<float>) + k1L * sizeof(int);
+    const size_t smem = ((size_t)(t.sp.Nb + 1) * k1L + t.sp.Nb) * sizeof(cx<float>) + 2 * k1L * sizeof(int);
     dim3 grid((unsigned)G, ceil_div(t.sp.Na, k1L));
     launch(std::string(part ? "1d_row_mod_leaf:N" : "1d_row_mod:N") + std::to_string(N), algo_bytes, st,
            [&] { (part ? k.leaf : k.parent)<<<grid, block1d(), smem, st>>>(a); });
