@@ -92,6 +92,36 @@ template <int NA, int NB> static double run(int Fc) {
         }
     }
     for (int f = 0; f < Fc; ++f) err = std::max(err, (double)std::abs(part[f] - Xref[f]));
+    // the leaf kernel's formulation: blocks of 16 scrambled rows hold t1 = base + stride*k; one twiddle and a power ladder
+    // (z, z^2, z^4, z^8) per bin.  R rows are recomputed from Z (divide the four-step twiddle back out).
+    {
+        const int L = std::min(16, NA), stride = std::max(1, NA / 16);
+        std::vector<cld> part2(Fc, cld(0));
+        for (int p0 = 0; p0 < NA; p0 += L) {
+            int base = invA[p0];
+            for (int l = 1; l < L; ++l) base = std::min(base, invA[p0 + l]);
+            std::vector<int> lk(L);
+            for (int l = 0; l < L; ++l) lk[(invA[p0 + l] - base) / stride] = l;
+            for (int f = 0; f < Fc; ++f) {
+                const cx<T> z1 = wN((int)((long long)stride * f % N), N);
+                const cx<T> z2 = cmul(z1, z1), z4 = cmul(z2, z2), z8 = cmul(z4, z4);
+                cx<T> acc = mk<T>(0, 0);
+                for (int k = 0; k < L; ++k) {
+                    cx<T> pk = mk<T>(1, 0);
+                    if (k & 1) pk = cmul(pk, z1);
+                    if (k & 2) pk = cmul(pk, z2);
+                    if (k & 4) pk = cmul(pk, z4);
+                    if (k & 8) pk = cmul(pk, z8);
+                    const int p = p0 + lk[k], e = f % NB;
+                    const cx<T> r = cmulc(Z[(size_t)p * NB + e], wN(invA[p] * e, N));     // R[p][e]
+                    acc = acc + cmul(r, pk);
+                }
+                const cx<T> v = cmul(acc, wN((int)((long long)base * f % N), N));
+                part2[f] += cld(v.x, v.y);
+            }
+        }
+        for (int f = 0; f < Fc; ++f) err = std::max(err, (double)std::abs(part2[f] - Xref[f]));
+    }
     // real-input forward transform (k1d_row_real + k1d_col_fwd with posA staging) of U
     double err_r = 0;
     for (int t1 = 0; t1 < NA; ++t1) {
