@@ -122,6 +122,12 @@ template <int NA, int NB> static double run(int Fc) {
         }
         for (int f = 0; f < Fc; ++f) err = std::max(err, (double)std::abs(part2[f] - Xref[f]));
     }
+    // Hermitian index map of the [NA][NB] layout (next step: half spectra): X[NB f1 + f2] = conj X[NB f1m + f2m] with
+    // (f1m, f2m) = (NA-1-f1, NB-f2) for f2 != 0 and ((NA-f1) % NA, 0) for f2 == 0
+    for (int f1 = 0; f1 < NA; ++f1) for (int f2 = 0; f2 < NB; ++f2) {
+        const int f1m = f2 ? NA - 1 - f1 : (NA - f1) % NA, f2m = f2 ? NB - f2 : 0;
+        err = std::max(err, (double)std::abs(Xref[NB * f1 + f2] - std::conj(Xref[NB * f1m + f2m])));
+    }
     // real-input forward transform (k1d_row_real + k1d_col_fwd with posA staging) of U
     double err_r = 0;
     for (int t1 = 0; t1 < NA; ++t1) {
