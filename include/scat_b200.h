@@ -47,6 +47,9 @@ uint64_t scat_launch_count(void);
  * scat_timing_report synchronises on the recorded events; returns the bytes needed. */
 void scat_timing_enable(int on);
 size_t scat_timing_report(char* buf, size_t buflen);
+/* profiling build only (make prof -> libscat_b200_prof.so): cycles spent per phase of the 2-D tile kernels,
+ * out[kind * 8 + phase]; returns the number of slots written, 0 in the production library.  Synchronises the device. */
+int scat_phase_prof_read(unsigned long long* out, int max_n, int reset);
 
 /* 2-D plan ----------------------------------------------------------------------- */
 int  scat_plan2d_create(const scat_plan2d_desc* desc, scat_plan2d** out_plan);

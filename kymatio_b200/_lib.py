@@ -34,6 +34,7 @@ SIGNATURES = {
     "scat_launch_count": (_c.c_uint64, []),
     "scat_timing_enable": (None, [_c.c_int]),
     "scat_timing_report": (_c.c_size_t, [_c.c_char_p, _c.c_size_t]),
+    "scat_phase_prof_read": (_c.c_int, [_c.POINTER(_c.c_uint64), _c.c_int, _c.c_int]),
     "scat_plan2d_create": (_c.c_int, [_c.POINTER(PlanDesc2D), _c.POINTER(_c.c_void_p)]),
     "scat_plan2d_destroy": (None, [_c.c_void_p]),
     "scat_plan2d_info": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_int32)] * 5),

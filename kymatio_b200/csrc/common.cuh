@@ -5,6 +5,9 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstdint>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -54,6 +57,19 @@ constexpr size_t kMaxDynSmem = 227 * 1024;
 // opt in to large dynamic shared memory once per kernel instantiation
 template <typename K> inline void enable_big_smem(K kernel) {
     SB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+}
+
+// The > 48 KB dynamic shared-memory opt-in (cudaFuncSetAttribute) is a per-DEVICE attribute: run `f` once per
+// (tag, current device), so a process that drives several GPUs opts every one of them in.
+template <typename F> inline void once_per_device(const char* tag, F&& f) {
+    static std::mutex mu;
+    static std::set<std::pair<std::string, int>> done;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.insert(std::make_pair(std::string(tag), dev)).second) {
+        try { f(); } catch (...) { done.erase(std::make_pair(std::string(tag), dev)); throw; }
+    }
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

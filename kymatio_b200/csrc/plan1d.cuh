@@ -93,8 +93,7 @@ inline void fin_tables1d_init(void* dev, int M, cudaStream_t st) {
 }
 
 inline void enable1d_once() {
-    static bool done = false;
-    if (!done) { kern1d_enable_smem(); done = true; }
+    once_per_device("kern1d", [] { kern1d_enable_smem(); });
 }
 inline TwN<float> twn_of(const Tables1d& t, const unsigned char* cb) {
     TwN<float> w;

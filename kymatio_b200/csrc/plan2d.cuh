@@ -153,9 +153,11 @@ public:
         tile_smem_.assign(d.J, 0);
         force_stream_ = env_int("SCAT_B200_NO_TILE", 0) != 0;
 
-        stream_kernels_enable_smem<T>();
-        enable_big_smem(k2d_lowpass<T>);
-        tile_kernels_enable_smem<T>();
+        once_per_device(sizeof(T) == 4 ? "plan2d_f" : "plan2d_d", [] {
+            stream_kernels_enable_smem<T>();
+            enable_big_smem(k2d_lowpass<T>);
+            tile_kernels_enable_smem<T>();
+        });
         {
             int dev = 0;
             SB_CUDA(cudaGetDevice(&dev));

@@ -42,8 +42,7 @@ inline void tables3d_init(void* dev, int M, int N, int O, cudaStream_t st) {
     SB_CUDA(cudaStreamSynchronize(st));
 }
 inline void enable3d_once() {
-    static bool done = false;
-    if (!done) { kern3d_enable_smem(); done = true; }
+    once_per_device("kern3d", [] { kern3d_enable_smem(); });
 }
 
 inline void col_prod3d(const void* tables, const void* U, const void* filt, void* Y, long long B, int nm, int M, int N, int O,

@@ -332,12 +332,10 @@ template <typename T> void fft1d_init(void* const_dev, int N, cudaStream_t st) {
 template <typename T>
 void fft1d_exec(const void* const_dev, const void* in, void* tmp, void* out, int64_t G, int N, bool inverse,
                 cudaStream_t st) {
-    static bool enabled = false;
-    if (!enabled) {
+    once_per_device("fft1d", [] {
         enable_big_smem(k1d_rowpass_tw<float, false>); enable_big_smem(k1d_rowpass_tw<float, true>);
         enable_big_smem(k1d_rowpass_tw<double, false>); enable_big_smem(k1d_rowpass_tw<double, true>);
-        enabled = true;
-    }
+    });
     Fft1dTables<T> t(N);
     const unsigned char* cb = static_cast<const unsigned char*>(const_dev);
     const cx<T>* src = static_cast<const cx<T>*>(in);

@@ -22,6 +22,14 @@ int scat_version(void) { return 100; }
 const char* scat_last_error(void) { return last_error().c_str(); }
 uint64_t scat_launch_count(void) { return launch_counter().load(); }
 
+// profiling build only (libscat_b200_prof.so): per-phase cycle counters of the 2-D tile kernels, [24 kinds][8 phases];
+// returns the number of slots written (0 in the production build).  Synchronises the device.
+int scat_phase_prof_read(unsigned long long* out, int max_n, int reset) {
+    int n = 0;
+    guarded([&] { n = phase_prof_read(out, max_n, reset != 0); });
+    return n;
+}
+
 void scat_timing_enable(int on) {
     timing_on() = on != 0;
     if (!on) {
@@ -129,8 +137,7 @@ int scat_fft2d_init(void* const_dev, int32_t n0, int32_t n1, int32_t dtype, void
 int scat_fft2d_exec(const void* const_dev, const void* in_dev, void* out_dev, int64_t G, int32_t n0, int32_t n1,
                     int32_t inverse, int32_t dtype, void* stream) {
     return guarded([&] {
-        static bool enabled = false;
-        if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
+        once_per_device("stream", [] { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); });
         SB_DISPATCH(dtype, fft2d_exec<T>(const_dev, in_dev, out_dev, G, n0, n1, inverse, static_cast<cudaStream_t>(stream)));
     });
 }
@@ -210,8 +217,7 @@ int scat_fft1d_init(void* const_dev, int32_t N, int32_t dtype, void* stream) {
 int scat_fft1d_exec(const void* const_dev, const void* in_dev, void* tmp_dev, void* out_dev, int64_t G, int32_t N,
                     int32_t inverse, int32_t dtype, void* stream) {
     return guarded([&] {
-        static bool enabled = false;
-        if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
+        once_per_device("stream", [] { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); });
         if (G <= 0) return;
         SB_DISPATCH(dtype, fft1d_exec<T>(const_dev, in_dev, tmp_dev, out_dev, G, N, inverse != 0, static_cast<cudaStream_t>(stream)));
     });
@@ -253,8 +259,7 @@ int scat_fft3d_init(void* const_dev, int32_t M, int32_t N, int32_t O, int32_t dt
 int scat_fft3d_exec(const void* const_dev, const void* in_dev, void* out_dev, int64_t G, int32_t M, int32_t N, int32_t O,
                     int32_t inverse, int32_t dtype, void* stream) {
     return guarded([&] {
-        static bool enabled = false;
-        if (!enabled) { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); enabled = true; }
+        once_per_device("stream", [] { stream_kernels_enable_smem<float>(); stream_kernels_enable_smem<double>(); });
         if (G <= 0) return;
         SB_DISPATCH(dtype, fft3d_exec<T>(const_dev, in_dev, out_dev, G, M, N, O, inverse != 0, static_cast<cudaStream_t>(stream)));
     });

@@ -20,6 +20,27 @@
 
 namespace sb {
 
+// Optional per-phase cycle accounting (profiling build only, -DSB_PHASE_PROF -> libscat_b200_prof.so): thread 0 of
+// every CTA adds the cycles between phase boundaries to g_phase_cycles[kernel id][phase]; read back through
+// scat_phase_prof_read (tile_inst.cu).  The production build compiles none of it.
+#ifdef SB_PHASE_PROF
+constexpr int kPhaseKinds = 24, kPhaseSlots = 8;
+static __device__ unsigned long long g_phase_cycles[kPhaseKinds * kPhaseSlots];
+#define SB_PHASE_INIT(kid_expr) const int sb_kid = (kid_expr); long long sb_t_last = clock64();
+#define SB_PHASE(i)                                                                            \
+    do {                                                                                       \
+        __syncthreads();                                                                       \
+        if (flat_tid() == 0) {                                                                 \
+            const long long sb_t = clock64();                                                  \
+            atomicAdd(&g_phase_cycles[sb_kid * kPhaseSlots + (i)], (unsigned long long)(sb_t - sb_t_last)); \
+            sb_t_last = sb_t;                                                                  \
+        }                                                                                      \
+    } while (0)
+#else
+#define SB_PHASE_INIT(kid_expr)
+#define SB_PHASE(i)
+#endif
+
 template <typename T> struct TileArgs {
     const cx<T>* parent; const T* const* filt; const int2* supp;
     cx<T>* spec_out; T* out;
@@ -255,12 +276,14 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
         stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
     }
 
+    SB_PHASE_INIT((N0 == 136 ? 0 : N0 == 68 ? 1 : 2) * 8 + (KT == 4 ? 4 : 0) + (a.spec_out ? 2 : 0) + (a.PP != a.NFch ? 1 : 0))
     for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
         const int fi = g % a.NF, pg = g / a.NF;
         const int b = g / a.PP, path = g - b * a.PP;
         const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
         stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
         __syncthreads();
+        SB_PHASE(0);
 
         // 1. product + periodise: 4 (or 2) adjacent columns per thread, 128-bit loads, aliases outside the
         //    filter support skipped
@@ -283,13 +306,16 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             }
         }
         __syncthreads();
+        SB_PHASE(1);
         // 2+3. inverse 2-D FFT and modulus.
         //   static : DIF (natural Fourier in -> scrambled spatial out), modulus in the registers of the last pass;
         //            the spatial field stays scrambled: U[y][x] lives at s[pos0[y]*W + pos1[x]]
         //   generic: DIT (scattered input -> natural spatial), separate modulus sweep
         if constexpr (ST) {
             slab_fft_s<N1, false, +1, (N1 | 1), 1, T>(s, N0, m.tw1);
+            SB_PHASE(2);
             slab_fft_s<N0, false, +1, 1, (N1 | 1), T, true>(s, N1, m.tw0);
+            SB_PHASE(3);
         } else {
             slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
             slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
@@ -381,6 +407,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             }
         }
         __syncthreads();
+        SB_PHASE(4);
         // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
         //     S[yo][xo] = sum_y G0[y][yo] * w1[row(y)][xo]; 4 output rows per thread, lanes along xo
         {
@@ -408,6 +435,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             }
         }
         }   // !mma
+        SB_PHASE(5);
         // 5. forward 2-D FFT of U for the children of this path, natural-order store
         //    (static: DIT, scrambled spatial in -> natural Fourier out; generic: DIF + gather)
         if (a.spec_out) {
@@ -431,6 +459,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             }
         }
         __syncthreads();   // the next path rewrites the tile, the support rows and w1
+        SB_PHASE(6);
     }
 }
 
@@ -583,5 +612,6 @@ template <typename T> using TileKernel = void (*)(TileArgs<T>);
 template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bool* is_static);
 template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k, bool* is_static);
 template <typename T> void tile_kernels_enable_smem();
+int phase_prof_read(unsigned long long* out, int max_n, bool reset);
 
 }  // namespace sb

@@ -48,6 +48,23 @@ template <typename T> void tile_kernels_enable_smem() {
     enable_big_smem(k2d_tile_bwd<T, 0, 0, 0>);
 }
 
+// profiling build: copy out (and optionally reset) the per-phase cycle counters; the production build reports 0 slots
+int phase_prof_read(unsigned long long* out, int max_n, bool reset) {
+#ifdef SB_PHASE_PROF
+    const int n = std::min(max_n, kPhaseKinds * kPhaseSlots);
+    SB_CUDA(cudaDeviceSynchronize());
+    SB_CUDA(cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * n));
+    if (reset) {
+        static const unsigned long long zeros[kPhaseKinds * kPhaseSlots] = {};
+        SB_CUDA(cudaMemcpyToSymbol(g_phase_cycles, zeros, sizeof zeros));
+    }
+    return n;
+#else
+    (void)out; (void)max_n; (void)reset;
+    return 0;
+#endif
+}
+
 template TileKernel<float> tile_kernel_lookup<float>(int, int, int, bool*);
 template TileKernel<double> tile_kernel_lookup<double>(int, int, int, bool*);
 template TileKernel<float> tile_bwd_kernel_lookup<float>(int, int, int, bool*);

@@ -30,7 +30,9 @@ class Engine2D:
         desc = _lib.PlanDesc2D(int(M), int(N), int(J), int(L), int(max_order), int(bool(pre_pad)),
                                _DTYPES[dtype], 0)
         handle = ctypes.c_void_p()
-        _lib.check(self.lib.scat_plan2d_create(ctypes.byref(desc), ctypes.byref(handle)))
+        # the plan reads the SM count of, and opts its kernels into large shared memory on, the CURRENT device
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_create(ctypes.byref(desc), ctypes.byref(handle)))
         self._plan = handle
         vals = [ctypes.c_int32() for _ in range(5)]
         _lib.check(self.lib.scat_plan2d_info(self._plan, *[ctypes.byref(v) for v in vals]))

@@ -85,3 +85,32 @@ def test_fused_order2_block_matches_per_op_graph():
             outs.append(y.detach()); grads.append(xi.grad)
         assert_parity(outs[1].cpu().numpy(), outs[0].cpu().numpy(), tol=tol, what="order2 fwd")
         assert_parity(grads[1].cpu().numpy()[:, None], grads[0].cpu().numpy()[:, None], tol=10 * tol, what="order2 bwd")
+
+
+@pytest.mark.parametrize("J,shape,B", [(4, (224, 224), 2), (3, (256, 256), 1)])
+def test_gradient_at_config_shapes_through_kymatio_plugin(J, shape, B):
+    """BASELINE configs[4] (C5: J=4, 224x224) and the headline shape: gradient of the UNMODIFIED
+    kymatio.torch.Scattering2D(backend='torch_b200') against the reference torch backend's autograd (contract:
+    tests/scattering2d/test_torch_scattering2d.py:238-248 + kymatio/backend/torch_backend.py:64-96).  This exercises the
+    static 128/64/32 (resp. 136/68) backward tiles and their atomics scatter against something other than the repo."""
+    if not import_reference():
+        pytest.skip("reference not installed under baseline/_ref")
+    import kymatio_b200.kymatio_plugin as plugin
+    plugin.install()
+    try:
+        from kymatio.torch import Scattering2D as KScattering2D
+        torch.manual_seed(4)
+        x = torch.randn(B, *shape, device="cuda")
+        Sb = KScattering2D(J, shape, backend="torch_b200").cuda()
+        Sr = KScattering2D(J, shape, backend="torch").cuda()
+        xb = x.clone().requires_grad_(True)
+        yb = Sb(xb)
+        w = torch.randn_like(yb)
+        (yb * w).sum().backward()
+        xr = x.clone().requires_grad_(True)
+        yr = Sr(xr)
+        (yr * w).sum().backward()
+        assert_parity(yb.detach().cpu().numpy(), yr.detach().cpu().numpy(), what="fwd " + str((J, shape)))
+        assert_parity(xb.grad.cpu().numpy()[:, None], xr.grad.cpu().numpy()[:, None], tol=1e-4, what="grad " + str((J, shape)))
+    finally:
+        plugin.uninstall()

@@ -82,6 +82,8 @@ FUSED_1D = [
     dict(J=7, shape=8192, Q=(12, 1), T=32),
     dict(J=5, shape=3000, Q=(6, 1), stride=8),
     dict(J=9, shape=2 ** 15, Q=(8, 1)),
+    dict(J=6, shape=4096, Q=(8, 1), oversampling=1),           # kymatio/scattering1d/frontend/base_frontend.py:127-145
+    dict(J=5, shape=3000, Q=(6, 2), oversampling=2, T=16),
 ]
 
 

@@ -85,6 +85,7 @@ FUSED_CASES = [
     dict(J=2, shape=(16, 16, 16), L=2, rotation_covariant=False),
     dict(J=2, shape=(64, 64, 64), L=1, integral_powers=(0.5, 1.0, 2.0, 3.0)),
     dict(J=1, shape=(96, 64, 48), L=1),                      # non-power-of-two instance (radix-3 factors along M and O)
+    dict(J=2, shape=(128, 128, 128), L=2),                   # BASELINE configs[3] (C4) at its own size
 ]
 
 
