@@ -61,6 +61,22 @@ template <typename V> __device__ __forceinline__ V ld_pred(const void* ptr, bool
     return u.v;
 }
 
+// Bulk L2 prefetch (cp.async.bulk.prefetch.L2, the TMA unit's prefetch form; SASS UBLKPF): pulls `bytes` (multiple of 16,
+// 16-byte aligned) from HBM into L2 without occupying registers or shared memory.  The persistent tile kernels issue
+// it one path ahead, so the product/periodise loads of the next path hit L2 instead of stalling on DRAM latency.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* ptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+// rows [slice * ceil(P0/nslices), ...) of a P0 x P1 field at `base` (one instruction per row, one row per thread)
+template <typename E>
+__device__ __forceinline__ void prefetch_rows_slice(const E* base, int P0, int P1, int slice, int nslices, int tid, int nt) {
+    const unsigned row_bytes = (unsigned)(P1 * sizeof(E));
+    if (row_bytes & 15u) return;
+    const int per = (P0 + nslices - 1) / nslices;
+    const int r1 = min(P0, (slice + 1) * per);
+    for (int r = slice * per + tid; r < r1; r += nt) prefetch_l2_bulk(base + (size_t)r * P1, row_bytes);
+}
+
 // sum over the k x k aliases of (parent * filter) for output bin (r, e), skipping aliases outside
 // the filter's per-row support interval.  supp may live in shared or global memory.
 template <typename T>

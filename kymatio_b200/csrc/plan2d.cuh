@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels2d.cuh"
 #include "tile2d.cuh"
+#include "tile2h.cuh"
 #include "plan_host.h"
 
 struct scat_plan2d {
@@ -47,6 +48,7 @@ struct FirLevel {
     bool ok = false;
     int y0lo = 0, y0cnt = 0, x1lo = 0, x1cnt = 0;   // input window per group of 4 outputs (tile2d.cuh)
     size_t G0_off = 0, G1_off = 0;                  // dense [n][o?p] decimation matrices
+    size_t TT0_off = 0, TT1_off = 0;                // the same taps as [cnt][4] tables (shift invariance, tile2h.cuh)
 };
 
 // per-row circular support interval of a real filter (natural order)
@@ -125,6 +127,8 @@ public:
             phi_supp_off_[j] = take((size_t)lev_[j].a0.n * sizeof(int2));
             fir_[j].G0_off = take((size_t)lev_[j].a0.n * o0p() * sizeof(T));
             fir_[j].G1_off = take((size_t)lev_[j].a1.n * o1p() * sizeof(T));
+            fir_[j].TT0_off = take((size_t)lev_[j].a0.n * 4 * sizeof(T));
+            fir_[j].TT1_off = take((size_t)lev_[j].a1.n * 4 * sizeof(T));
         }
         psi_ptr_off_.resize(d.J); psi_supp_off_.resize(d.J);
         n_psi_expected_ = 0;
@@ -157,6 +161,7 @@ public:
             stream_kernels_enable_smem<T>();
             enable_big_smem(k2d_lowpass<T>);
             tile_kernels_enable_smem<T>();
+            tile2h_kernels_enable_smem<T>();
         });
         {
             int dev = 0;
@@ -307,7 +312,7 @@ private:
         // spatial taps a[t] (circular), truncated where |a| <= 1e-6 max|a|, expanded into the dense
         // matrix G[x][o] = a[(kl*(o+1) - x) mod n] (zero outside the kept radius / for padded columns)
         const int kl = 1 << (d_.J - j);
-        auto build = [&](int n, int stride, double norm, int nout, int noutp, int& lo, int& cnt, size_t off) {
+        auto build = [&](int n, int stride, double norm, int nout, int noutp, int& lo, int& cnt, size_t off, size_t tt_off) {
             std::vector<double> a(n);
             double mx = 0;
             for (int y = 0; y < n; ++y) {
@@ -334,9 +339,16 @@ private:
                     }
                     G[(size_t)x * noutp + o] = (T)v;
                 }
+            // G[x][4g+i] for the st-th input x = kl (4g+1) + lo + st of output group g does not depend on g
+            T* TT = reinterpret_cast<T*>(host_const_.data() + tt_off);
+            for (int st = 0; st < cnt; ++st)
+                for (int i = 0; i < 4; ++i) {
+                    const int t = ((((long long)kl * i - lo - st) % n) + n) % n;
+                    TT[4 * st + i] = (T)((full || std::min(t, n - t) <= R) ? a[t] : 0.0);
+                }
         };
-        build(n0, n1, 1.0, o0_, o0p(), F.y0lo, F.y0cnt, F.G0_off);   // column 0 of phi_hat: f[u*n1]
-        build(n1, 1, c, o1_, o1p(), F.x1lo, F.x1cnt, F.G1_off);      // row 0 of phi_hat:    f[v]
+        build(n0, n1, 1.0, o0_, o0p(), F.y0lo, F.y0cnt, F.G0_off, F.TT0_off);   // column 0 of phi_hat: f[u*n1]
+        build(n1, 1, c, o1_, o1p(), F.x1lo, F.x1cnt, F.G1_off, F.TT1_off);      // row 0 of phi_hat:    f[v]
         F.ok = true;
     }
 
@@ -524,9 +536,32 @@ private:
         // dense (full-circle) low-pass windows go to the tensor cores (float static instances only)
         a.use_mma = (!gparent && !spec_out && use_mma_ && sizeof(T) == 4 && F.x1cnt >= a.n1 && F.y0cnt >= a.n0 &&
                      a.o1p % 16 == 0 && a.o0p % 16 == 0) ? 1 : 0;
-        const size_t smem = tile_smem_layout<T>(a, nullptr);
         const int G = Bp * NF;
         a.G = G;
+        a.prefetch = prefetch_;
+        const double bytes = (double)G * a.P0 * a.P1 * sizeof(cx<T>) + (double)NF * a.P0 * a.P1 * sizeof(T) +
+                             (double)G * o0_ * o1_ * sizeof(T) + (spec_out ? (double)G * a.n0 * a.n1 * sizeof(cx<T>) : 0.0);
+        const std::string label = std::string("tile_") + what + ":L" + std::to_string(parent_res) + ">L" +
+                                  std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_));
+        // leaf paths of fields that would fill an SM: two half-size passes per path, two CTAs per SM (tile2h.cuh)
+        if (!spec_out && !gparent && tile2h_mode_ > 0 && (tile2h_mode_ > 1 || tile_is_big(a.n0, a.n1)) && res + 1 <= d_.J &&
+            lev_[res + 1].a0.n * 2 == a.n0 && a.n1 % 4 == 0 && a.P1 % 4 == 0) {
+            if (TileKernel<T> k2 = tile2h_kernel_lookup<T>(a.n0, a.n1, a.k)) {
+                a.twh = tw(lev_[res + 1].a0); a.posh = pos(lev_[res + 1].a0);
+                a.TT0 = reinterpret_cast<const T*>(cbuf_ + F.TT0_off);
+                a.TT1 = reinterpret_cast<const T*>(cbuf_ + F.TT1_off);
+                const size_t smem2 = tile2h_smem_layout<T>(a, nullptr);
+                const int threads2 = std::max(64, std::min(kTile2hMaxThreads, tile2h_threads_) / 32 * 32);
+                if ((a.o0p >> 2) * a.o1p <= threads2 && smem2 <= kMaxDynSmem) {
+                    int occ2 = 0;
+                    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2, threads2, smem2));
+                    const int grid2 = std::max(1, std::min(G, std::max(1, occ2) * num_sms_));
+                    launch(label, bytes, st, [&] { k2<<<(unsigned)grid2, dim3(32, threads2 / 32), smem2, st>>>(a); });
+                    return;
+                }
+            }
+        }
+        const size_t smem = tile_smem_layout<T>(a, nullptr);
         bool is_static = false;
         TileKernel<T> kern = gparent ? tile_bwd_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static)
                                      : tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
@@ -557,11 +592,7 @@ private:
         int occ = 0;
         SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         const int grid = std::max(1, std::min(G, std::max(1, occ) * num_sms_));
-        const double bytes = (double)G * a.P0 * a.P1 * sizeof(cx<T>) + (double)NF * a.P0 * a.P1 * sizeof(T) +
-                             (double)G * o0_ * o1_ * sizeof(T) + (spec_out ? (double)G * a.n0 * a.n1 * sizeof(cx<T>) : 0.0);
-        launch(std::string("tile_") + what + ":L" + std::to_string(parent_res) + ">L" + std::to_string(res) + ":G" +
-                   std::to_string(G / std::max(1, last_B_)),
-               bytes, st, [&] { kern<<<(unsigned)grid, block, smem, st>>>(a); });
+        launch(label, bytes, st, [&] { kern<<<(unsigned)grid, block, smem, st>>>(a); });
     }
 
     void forward_chunk(const T* x, T* out, cx<T>* ws, int B, cudaStream_t st) {
@@ -654,6 +685,9 @@ private:
     std::vector<size_t> tile_smem_;
     bool force_stream_ = false;
     int tile_threads_cap_ = env_int("SCAT_B200_TILE_THREADS", 608);
+    int prefetch_ = env_int("SCAT_B200_PREFETCH", 1);             // bulk L2 prefetch of the next path's parent
+    int tile2h_mode_ = env_int("SCAT_B200_TILE2H", 1);            // 0 off, 1 big fields only, 2 every static size
+    int tile2h_threads_ = env_int("SCAT_B200_TILE2H_THREADS", 384);
     int chunk_cap_ = env_int("SCAT_B200_CHUNK", 0);
     int num_sms_ = 148;
     bool use_mma_ = env_int("SCAT_B200_NO_MMA", 0) == 0;

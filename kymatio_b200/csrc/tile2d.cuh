@@ -53,20 +53,24 @@ template <typename T> struct TileArgs {
     int PP, NFch, ch0, chs, K;
     int G;                                 // number of paths; CTAs are persistent and stride over them
     int use_mma;                           // 1: dense low-pass products on the tensor cores (3xTF32 mma.sync)
+    int prefetch;                          // 1: bulk L2 prefetch of the next path's parent spectrum (kernels2d.cuh)
     // backward kernel only: gradient w.r.t. the output planes (same layout / channel mapping as `out`) and the
     // parent-gradient accumulator [NPAR][P0][P1] (atomically added to; zeroed by the caller)
     const T* gout; cx<T>* gparent;
+    // two-half leaf kernel only (tile2h.cuh): twiddles / scramble table of the half-length column transform and the
+    // [cnt][4] tap tables of the shift-invariant low-pass
+    const cx<T>* twh; const int* posh; const T* TT0; const T* TT1;
 };
 
 template <typename T> struct TileSmem {
-    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; int2* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1; T* gs; int2* xr;
+    cx<T>* tile; cx<T>* tw0; cx<T>* tw1; unsigned* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1; T* gs; int2* xr;
 };
 template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return o; };
     const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
     const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
-    const size_t o_supp = take(sizeof(int2) * a.P0);
+    const size_t o_supp = take(sizeof(unsigned) * 2 * a.P0);  // packed (start | len << 16), double buffered: the next path's rows are staged early
     // pitches: +4 (CUDA-core path, 16-byte rows) or +8 (mma path, conflict-free fragment loads); K padded to 8
     const size_t o_w1 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o1p + 8));
     const size_t o_g0 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
@@ -81,7 +85,7 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
         unsigned char* base = dyn_smem<unsigned char>();
         L->tile = reinterpret_cast<cx<T>*>(base + o_tile);
         L->tw0 = reinterpret_cast<cx<T>*>(base + o_tw0); L->tw1 = reinterpret_cast<cx<T>*>(base + o_tw1);
-        L->supp = reinterpret_cast<int2*>(base + o_supp);
+        L->supp = reinterpret_cast<unsigned*>(base + o_supp);
         L->w1 = reinterpret_cast<T*>(base + o_w1);
         L->G0 = reinterpret_cast<T*>(base + o_g0); L->G1 = reinterpret_cast<T*>(base + o_g1);
         L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
@@ -91,6 +95,12 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     }
     return off;
 }
+
+// per-row filter supports are staged packed: start | len << 16 (both < 65536 for any field that fits a tile)
+__device__ __forceinline__ void stage_supp(unsigned* dst, const int2* __restrict__ src, int n) {
+    for (int i = flat_tid(); i < n; i += flat_nt()) { const int2 v = src[i]; dst[i] = (unsigned)v.x | ((unsigned)v.y << 16); }
+}
+__device__ __forceinline__ int2 unpack_supp(unsigned v) { return make_int2((int)(v & 0xffffu), (int)(v >> 16)); }
 
 __device__ __forceinline__ float fast_abs(float x, float y) {
     const float m2 = x * x + y * y;
@@ -109,9 +119,9 @@ __host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_
 //   NATURAL = true : result stored at s[r*W + e + i] (static instances: the inverse runs as DIF)
 //   NATURAL = false: result scattered to s[pos0[r]*W + pos1[e+i]] (generic instance: DIT inverse)
 template <typename T, int VEC, int KT, bool NATURAL>
-__device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, const cx<T>* __restrict__ pb,
-                                               const T* __restrict__ fb, int r, int e, int k, int n0, int n1, int W,
-                                               int P1, T scale, int lane) {
+__device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, const unsigned* supp,
+                                               const cx<T>* __restrict__ pb, const T* __restrict__ fb, int r, int e,
+                                               int k, int n0, int n1, int W, int P1, T scale, int lane) {
     T ax[VEC], ay[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { ax[i] = T(0); ay[i] = T(0); }
@@ -120,7 +130,7 @@ __device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, c
 #pragma unroll
         for (int c = 0; c < KT; ++c) {
             const int R = r + c * n0;
-            const int2 sp = m.supp[R];
+            const int2 sp = unpack_supp(supp[R]);
             if (KT > 2 && sp.y == 0) continue;            // whole filter row negligible (common for coarse psi)
             const size_t rowoff = (size_t)R * P1;
             cx2<T> v0[KT], v1[KT];
@@ -146,7 +156,7 @@ __device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, c
     } else {
         for (int c = 0; c < k; ++c) {
             const int R = r + c * n0;
-            const int2 sp = m.supp[R];
+            const int2 sp = unpack_supp(supp[R]);
             if (sp.y == 0) continue;
             const size_t rowoff = (size_t)R * P1;
             for (int d = 0; d < k; ++d) {
@@ -207,10 +217,12 @@ __device__ __forceinline__ void tile_load_item(cx<T>* s, const TileSmem<T>& m, c
 // which keeps fp32-level accuracy (dropped term ~2^-22).  G0s/G1s are G0/G1 with rows permuted into the
 // storage (scrambled) order of the field, so no position lookups are needed.
 // ---------------------------------------------------------------------------------------------------
+// hi = x truncated to the 10 explicit mantissa bits of TF32 (one LOP3), lo = x - hi exactly (one FADD); the tensor core
+// reads only the TF32 bits of lo, i.e. truncates it again: |x - (hi + tf32(lo))| < 2^-20 |x|.  (cvt.rna.tf32.f32 is a
+// multi-instruction emulation on sm_100a - it was a quarter of the instructions of the 68 x 68 tile kernel.)
 __device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -277,11 +289,20 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     }
 
     SB_PHASE_INIT((N0 == 136 ? 0 : N0 == 68 ? 1 : 2) * 8 + (KT == 4 ? 4 : 0) + (a.spec_out ? 2 : 0) + (a.PP != a.NFch ? 1 : 0))
-    for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
+    if ((int)blockIdx.x < a.G) stage_supp(m.supp, a.supp + (size_t)(blockIdx.x % a.NF) * a.P0, a.P0);
+    int sbuf = 0;
+    for (int g = blockIdx.x; g < a.G; g += gridDim.x, sbuf ^= 1) {
         const int fi = g % a.NF, pg = g / a.NF;
         const int b = g / a.PP, path = g - b * a.PP;
         const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
-        stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
+        const unsigned* supp = m.supp + sbuf * a.P0;
+        const int gn = g + gridDim.x;
+        // the next path of this CTA: pull its slice of the parent spectrum into L2 now (the NF CTAs that share a
+        // parent cover it together), and stage its support rows into the other buffer
+        if (gn < a.G) {
+            if (a.prefetch) prefetch_rows_slice(a.parent + (size_t)(gn / a.NF) * a.P0 * a.P1, a.P0, a.P1, gn % a.NF, a.NF, tid, nt);
+            stage_supp(m.supp + (sbuf ^ 1) * a.P0, a.supp + (size_t)(gn % a.NF) * a.P0, a.P0);
+        }
         __syncthreads();
         SB_PHASE(0);
 
@@ -295,13 +316,13 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 const int per_row = n1 >> 2, items = n0 * per_row;
                 for (int it = tid; it < items; it += nt) {
                     const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
-                    tile_load_item<T, 4, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
+                    tile_load_item<T, 4, KT, ST>(s, m, supp, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
                 }
             } else {
                 const int per_row = n1 >> 1, items = n0 * per_row;
                 for (int it = tid; it < items; it += nt) {
                     const int r0 = it / per_row, e0 = 2 * (it - r0 * per_row);
-                    tile_load_item<T, 2, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
+                    tile_load_item<T, 2, KT, ST>(s, m, supp, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
                 }
             }
         }
@@ -508,7 +529,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
         const int fi = g % a.NF, pg = g / a.NF;
         const int b = g / a.PP, path = g - b * a.PP;
         const int ch = a.ch0 + (path / a.NFch) * a.chs + (path % a.NFch);
-        stage(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
+        stage_supp(m.supp, a.supp + (size_t)fi * a.P0, a.P0);
         {
             const T* gb = a.gout + ((size_t)b * a.K + ch) * a.o0 * a.o1;
             for (int i = tid; i < a.o0p * a.o1p; i += nt) {
@@ -525,13 +546,13 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             const int per_row = n1 >> 2, items = n0 * per_row;
             for (int it = tid; it < items; it += nt) {
                 const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
-                tile_load_item<T, 4, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
+                tile_load_item<T, 4, KT, ST>(s, m, m.supp, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
             }
         } else {
             const int per_row = n1 >> 1, items = n0 * per_row;
             for (int it = tid; it < items; it += nt) {
                 const int r0 = it / per_row, e0 = 2 * (it - r0 * per_row);
-                tile_load_item<T, 2, KT, ST>(s, m, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
+                tile_load_item<T, 2, KT, ST>(s, m, m.supp, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
             }
         }
         // 3a. T[row][xo] = sum_yo G0[y][yo] * gS[yo][xo]   (row = storage row of y) - independent of the tile
@@ -581,7 +602,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
                 const cx<T> gv = scal(ST ? s[r * W + e] : s[m.pos0[r] * W + m.pos1[e]], a.scale);
                 for (int c = 0; c < k; ++c) {
                     const int R = r + c * n0;
-                    const int2 sp = m.supp[R];
+                    const int2 sp = unpack_supp(m.supp[R]);
                     if (sp.y == 0) continue;
                     for (int d = 0; d < k; ++d) {
                         const int C = e + d * n1;
