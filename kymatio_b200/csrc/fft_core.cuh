@@ -311,15 +311,11 @@ SB_HD void butterfly(cx<T>* line, int estride, int base, int q, int twstep, cons
 // butterfly, scrambled -> natural; DIF: butterfly then twiddle, natural -> scrambled) and the sign of
 // the exponent are independent, so an inverse transform can run as DIF (natural-order input) and a
 // forward one as DIT (natural-order output).
-template <int R, bool DIT, int SIGN, int Q, int ES, bool MODULUS, typename T>
-SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
+// the register part of butterfly_s: v[0..R) holds the group (natural order in for DIF, slot order in for DIT)
+template <int R, bool DIT, int SIGN, int Q, typename T>
+SB_HD void butterfly_v(cx<T>* v, int twstep, const cx<T>* tw) {
     constexpr bool P2 = ct_is_pow2(R);
     constexpr int LG = ct_log2(R);
-    cx<T> v[R];
-    static_for<0, R>([&](auto k_) {
-        constexpr int k = decltype(k_)::value;
-        v[k] = p0[k * Q * ES];
-    });
     if (!DIT) {
         if constexpr (P2) dif_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
         if constexpr (Q > 1) {
@@ -339,6 +335,16 @@ SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
         }
         if constexpr (P2) dit_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
     }
+}
+
+template <int R, bool DIT, int SIGN, int Q, int ES, bool MODULUS, typename T>
+SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
+    cx<T> v[R];
+    static_for<0, R>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        v[k] = p0[k * Q * ES];
+    });
+    butterfly_v<R, DIT, SIGN, Q, T>(v, twstep, tw);
     static_for<0, R>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
         if constexpr (MODULUS) p0[k * Q * ES] = mk<T>(cabs_fast<T>(v[k]), T(0));

@@ -67,14 +67,19 @@ template <typename V> __device__ __forceinline__ V ld_pred(const void* ptr, bool
 __device__ __forceinline__ void prefetch_l2_bulk(const void* ptr, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
-// rows [slice * ceil(P0/nslices), ...) of a P0 x P1 field at `base` (one instruction per row, one row per thread)
+// rows [slice * ceil(P0/nslices), ...) of a P0 x P1 field at `base`: the slice is contiguous, so ONE thread issues ONE
+// bulk prefetch for all of it (a per-row, per-lane version costs a serialising "waterfall" loop: UBLKPF takes uniform
+// registers)
 template <typename E>
 __device__ __forceinline__ void prefetch_rows_slice(const E* base, int P0, int P1, int slice, int nslices, int tid, int nt) {
-    const unsigned row_bytes = (unsigned)(P1 * sizeof(E));
-    if (row_bytes & 15u) return;
+    (void)nt;
+    if (tid != 0) return;
     const int per = (P0 + nslices - 1) / nslices;
-    const int r1 = min(P0, (slice + 1) * per);
-    for (int r = slice * per + tid; r < r1; r += nt) prefetch_l2_bulk(base + (size_t)r * P1, row_bytes);
+    const int r0 = slice * per, r1 = min(P0, r0 + per);
+    if (r1 <= r0) return;
+    const size_t b0 = (size_t)r0 * P1 * sizeof(E), b1 = (size_t)r1 * P1 * sizeof(E);
+    const size_t a0 = (b0 + 15) & ~(size_t)15, a1 = b1 & ~(size_t)15;      // 16-byte granules inside the slice
+    if (a1 > a0) prefetch_l2_bulk(reinterpret_cast<const char*>(base) + a0, (unsigned)(a1 - a0));
 }
 
 // sum over the k x k aliases of (parent * filter) for output bin (r, e), skipping aliases outside

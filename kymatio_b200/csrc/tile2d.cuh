@@ -54,6 +54,8 @@ template <typename T> struct TileArgs {
     int G;                                 // number of paths; CTAs are persistent and stride over them
     int use_mma;                           // 1: dense low-pass products on the tensor cores (3xTF32 mma.sync)
     int prefetch;                          // 1: bulk L2 prefetch of the next path's parent spectrum (kernels2d.cuh)
+    int stagger_ns;                        // > 0: CTA i starts (i % 4) * stagger_ns late, so that the L2-bound load phases
+                                           // of the persistent CTAs do not all coincide
     // backward kernel only: gradient w.r.t. the output planes (same layout / channel mapping as `out`) and the
     // parent-gradient accumulator [NPAR][P0][P1] (atomically added to; zeroed by the caller)
     const T* gout; cx<T>* gparent;
@@ -114,6 +116,56 @@ __device__ __forceinline__ double fast_abs(double x, double y) { return sqrt(x *
 __host__ __device__ constexpr bool tile_is_big(int n0, int n1) { return n0 == 0 || (long long)n0 * n1 > 10000; }
 __host__ __device__ constexpr int tile_max_threads(int n0, int n1) { return tile_is_big(n0, n1) ? 640 : 320; }
 __host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_is_big(n0, n1) ? 1 : 3; }
+
+// Static instances (alias count KT and field size known at compile time, parent = KT*N0 x KT*N1): product + periodise of
+// the 4 adjacent columns e..e+3 of output row r.  One base address per operand, every alias at an immediate offset; the
+// loads of an alias outside the filter's support are predicated off (zero-filled).
+template <typename T, int N0, int N1, int KT>
+__device__ __forceinline__ void tile_load_item_s(cx<T>* s, const unsigned* supp, const cx<T>* __restrict__ pb,
+                                                 const T* __restrict__ fb, int r, int e, T scale, int lane) {
+    constexpr int P1 = N1 * KT, W = N1 | 1;
+    T ax[4], ay[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ax[i] = T(0); ay[i] = T(0); }
+    const cx<T>* __restrict__ p0 = pb + (size_t)r * P1 + e;
+    const T* __restrict__ f0 = fb + (size_t)r * P1 + e;
+#pragma unroll
+    for (int c = 0; c < KT; ++c) {
+        const int2 sp = unpack_supp(supp[r + c * N0]);
+        if (KT > 2 && sp.y == 0) continue;                // whole filter row negligible (common for coarse psi)
+        cx2<T> v0[KT], v1[KT];
+        re4<T> f[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            int rel = e + d * N1 - sp.x;
+            if (rel < 0) rel += P1;
+            const bool in = (rel < sp.y) | ((rel > P1 - 4) & (sp.y > 0));
+            const size_t off = (size_t)c * N0 * P1 + (size_t)d * N1;
+            v0[d] = ld_pred<cx2<T>>(p0 + off, in);
+            v1[d] = ld_pred<cx2<T>>(p0 + off + 2, in);
+            f[d] = ld_pred<re4<T>>(f0 + off, in);
+        }
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            ax[0] += v0[d].a.x * f[d].a; ay[0] += v0[d].a.y * f[d].a;
+            ax[1] += v0[d].b.x * f[d].b; ay[1] += v0[d].b.y * f[d].b;
+            ax[2] += v1[d].a.x * f[d].c; ay[2] += v1[d].a.y * f[d].c;
+            ax[3] += v1[d].b.x * f[d].d; ay[3] += v1[d].b.y * f[d].d;
+        }
+    }
+    cx<T>* dst = s + r * W + e;
+    // rotate which of its 4 columns a lane writes in each of the 4 store instructions by (lane>>2)&3:
+    // lanes l, l+4, l+8, l+12 (same bank group, columns 16 apart) then hit distinct banks
+    const int rot = (lane >> 2) & 3;
+    const bool p0r = rot & 1, p1r = rot & 2;
+    T bx[4], by[4], cxr[4], cyr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { bx[i] = p0r ? ax[(i + 1) & 3] : ax[i]; by[i] = p0r ? ay[(i + 1) & 3] : ay[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { cxr[i] = p1r ? bx[(i + 2) & 3] : bx[i]; cyr[i] = p1r ? by[(i + 2) & 3] : by[i]; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dst[(t + rot) & 3] = mk<T>(cxr[t] * scale, cyr[t] * scale);
+}
 
 // product + periodise for VEC adjacent columns starting at column e of output row r.
 //   NATURAL = true : result stored at s[r*W + e + i] (static instances: the inverse runs as DIF)
@@ -290,6 +342,9 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
 
     SB_PHASE_INIT((N0 == 136 ? 0 : N0 == 68 ? 1 : 2) * 8 + (KT == 4 ? 4 : 0) + (a.spec_out ? 2 : 0) + (a.PP != a.NFch ? 1 : 0))
     if ((int)blockIdx.x < a.G) stage_supp(m.supp, a.supp + (size_t)(blockIdx.x % a.NF) * a.P0, a.P0);
+    if (a.stagger_ns > 0) {
+        for (int i = (int)(blockIdx.x & 3); i > 0; --i) __nanosleep((unsigned)a.stagger_ns);
+    }
     int sbuf = 0;
     for (int g = blockIdx.x; g < a.G; g += gridDim.x, sbuf ^= 1) {
         const int fi = g % a.NF, pg = g / a.NF;
@@ -312,7 +367,13 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
             const T* __restrict__ fb = a.filt[fi];
             const int P1 = a.P1;
-            if ((n1 & 3) == 0 && (P1 & 3) == 0) {
+            if constexpr (ST && KT > 0 && (N1 & 3) == 0) {
+                constexpr int per_row = N1 >> 2, items = N0 * per_row;
+                for (int it = tid; it < items; it += nt) {
+                    const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
+                    tile_load_item_s<T, N0, N1, KT>(s, supp, pb, fb, r0, e0, a.scale, lane);
+                }
+            } else if ((n1 & 3) == 0 && (P1 & 3) == 0) {
                 const int per_row = n1 >> 2, items = n0 * per_row;
                 for (int it = tid; it < items; it += nt) {
                     const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
