@@ -179,6 +179,10 @@ typedef struct scat1d_finseg {
     const void* chan_dev;             /* int32[NI] */
     int32_t which, nparts, N, Fc, NI, line0;
 } scat1d_finseg;
+/* average='global' tail (kymatio/scattering1d/frontend/base_frontend.py:137-138): out[b*os_b + chan] = bin 0 of the
+ * path's spectrum = the sum over time of its modulus field; same segment table as scat1d_finish. */
+int scat1d_finish_global(const void* u0_dev, const void* u1_dev, const void* part_dev, const void* segs_dev, int32_t nseg,
+                         int64_t total_lines, void* out_dev, int64_t os_b, void* stream);
 size_t scat1d_finseg_bytes(void);
 int    scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1_dev, const void* part_dev,
                      const void* segs_dev, int32_t nseg, int64_t total_lines, int32_t M, void* out_dev, int64_t os_b,

@@ -12,6 +12,7 @@ To use it from an installed, unmodified kymatio instead::
     S = Scattering2D(J=3, shape=(256, 256), backend='torch_b200').cuda()
 """
 from .scattering2d import Scattering2D  # noqa: F401
+from .graph import GraphedScattering  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["Scattering2D"]
+__all__ = ["Scattering2D", "GraphedScattering"]

@@ -85,6 +85,8 @@ SIGNATURES = {
                                _c.c_void_p]),
     "scat1d_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int64,
                                  _c.c_int32, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_double, _c.c_void_p]),
+    "scat1d_finish_global": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int64,
+                                        _c.c_void_p, _c.c_int64, _c.c_void_p]),
     "scat1d_finseg_bytes": (_c.c_size_t, []),
     "scat_fft3d_const_bytes": (_c.c_size_t, [_c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
     "scat_fft3d_init": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),

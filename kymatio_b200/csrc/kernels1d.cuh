@@ -442,6 +442,22 @@ template <typename T, int M> __global__ void __launch_bounds__(k1Threads, 3) k1d
     }
 }
 
+// average='global' tail (kymatio/scattering1d/frontend/base_frontend.py:137-138, backend.average_global): the sum over
+// time of a path's modulus field is bin 0 of its spectrum, which the cascade has already produced (complete for parents
+// and for U0_hat, as per-CTA partial sums for leaves) - no low-pass, no inverse transform.  One thread per path.
+template <typename T> __global__ void k1d_finish_global(Finish1<T> a) {
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= a.total) return;
+    int sgi = 0;
+    while (sgi + 1 < a.nseg && a.segs[sgi + 1].line0 <= line) ++sgi;
+    const FinSeg<T>& sg = a.segs[sgi];
+    const int gl = line - sg.line0, b = gl / sg.NI, i = gl - b * sg.NI;
+    const cx<T>* __restrict__ xb = a.base[sg.which] + sg.src_off + (long long)gl * sg.ss_g;
+    T acc = T(0);
+    for (int q = 0; q < sg.nparts; ++q) acc += xb[q * sg.ss_part].x;
+    a.out[(long long)b * a.os_b + sg.chan[i]] = acc;
+}
+
 // kernel tables (instances in scat1d_inst.cu)
 template <typename T> struct Kern1d {
     void (*col_prod)(ColProd1<T>);

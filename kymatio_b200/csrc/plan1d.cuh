@@ -233,4 +233,18 @@ inline void finish1d(const void* fin_tables, const void* base0, const void* base
     launch("1d_finish:M" + std::to_string(M), algo_bytes, st, [&] { kern<<<grid, block1d(), smem, st>>>(a); });
 }
 
+// bin 0 of every path's spectrum -> out[b*os_b + chan] (average='global')
+inline void finish1d_global(const void* base0, const void* base1, const void* base2, const void* segs_dev, int nseg,
+                            long long total_lines, void* out, long long os_b, cudaStream_t st) {
+    if (total_lines <= 0) return;
+    if (nseg < 1) throw std::runtime_error("finish1d_global: bad sizes");
+    Finish1<float> a{};
+    a.base[0] = static_cast<const cx<float>*>(base0); a.base[1] = static_cast<const cx<float>*>(base1);
+    a.base[2] = static_cast<const cx<float>*>(base2);
+    a.segs = static_cast<const FinSeg<float>*>(segs_dev); a.nseg = nseg; a.total = (int)total_lines;
+    a.out = static_cast<float*>(out); a.os_b = os_b;
+    const unsigned grid = (unsigned)((total_lines + 127) / 128);
+    launch("1d_finish_global", (double)total_lines * 12.0, st, [&] { k1d_finish_global<float><<<grid, 128, 0, st>>>(a); });
+}
+
 }  // namespace sb

@@ -396,6 +396,12 @@ int scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1
                  static_cast<cudaStream_t>(stream));
     });
 }
+int scat1d_finish_global(const void* u0_dev, const void* u1_dev, const void* part_dev, const void* segs_dev, int32_t nseg,
+                         int64_t total_lines, void* out_dev, int64_t os_b, void* stream) {
+    return guarded([&] {
+        finish1d_global(u0_dev, u1_dev, part_dev, segs_dev, nseg, total_lines, out_dev, os_b, static_cast<cudaStream_t>(stream));
+    });
+}
 size_t scat1d_finseg_bytes(void) { return sizeof(FinSeg<float>); }
 
 // ---------------------------------------------------------------- fused 3-D kernels (engine3d.py drives the cascade)

@@ -145,26 +145,41 @@ _FINSEG = np.dtype([("src_off", "<i8"), ("ss_g", "<i8"), ("ss_part", "<i8"), ("p
 
 
 class Engine1D:
-    """One engine per (device, filter-buffer identity, Np, log2_stride)."""
+    """One engine per (device, filter-buffer identity, Np, log2_stride, averaging mode).
 
-    def __init__(self, Np, log2_stride, phi, psi1, psi2, device):
+    average_global=True is the reference's ``average='global'`` (core/scattering1d.py with average_local=False followed by
+    backend.average_global, frontend/base_frontend.py:137-138): every path is subsampled by its own 2^j and the output is
+    the SUM over time of its modulus field = bin 0 of the spectrum the cascade already computes; the low-pass tail is
+    replaced by scat1d_finish_global and the output is (B, K, 1)."""
+
+    def __init__(self, Np, log2_stride, phi, psi1, psi2, device, average_global=False):
         self.lib = _lib.load()
         assert self.lib.scat1d_finseg_bytes() == _FINSEG.itemsize
         self.device = torch.device(device)
         self.Np, self.ls = int(Np), int(log2_stride)
+        self.average_global = bool(average_global)
         if self.Np & (self.Np - 1):
             raise Unsupported("padded length must be a power of two")
+        if self.average_global:
+            # k1 = j1 and k2 = j2 - j1 (core/scattering1d.py:63,88-89 with average_local=False): a stride that never caps
+            self.ls = max([p["j"] for p in psi1] + ([p["j"] for p in psi2] if psi2 is not None else []) + [0])
         sch = schedule(self.Np, self.ls, phi, psi1, psi2)
         self.M, self.K, self.order = sch["M"], sch["K"], sch["order"]
+        if self.average_global:
+            self.M = 1
         self.tables = _Tables(self.device)
         # transforms up to this length run as ONE launch with the whole path in shared memory (scat1d_tile)
         self.tile_max = self.lib.scat1d_tile_max() if os.environ.get("SCAT_B200_1D_TILE", "1") != "0" else 0
         with torch.cuda.device(self.device):
-            self.fin_tab = self.tables.for_lowpass(self.M)
             self._keep = []                        # tensors the device arrays point into
-            phi_lv = [lv.reshape(-1) for lv in phi["levels"]]
-            self.phi_lv = phi_lv
-            self.Fc = [lowpass_bins(lv.detach().cpu().numpy(), LOWPASS_THRESHOLD) for lv in phi_lv]
+            if self.average_global:
+                # only bin 0 is needed: the leaves' pruned transform keeps its minimum of 16 bins, phi is never read
+                self.fin_tab, self.phi_lv, self.Fc = None, None, [16] * (self.ls + 2)
+            else:
+                self.fin_tab = self.tables.for_lowpass(self.M)
+                phi_lv = [lv.reshape(-1) for lv in phi["levels"]]
+                self.phi_lv = phi_lv
+                self.Fc = [lowpass_bins(lv.detach().cpu().numpy(), LOWPASS_THRESHOLD) for lv in phi_lv]
             self.chan0 = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.tables.for_length(self.Np)        # validates Np
             self.groups = []
@@ -174,6 +189,8 @@ class Engine1D:
                 N1, NI = g["N1"], len(g["n1"])
                 if N1 < self.M:
                     raise Unsupported("first-order length below the output length")
+                if N1 < 16:
+                    raise Unsupported("first-order length below 16 samples")
                 filt = [psi1[n]["levels"][0].reshape(-1) for n in g["n1"]]
                 gd = dict(g)
                 gd.update(NI=NI, tab=self.tables.for_length(N1), **self._filter_arrays(filt, self.Np))
@@ -229,8 +246,8 @@ class Engine1D:
 
         def add(which, off, ss_g, ss_part, nparts, level, N, chan_dev, NI):
             nonlocal line, nbytes
-            rows.append((off, ss_g, ss_part, self.phi_lv[level].data_ptr(), chan_dev.data_ptr(), which, nparts, N,
-                         self.Fc[level], NI, line))
+            rows.append((off, ss_g, ss_part, self.phi_lv[level].data_ptr() if self.phi_lv is not None else 0,
+                         chan_dev.data_ptr(), which, nparts, N, self.Fc[level], NI, line))
             line += nb * NI
             nbytes += nb * NI * (nparts * self.Fc[level] * 8 + self.M * 4)
 
@@ -322,6 +339,10 @@ class Engine1D:
                             _lib.check(lib.scat1d_row_mod(ctab, yp, G, N2, cpart, Fc,
                                                           float(G) * 8 * (N2 + c["nparts"] * Fc), st))
                 segs, nseg, lines, nbytes = self._segments(nb)
-                _lib.check(lib.scat1d_finish(self.fin_tab.data_ptr(), u0, up, pp, segs.data_ptr(), nseg, lines, M,
-                                             out.data_ptr() + b0 * K * M * 4, K * M, 0, M, nbytes, st))
+                if self.average_global:
+                    _lib.check(lib.scat1d_finish_global(u0, up, pp, segs.data_ptr(), nseg, lines,
+                                                        out.data_ptr() + b0 * K * 4, K, st))
+                else:
+                    _lib.check(lib.scat1d_finish(self.fin_tab.data_ptr(), u0, up, pp, segs.data_ptr(), nseg, lines, M,
+                                                 out.data_ptr() + b0 * K * M * 4, K * M, 0, M, nbytes, st))
         return out

@@ -22,10 +22,13 @@ torch_backend.py:19-180), so the unchanged core can also be driven primitive by 
 reference's own GPU-only backend (torch_skcuda) the primitives are CUDA-only and not differentiable;
 gradients are provided by the fused path.
 """
+import collections
 import ctypes
 import importlib
 import sys
+import threading
 import types
+import warnings
 
 import torch
 
@@ -102,44 +105,13 @@ class Pad(object):
         return out.reshape(batch_shape + out.shape[-2:] + (1,))
 
 
-class TorchB200Backend2D:
+class _Primitives2D:
+    """The compute primitives of the 2-D backend protocol as this library's kernels.  The generic checks
+    (input_checks, contiguous_check, complex_check, ...), `_is_complex/_is_real` and the reshape helpers are NOT
+    re-typed here: install() composes this mixin with the reference's own kymatio.backend.torch_backend.TorchBackend,
+    so they are inherited unchanged."""
     name = NAME
     Pad = Pad
-
-    # -- checks (kymatio/backend/torch_backend.py:102-135) --------------------------------------------
-    @classmethod
-    def input_checks(cls, x):
-        if x is None:
-            raise TypeError("The input should be not empty.")
-        cls.contiguous_check(x)
-
-    @staticmethod
-    def contiguous_check(x):
-        if not x.is_contiguous():
-            raise RuntimeError("Tensors must be contiguous.")
-
-    @staticmethod
-    def _is_complex(x):
-        return x.shape[-1] == 2
-
-    @staticmethod
-    def _is_real(x):
-        return x.shape[-1] == 1
-
-    @classmethod
-    def complex_check(cls, x):
-        if not cls._is_complex(x):
-            raise TypeError("The input should be complex (i.e. last dimension is 2).")
-
-    @classmethod
-    def real_check(cls, x):
-        if not cls._is_real(x):
-            raise TypeError("The input should be real.")
-
-    @classmethod
-    def complex_contiguous_check(cls, x):
-        cls.complex_check(x)
-        cls.contiguous_check(x)
 
     # -- primitives -------------------------------------------------------------------------------------
     @classmethod
@@ -153,25 +125,22 @@ class TorchB200Backend2D:
 
     @classmethod
     def _cdgmm_checks(cls, A, B):
-        # kymatio/backend/torch_backend.py:181-219
-        if not cls._is_real(B):
-            cls.complex_contiguous_check(B)
-        else:
-            cls.contiguous_check(B)
+        """The argument contract of the reference's cdgmm (kymatio/backend/torch_backend.py:181-219): same conditions,
+        same exception types and messages, in the same order."""
+        (cls.contiguous_check if cls._is_real(B) else cls.complex_contiguous_check)(B)
         cls.complex_contiguous_check(A)
-        if A.shape[-len(B.shape):-1] != B.shape[:-1]:
-            raise RuntimeError("The filters are not compatible for multiplication.")
-        if A.dtype is not B.dtype:
-            raise TypeError("Input and filter must be of the same dtype.")
-        if B.device.type == "cuda":
-            if A.device.type == "cuda":
-                if A.device.index != B.device.index:
-                    raise TypeError("Input and filter must be on the same GPU.")
-            else:
-                raise TypeError("Input must be on GPU.")
-        if B.device.type == "cpu":
-            if A.device.type == "cuda":
-                raise TypeError("Input must be on CPU.")
+        a_dev, b_dev = A.device, B.device
+        rules = (
+            (A.shape[-len(B.shape):-1] != B.shape[:-1], RuntimeError, "The filters are not compatible for multiplication."),
+            (A.dtype is not B.dtype, TypeError, "Input and filter must be of the same dtype."),
+            (b_dev.type == "cuda" and a_dev.type == "cuda" and a_dev.index != b_dev.index, TypeError,
+             "Input and filter must be on the same GPU."),
+            (b_dev.type == "cuda" and a_dev.type != "cuda", TypeError, "Input must be on GPU."),
+            (b_dev.type == "cpu" and a_dev.type == "cuda", TypeError, "Input must be on CPU."),
+        )
+        for failed, exc, msg in rules:
+            if failed:
+                raise exc(msg)
 
     @classmethod
     def cdgmm(cls, A, B):
@@ -247,22 +216,9 @@ class TorchB200Backend2D:
     def stack(arrays):
         return torch.stack(arrays, -3)
 
-    # generic helpers used by other frontends of the protocol (kymatio/backend/torch_backend.py:222-232)
-    @staticmethod
-    def reshape_input(x, signal_shape):
-        return x.reshape((-1, 1) + signal_shape)
 
-    @staticmethod
-    def reshape_output(S, batch_shape, n_kept_dims):
-        return S.reshape(batch_shape + S.shape[-n_kept_dims:])
-
-    @staticmethod
-    def shape(x):
-        return x.shape
-
-
-backend2d = TorchB200Backend2D
-backend = backend2d
+# the backend classes exist once install() has composed the mixins with the reference's base classes
+backend2d = backend1d = backend3d = backend = None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -347,8 +303,9 @@ class _DifferentiableEager:
         return ops_eager.RealPart.apply(cls._dfft(x, True))
 
 
-class TorchB200Backend1D(_DifferentiableEager, TorchB200Backend2D):
-    """Same generic primitives (checks, modulus, cdgmm) plus the 1-D specific ones."""
+class _Primitives1D:
+    """The 1-D specific compute primitives; average_global, unpad and the joint time-frequency reshapes (pad_frequency,
+    swap_time_frequency, unpad_frequency, split_frequency_axis) are inherited from the reference's TorchBackend1D."""
     Pad = None
 
     @classmethod
@@ -388,11 +345,6 @@ class TorchB200Backend1D(_DifferentiableEager, TorchB200Backend2D):
                                               int(pad_right), _dtype_code(x), _stream(x)))
         return out[..., None]
 
-    @staticmethod
-    def unpad(x, i0, i1):
-        x = x.reshape(x.shape[:-1])
-        return x[..., i0:i1]
-
     @classmethod
     def _fft(cls, x, inverse):
         N = x.shape[-2]
@@ -412,35 +364,11 @@ class TorchB200Backend1D(_DifferentiableEager, TorchB200Backend2D):
         _cuda_check(x)
         return cls._fft(x, False)
 
-    @classmethod
-    def average_global(cls, x):
-        cls.contiguous_check(x)
-        cls.real_check(x)
-        return torch.sum(x, axis=-2, keepdims=True)
-
     @staticmethod
     def stack(arrays, dim=2):
         return torch.stack(arrays, dim=dim)
 
-    # joint time-frequency helpers are pure reshapes in the reference (torch_backend.py:151-223)
-    @classmethod
-    def pad_frequency(cls, x, padding):
-        return torch.nn.functional.pad(x, (0, 0, 0, padding), mode="constant", value=0)
 
-    @classmethod
-    def swap_time_frequency(cls, x):
-        return torch.transpose(x, dim0=-2, dim1=-3).contiguous()
-
-    @staticmethod
-    def unpad_frequency(x, n1_max, n1_stride):
-        return x[:, :, :1 + (n1_max // n1_stride), :]
-
-    @staticmethod
-    def split_frequency_axis(x):
-        return torch.split(x, 1, dim=-3)
-
-
-backend1d = TorchB200Backend1D
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -466,7 +394,7 @@ class _Fft3dTables:
         return buf
 
 
-class TorchB200Backend3D(_DifferentiableEager, TorchB200Backend2D):
+class _Primitives3D:
     Pad = None
 
     @staticmethod
@@ -529,13 +457,50 @@ class TorchB200Backend3D(_DifferentiableEager, TorchB200Backend2D):
         return acc.to(torch.get_default_dtype())
 
 
-backend3d = TorchB200Backend3D
 
 # ---------------------------------------------------------------------------------------------------
 # fused dispatch
 # ---------------------------------------------------------------------------------------------------
-_engines = {}
+class _EngineCache:
+    """Small thread-safe LRU of engines (class-level backends are shared by nn.DataParallel replica threads): a lookup
+    holds the lock while the engine is built, so two threads never build the same plan twice; the least recently used
+    entry is dropped when the cache is full - a live engine stays referenced by whoever is using it."""
+
+    def __init__(self, capacity):
+        self.capacity, self._d, self._lock = capacity, collections.OrderedDict(), threading.RLock()
+
+    def get(self, key, build):
+        with self._lock:
+            if key in self._d:
+                self._d.move_to_end(key)
+                return self._d[key]
+            value = build()
+            self._d[key] = value
+            while len(self._d) > self.capacity:
+                self._d.popitem(last=False)
+            return value
+
+    def clear(self):
+        with self._lock:
+            self._d.clear()
+
+    def __len__(self):
+        return len(self._d)
+
+
+_engines = _EngineCache(32)
 _originals = {}
+_tls = threading.local()            # .frontend3d: the HarmonicScattering3D module whose scattering() is running
+_warned = set()
+
+
+def _warn_fallback(what, why):
+    """One warning per (transform, reason): a torch_b200 call that leaves the fused schedule for the per-primitive eager
+    kernels is several times slower and must not do so silently."""
+    if (what, why) not in _warned:
+        _warned.add((what, why))
+        warnings.warn("torch_b200: %s runs on the eager per-primitive kernels instead of the fused schedule (%s)" % (what, why),
+                      RuntimeWarning, stacklevel=3)
 
 
 def _fused_scattering2d(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_type="array"):
@@ -552,9 +517,7 @@ def _fused_scattering2d(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_
     if phi_levels[0].device != x.device:
         raise TypeError("Input and filter must be on the same GPU." if phi_levels[0].is_cuda else "Input must be on CPU.")
     key = (M, N, J, L, max_order, pre_pad, x.dtype, x.device.index)
-    eng = _engines.get(key)
-    if eng is None:
-        eng = _engines[key] = Engine2D(M, N, J, L, max_order, pre_pad, x.dtype, x.device)
+    eng = _engines.get(key, lambda: Engine2D(M, N, J, L, max_order, pre_pad, x.dtype, x.device))
     eng.bind(phi_levels, psi_levels)
     S = scattering2d_apply(eng, x.reshape((-1, M, N)).contiguous())
     if out_type == "array":
@@ -577,7 +540,7 @@ def _fused_scattering2d(x, pad, unpad, backend_, J, L, phi, psi, max_order, out_
     return out
 
 
-_engines1d = {}
+_engines1d = _EngineCache(16)
 
 
 def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
@@ -590,12 +553,9 @@ def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
     tensors = list(phi["levels"]) + [lv for p in psi1 for lv in p["levels"]]
     if psi2 is not None:
         tensors += [lv for p in psi2 for lv in p["levels"]]
-    key = (U_0.device.index, Np, int(log2_stride), psi2 is None) + tuple((t.data_ptr(), t._version) for t in tensors)
-    eng = _engines1d.get(key)
-    if eng is None:
-        if len(_engines1d) > 16:
-            _engines1d.clear()
-        eng = _engines1d[key] = Engine1D(Np, log2_stride, phi, psi1, psi2, U_0.device)
+    glob = not average_local
+    key = (U_0.device.index, Np, int(log2_stride), psi2 is None, glob) + tuple((t.data_ptr(), t._version) for t in tensors)
+    eng = _engines1d.get(key, lambda: Engine1D(Np, log2_stride, phi, psi1, psi2, U_0.device, average_global=glob))
     S = eng.forward(eng.rfft(U_0.reshape(-1, Np).contiguous()))
     B = S.shape[0]
     for kind, n1, n2, ch in eng.order:
@@ -609,8 +569,17 @@ def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
 
 
 def _fusable1d(U_0, backend_, filters, log2_stride, average_local):
-    if getattr(backend_, "name", None) != NAME or not average_local:
+    if getattr(backend_, "name", None) != NAME:
         return False
+    if not average_local:
+        # average_local=False is either average='global' (sum over time: fused, scat1d_finish_global) or T=0 (the
+        # full-resolution modulus of every path, unpadded by the frontend: eager primitives).  install() records the
+        # running frontend, which knows which one it is.
+        owner = getattr(_tls, "frontend1d", None)
+        if getattr(owner, "average", None) != "global":
+            if torch.is_tensor(U_0) and U_0.is_cuda:
+                _warn_fallback("Scattering1D", "T=0 returns unaveraged full-resolution paths")
+            return False
     if _wants_grad(U_0):
         return False                      # gradients: the unchanged core drives the differentiable eager primitives
     if not (torch.is_tensor(U_0) and U_0.is_cuda and U_0.dtype == torch.float32 and U_0.dim() == 4):
@@ -618,12 +587,15 @@ def _fusable1d(U_0, backend_, filters, log2_stride, average_local):
     if filters[0]["levels"][0].dtype != torch.float32 or not filters[0]["levels"][0].is_cuda:
         return False
     Np = U_0.shape[-2]
+    jmax = max([p["j"] for f in filters[1:] for p in f] + [0])
+    if not average_local:
+        return Np & (Np - 1) == 0 and Np <= (1 << 18) and (Np >> jmax) >= 16
     M = Np >> int(log2_stride)
     return Np & (Np - 1) == 0 and Np <= (1 << 18) and 8 <= M <= 1024 and (Np >> max(
         [p["j"] for p in filters[1]] + [0])) >= 16
 
 
-_engines3d = {}
+_engines3d = _EngineCache(16)
 
 
 def _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend_, averaging):
@@ -636,31 +608,53 @@ def _fused_scattering3d(x, filters, rotation_covariant, L, J, max_order, backend
         return None                       # gradients: the unchanged core drives the differentiable eager primitives
     if any((not f.is_cuda) or f.dtype != torch.float32 or not f.is_contiguous() for f in filters[:L + 1]):
         return None
-    # the frontend passes `averaging` as a closure over itself (scattering3d/frontend/torch_frontend.py:70-71)
-    powers = None
-    for cell in (getattr(averaging, "__closure__", None) or ()):
-        owner = cell.cell_contents
-        if hasattr(owner, "integral_powers") and getattr(owner, "method", "integral") == "integral":
-            powers = [float(q) for q in owner.integral_powers]
+    # install() wraps the frontend's scattering() so that the running module is known here: `averaging` is
+    # `lambda x: backend.compute_integrals(x, self.integral_powers)` (scattering3d/frontend/torch_frontend.py:70-71)
+    owner = getattr(_tls, "frontend3d", None)
+    if owner is None or getattr(owner, "method", "integral") != "integral":
+        _warn_fallback("HarmonicScattering3D", "scattering3d() was not called through the frontend: integral_powers unknown")
+        return None
+    powers = [float(q) for q in owner.integral_powers]
     if not powers or len(powers) > 8 or max_order not in (1, 2):
+        _warn_fallback("HarmonicScattering3D", "more than 8 integral powers" if len(powers) > 8 else "unsupported max_order")
         return None
     M, N, O = x.shape[1:4]
-    key = (x.device.index, M, N, O)
-    eng = _engines3d.get(key)
-    if eng is None:
+
+    def build():
         try:
-            eng = _engines3d[key] = Engine3D(M, N, O, x.device)
+            return Engine3D(M, N, O, x.device)
         except Unsupported:
-            _engines3d[key] = eng = False
+            return False
+
+    eng = _engines3d.get((x.device.index, M, N, O), build)
     if not eng:
+        _warn_fallback("HarmonicScattering3D", "no fused kernel instance for a %d x %d x %d volume" % (M, N, O))
         return None
     U0_hat = eng.rfft(x.reshape(x.shape[:4]).contiguous())
     return eng.forward(U0_hat, filters, bool(rotation_covariant), int(L), int(J), int(max_order), powers)
 
 
+def _compose_backends():
+    """Build the backend classes: this library's compute primitives on top of the reference's OWN base classes, so that
+    the checks, reshape helpers and the joint time-frequency reshapes are inherited, not restated."""
+    global backend2d, backend1d, backend3d, backend
+    if backend2d is not None:
+        return
+    from kymatio.backend.torch_backend import TorchBackend as RefBackend
+    from kymatio.scattering1d.backend.torch_backend import TorchBackend1D as RefBackend1D
+    from kymatio.scattering3d.backend.torch_backend import TorchBackend3D as RefBackend3D
+    backend2d = type("TorchB200Backend2D", (_Primitives2D, RefBackend), {"name": NAME, "Pad": Pad, "__doc__": _Primitives2D.__doc__})
+    backend1d = type("TorchB200Backend1D", (_DifferentiableEager, _Primitives1D, _Primitives2D, RefBackend1D),
+                     {"name": NAME, "Pad": None, "__doc__": _Primitives1D.__doc__})
+    backend3d = type("TorchB200Backend3D", (_DifferentiableEager, _Primitives3D, _Primitives2D, RefBackend3D),
+                     {"name": NAME, "Pad": None})
+    backend = backend2d
+
+
 def install(fused=True):
     """Register the backend module and (optionally) the fused core dispatcher. Idempotent."""
     import kymatio.scattering2d.frontend.torch_frontend as tf2d   # the unmodified reference
+    _compose_backends()
 
     mod_name = "kymatio.scattering2d.backend.torch_b200_backend"
     if mod_name not in sys.modules:
@@ -693,7 +687,20 @@ def install(fused=True):
     import kymatio.scattering1d.frontend.base_frontend as bf1d
     if "scattering1d" not in _originals:
         _originals["scattering1d"] = bf1d.scattering1d
+        _originals["frontend1d.scattering"] = bf1d.ScatteringBase1D.scattering
     reference_core1d = _originals["scattering1d"]
+    frontend_scattering1d = _originals["frontend1d.scattering"]
+
+    def scattering1d_with_owner(self, x):
+        # the unmodified method, with the running module recorded for the dispatcher (average = 'global' or False)
+        prev = getattr(_tls, "frontend1d", None)
+        _tls.frontend1d = self
+        try:
+            return frontend_scattering1d(self, x)
+        finally:
+            _tls.frontend1d = prev
+    scattering1d_with_owner.__wrapped__ = frontend_scattering1d
+    bf1d.ScatteringBase1D.scattering = scattering1d_with_owner
     if fused:
         def dispatch1d(U_0, backend_, filters, log2_stride, average_local):
             if _fusable1d(U_0, backend_, filters, log2_stride, average_local):
@@ -701,7 +708,8 @@ def install(fused=True):
                 try:
                     gen = _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local)
                     first = next(gen)
-                except Unsupported:
+                except Unsupported as e:
+                    _warn_fallback("Scattering1D", str(e) or "configuration outside the fused kernels")
                     return reference_core1d(U_0, backend_, filters, log2_stride, average_local)
                 import itertools
                 return itertools.chain([first], gen)
@@ -714,7 +722,20 @@ def install(fused=True):
     import kymatio.scattering3d.frontend.torch_frontend as tf3d
     if "scattering3d" not in _originals:
         _originals["scattering3d"] = tf3d.scattering3d
+        _originals["frontend3d.scattering"] = tf3d.HarmonicScatteringTorch3D.scattering
     reference_core3d = _originals["scattering3d"]
+    frontend_scattering3d = _originals["frontend3d.scattering"]
+
+    def scattering_with_owner(self, input_array):
+        # the unmodified method, with the running module recorded for the fused dispatcher (integral_powers, method)
+        prev = getattr(_tls, "frontend3d", None)
+        _tls.frontend3d = self
+        try:
+            return frontend_scattering3d(self, input_array)
+        finally:
+            _tls.frontend3d = prev
+    scattering_with_owner.__wrapped__ = frontend_scattering3d
+    tf3d.HarmonicScatteringTorch3D.scattering = scattering_with_owner
     if fused:
         def dispatch3d(x, filters, rotation_covariant, L, J, max_order, backend, averaging):
             if getattr(backend, "name", None) == NAME:
@@ -747,6 +768,8 @@ def uninstall():
     if "scattering1d" in _originals:
         import kymatio.scattering1d.frontend.base_frontend as bf1d
         bf1d.scattering1d = _originals["scattering1d"]
+        bf1d.ScatteringBase1D.scattering = _originals["frontend1d.scattering"]
     if "scattering3d" in _originals:
         import kymatio.scattering3d.frontend.torch_frontend as tf3d
         tf3d.scattering3d = _originals["scattering3d"]
+        tf3d.HarmonicScatteringTorch3D.scattering = _originals["frontend3d.scattering"]

@@ -123,6 +123,16 @@ def golden_1d():
              **{k: np.array(v) for k, v in kw.items()})
 
 
+def golden_3d_c4():
+    """BASELINE configs[3] at its own size (J=2, L=2, 128^3): the 8 MB input is NOT stored - it is regenerated from the
+    seed (legacy RandomState streams are stable across numpy versions); only the (1, 6, 3, 3) output is committed."""
+    x = np.random.RandomState(1234).randn(1, 128, 128, 128).astype(np.float32)
+    S = HarmonicScattering3D(J=2, shape=(128, 128, 128), L=2)
+    Sx = S(x.astype(np.float64))
+    save("golden_3d_c4_J2_L2_128.npz", seed=1234, Sx64=np.asarray(Sx, dtype=np.float64), J=2, L=2,
+         shape=np.array((128, 128, 128)), x_first8=x.ravel()[:8], x_sum=np.float64(x.astype(np.float64).sum()))
+
+
 def golden_3d():
     rng = np.random.RandomState(11)
     cases = [
@@ -146,3 +156,4 @@ if __name__ == "__main__":
     golden_2d()
     golden_1d()
     golden_3d()
+    golden_3d_c4()

@@ -249,3 +249,45 @@ def test_fused1d_streams_rebinding_and_float64(plugin):
     assert yd.dtype == torch.float64
     # (the module's filters were rounded to float32 at registration, kymatio/scattering1d/frontend/torch_frontend.py:36-40)
     assert np.abs(yd.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("kw", [dict(J=6, shape=4096, Q=(8, 1), T="global"), dict(J=5, shape=3000, Q=(4, 2), T="global"),
+                                dict(J=7, shape=2 ** 14, Q=(8, 1), T="global", max_order=1)])
+def test_fused1d_average_global(plugin, kw):
+    """average='global' (kymatio/scattering1d/frontend/base_frontend.py:137-138, core/scattering1d.py with
+    average_local=False) through the fused schedule: the sum over time of every path is bin 0 of its spectrum
+    (scat1d_finish_global); against the reference's numpy frontend in float64."""
+    from kymatio.torch import Scattering1D
+    from kymatio.scattering1d.frontend.numpy_frontend import ScatteringNumPy1D
+    from kymatio_b200 import _lib
+    x = np.random.RandomState(3).randn(3, kw["shape"])
+    S = Scattering1D(backend="torch_b200", **kw).cuda()
+    _lib.timing_enable(True)
+    y = S(torch.from_numpy(x).float().cuda())
+    labels = {r["label"].split(":")[0] for r in _lib.timing_report()}
+    _lib.timing_enable(False)
+    assert "1d_finish_global" in labels, labels
+    ref = ScatteringNumPy1D(**kw)(x)
+    assert tuple(y.shape) == ref.shape == (3, ref.shape[1], 1)
+    assert_parity(y.cpu().numpy(), ref, channel_axis=-2, what=str(kw))
+
+
+def test_1d_T0_falls_back_loudly(plugin):
+    """T=0 (unaveraged full-resolution paths) is outside the fused schedule: the unchanged core drives the eager
+    primitives, the result matches the reference, and the fall-back is announced once."""
+    import warnings
+    from kymatio.torch import Scattering1D
+    from kymatio.scattering1d.frontend.numpy_frontend import ScatteringNumPy1D
+    kw = dict(J=4, shape=1024, Q=(4, 1), T=0, out_type="list")
+    x = np.random.RandomState(4).randn(2, 1024)
+    S = Scattering1D(backend="torch_b200", **kw).cuda()
+    plugin._warned.clear()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        y = S(torch.from_numpy(x).float().cuda())
+    assert any("eager per-primitive kernels" in str(m.message) for m in w)
+    ref = ScatteringNumPy1D(**kw)(x)
+    assert len(y) == len(ref)
+    for a, b in zip(y, ref):
+        assert a["n"] == b["n"] and tuple(a["coef"].shape) == b["coef"].shape
+        assert np.abs(a["coef"].cpu().numpy() - b["coef"]).max() <= 1e-4 * max(np.abs(b["coef"]).max(), 1e-12)

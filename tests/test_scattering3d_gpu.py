@@ -165,3 +165,16 @@ def test_fused3d_batch_shapes(plugin):
     assert ((y.reshape(flat.shape) - flat).abs() / flat.abs().clamp_min(1e-30)).max().item() < 1e-5   # float64 atomics
     one = S(x[0, 0])
     assert ((one - flat[0]).abs() / flat[0].abs().clamp_min(1e-30)).max().item() < 1e-5
+
+
+def test_c4_size_golden(plugin, golden_dir):
+    """BASELINE configs[3] at its own size against the committed reference-generated golden (input regenerated from
+    the seed, tests/golden/make_golden.py:golden_3d_c4)."""
+    from kymatio.torch import HarmonicScattering3D
+    d = np.load(os.path.join(golden_dir, "golden_3d_c4_J2_L2_128.npz"))
+    x = np.random.RandomState(int(d["seed"])).randn(1, 128, 128, 128).astype(np.float32)
+    assert np.array_equal(x.ravel()[:8], d["x_first8"])
+    S = HarmonicScattering3D(J=2, shape=(128, 128, 128), L=2, backend="torch_b200").cuda()
+    y = S(torch.from_numpy(x).cuda()).cpu().numpy().astype(np.float64)
+    assert y.shape == d["Sx64"].shape
+    assert (np.abs(y - d["Sx64"]) / np.abs(d["Sx64"])).max() < 1e-4
