@@ -68,6 +68,15 @@ __device__ __forceinline__ cx<float> fma_rc(cx<float> acc, cx<float> a, float c)
     return sb_upk(r);
 }
 #endif
+// element-wise acc + a * b on the (x, y) pair (one FFMA2 for float on sm_100+)
+template <typename T> SB_HD cx<T> fma_cc(cx<T> acc, cx<T> a, cx<T> b) { return mk<T>(acc.x + a.x * b.x, acc.y + a.y * b.y); }
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+__device__ __forceinline__ cx<float> fma_cc(cx<float> acc, cx<float> a, cx<float> b) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(sb_pk(a)), "l"(sb_pk(b)), "l"(sb_pk(acc)));
+    return sb_upk(r);
+}
+#endif
 template <typename T> SB_HD cx<T> cmul(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 template <typename T> SB_HD cx<T> cmulc(cx<T> a, cx<T> b) { return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
@@ -312,13 +321,13 @@ SB_HD void butterfly(cx<T>* line, int estride, int base, int q, int twstep, cons
 // the exponent are independent, so an inverse transform can run as DIF (natural-order input) and a
 // forward one as DIT (natural-order output).
 // the register part of butterfly_s: v[0..R) holds the group (natural order in for DIF, slot order in for DIT)
-template <int R, bool DIT, int SIGN, int Q, typename T>
+template <int R, bool DIT, int SIGN, int Q, typename T, bool TW = (Q > 1)>
 SB_HD void butterfly_v(cx<T>* v, int twstep, const cx<T>* tw) {
     constexpr bool P2 = ct_is_pow2(R);
     constexpr int LG = ct_log2(R);
     if (!DIT) {
         if constexpr (P2) dif_pow2<R, SIGN, T>(v); else dft_prime<R, SIGN, T>(v);
-        if constexpr (Q > 1) {
+        if constexpr (TW) {
             static_for<1, R>([&](auto k_) {
                 constexpr int k = decltype(k_)::value;
                 constexpr int f = P2 ? ct_bitrev(k, LG) : k;
@@ -326,7 +335,7 @@ SB_HD void butterfly_v(cx<T>* v, int twstep, const cx<T>* tw) {
             });
         }
     } else {
-        if constexpr (Q > 1) {
+        if constexpr (TW) {
             static_for<1, R>([&](auto k_) {
                 constexpr int k = decltype(k_)::value;
                 constexpr int f = P2 ? ct_bitrev(k, LG) : k;
@@ -337,20 +346,49 @@ SB_HD void butterfly_v(cx<T>* v, int twstep, const cx<T>* tw) {
     }
 }
 
-template <int R, bool DIT, int SIGN, int Q, int ES, bool MODULUS, typename T>
+// MODULUS: 0 store the outputs; 1 store (|v|, 0); 2 store (|v|, |v|) - the duplicated form lets a consumer that only needs
+// the real field fetch a ready-made packed operand pair for FFMA2 with one 64-bit load
+template <int R, bool DIT, int SIGN, int Q, int ES, int MODULUS, typename T, bool TW = (Q > 1)>
 SB_HD void butterfly_s(cx<T>* p0, int twstep, const cx<T>* tw) {
     cx<T> v[R];
     static_for<0, R>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
         v[k] = p0[k * Q * ES];
     });
-    butterfly_v<R, DIT, SIGN, Q, T>(v, twstep, tw);
+    butterfly_v<R, DIT, SIGN, Q, T, TW>(v, twstep, tw);
     static_for<0, R>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
-        if constexpr (MODULUS) p0[k * Q * ES] = mk<T>(cabs_fast<T>(v[k]), T(0));
+        if constexpr (MODULUS == 1) p0[k * Q * ES] = mk<T>(cabs_fast<T>(v[k]), T(0));
+        else if constexpr (MODULUS == 2) { const T m = cabs_fast<T>(v[k]); p0[k * Q * ES] = mk<T>(m, m); }
         else p0[k * Q * ES] = v[k];
     });
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Good-Thomas / prime-factor variant for N = N1 * N2, N1 = 2^a (one radix pass), N2 an odd prime (one pass): the two
+// factors are coprime, so with the index maps
+//     input   n  = (N2 n1 + N1 n2) mod N   stored at position  n1 N2 + n2          (pfa_in)
+//     output  k  : k1 = k mod N1, k2 = k mod N2   found at      slot(k1) N2 + k2    (pfa_out; slot = bit reversal)
+// W_N^{nk} = W_N1^{n1 k1} W_N2^{n2 k2}: a true two-dimensional DFT - the SAME two butterfly passes as the Cooley-Tukey
+// plan (same strides, same positions touched) but WITHOUT the N twiddle multiplications between them (a quarter of the
+// instructions of a 136- or 272-point transform).  The price is a permuted input order, which is free wherever a kernel
+// scatters its input into shared memory anyway (the product/periodise prologue of the tile kernels).
+// The transposed (DIT) flow takes pfa_out positions in and leaves natural index n at pfa_in(n).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr bool ct_pfa_ok(int n) {
+    const Plan1 P = ct_plan1(n);
+    return P.npass == 2 && ct_is_pow2(P.radix[0]) && P.radix[0] >= 2 && (P.radix[1] & 1) && P.radix[1] > 1 &&
+           P.radix[0] * P.radix[1] == n;
+}
+constexpr int ct_modinv(int a, int m) {          // a^-1 mod m (a, m coprime, small)
+    a %= m;
+    for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
+    return 0;
+}
+SB_HD int pfa_in(int n, int N1, int N2, int inv21, int inv12) {     // inv21 = N2^-1 mod N1, inv12 = N1^-1 mod N2
+    return ((n * inv21) % N1) * N2 + (n * inv12) % N2;
+}
+SB_HD int pfa_out(int k, int N1, int N2) { return rt_bitrev(k % N1, ct_log2(N1)) * N2 + k % N2; }
 
 constexpr bool ct_radix_compiled(int r) {
     return r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 11 || r == 13 || r == 16 || r == 17;

@@ -430,31 +430,39 @@ template <typename T, bool INV, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_r
 template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_colpass_imrf(ColArgs<T> a) {
     static_assert(NS > 0 && NS % 2 == 0, "static even sizes only");
     constexpr int n0 = NS, LP = kSLP, H = NS / 2;
+    // prime-factor transforms where the length allows (272 = 16 x 17): the rows are scattered to their prime-factor input
+    // positions while staging (free), both transforms run without twiddles between their two passes, and the natural
+    // output row v of the forward (DIT) transform is found at pin[v]   (fft_core.cuh)
+    constexpr bool PFA = ct_pfa_ok(NS);
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)n0 * LP;
+    int* pin = reinterpret_cast<int*>(tw + n0);
     const int g = blockIdx.x, c0 = blockIdx.y * kSLines;    // launch requires n1 % kSLines == 0
     stage(tw, a.tw, n0);
+    if constexpr (PFA) { stage(pin, a.pos, n0); __syncthreads(); }      // a.pos = prime-factor input table for PFA sizes
     const cx<T>* ib = a.in + (size_t)g * n0 * a.n1 + c0;
     cx<T>* ob = a.out + (size_t)g * n0 * a.n1 + c0;
     const int tid = flat_tid(), nt = flat_nt();
     for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
         const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
         const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)e * a.n1 + l);
-        s[e * LP + l] = v.a; s[e * LP + l + 1] = v.b;
+        const int se = PFA ? pin[e] : e;
+        s[se * LP + l] = v.a; s[se * LP + l + 1] = v.b;
     }
     __syncthreads();
-    slab_fft_s<NS, false, +1, 1, kSLP, T, true>(s, kSLines, tw);           // inverse + modulus -> (|u|, 0), rows scrambled
+    slab_fft_s<NS, false, +1, 1, kSLP, T, 1, PFA>(s, kSLines, tw);         // inverse + modulus -> (|u|, 0), rows scrambled
     // pack column pairs: (|u|_{2m}, |u|_{2m+1}) -> one complex column at lane 2m
     for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
         const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
         s[e * LP + l].y = s[e * LP + l + 1].x;
     }
     __syncthreads();
-    slab_fft_s<NS, true, -1, 2, kSLP, T>(s, kSLines / 2, tw);              // forward on the 8 packed columns
+    slab_fft_s<NS, true, -1, 2, kSLP, T, 0, PFA>(s, kSLines / 2, tw);      // forward on the 8 packed columns
     // untangle: A[v] = (Z[v] + conj Z[n-v]) / 2,  B[v] = (Z[v] - conj Z[n-v]) / (2i);  rows v = 0..n0/2
     for (int idx = tid; idx < (H + 1) * (kSLines / 2); idx += nt) {
         const int v = idx / (kSLines / 2), l = 2 * (idx - v * (kSLines / 2));
-        const cx<T> z = s[v * LP + l], zm = s[(v == 0 ? 0 : n0 - v) * LP + l];
+        const int vm = v == 0 ? 0 : n0 - v;
+        const cx<T> z = s[(PFA ? pin[v] : v) * LP + l], zm = s[(PFA ? pin[vm] : vm) * LP + l];
         cxpair<T> o;
         o.a = mk<T>(T(0.5) * (z.x + zm.x), T(0.5) * (z.y - zm.y));
         o.b = mk<T>(T(0.5) * (z.y + zm.y), T(0.5) * (zm.x - z.x));

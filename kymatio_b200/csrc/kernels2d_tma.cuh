@@ -50,12 +50,15 @@ __device__ __forceinline__ void slab_fft_rm(cx<T>* s, const int rows, const cx<T
 
 // ------------------------------------------------------------------------------------------------------------------
 // out[g][r][:] = inverse row transform (DIF: natural in, scrambled out) of parent[g / NF][r][:] * filt[g % NF][r][:] * scale
-// (no periodisation: parent and output have the same size NS x NS).  grid = one wave of persistent CTAs.
+// (no periodisation: parent and output have the same size NS x NS).
+// Slab-to-CTA map: a CTA owns ONE (filter, row block) pair for its whole life and walks over the images, so the 16
+// filter values of each thread's first-pass butterfly are loaded ONCE into registers - the steady-state loop touches
+// global memory only through the two bulk copies.  grid = NF * (NS/16) * m CTAs; CTA (pair, j) takes images j, j+m, ...
 // ------------------------------------------------------------------------------------------------------------------
 template <int NS>
-__global__ void __launch_bounds__(kTmaThreads, 3) k2d_rowprod_tma(RowProdArgs<float> a, int nslabs) {
+__global__ void __launch_bounds__(kTmaThreads, 2) k2d_rowprod_tma(RowProdArgs<float> a, int Bp, int m) {
     using T = float;
-    constexpr int ROWS = kTmaRows, SPP = NS / ROWS;            // slabs per path
+    constexpr int ROWS = kTmaRows, SPP = NS / ROWS;            // row blocks per field
     static_assert(NS % ROWS == 0, "line count must be a multiple of the slab height");
     constexpr uint32_t SLAB_BYTES = ROWS * NS * sizeof(cx<T>);
     unsigned char* base = dyn_smem<unsigned char>();
@@ -71,23 +74,26 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k2d_rowprod_tma(RowProdArgs<fl
     }
     for (int i = tid; i < NS; i += kTmaThreads) tw[i] = a.tw[i];
     __syncthreads();
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int n_my = first < nslabs ? (nslabs - first + stride - 1) / stride : 0;
+    const int npairs = a.NF * SPP;
+    const int pair = blockIdx.x % npairs, j = blockIdx.x / npairs;
+    const int fi = pair / SPP, r0 = (pair - fi * SPP) * ROWS;
+    const int n_my = j < Bp ? (Bp - j + m - 1) / m : 0;       // images j, j + m, ...
 
     if (tid >= kTmaComputeThreads) {
         // ---------------- producer warp: one lane issues every bulk copy of this CTA
         if (tid != kTmaComputeThreads) return;
         auto issue_load = [&](int i) {
-            const int t = first + i * stride, g = t / SPP, r0 = (t - g * SPP) * ROWS, b = i & 1;
-            const cx<T>* src = a.parent + ((size_t)(g / a.NF) * NS + r0) * NS;
+            const int b = i & 1;
+            const cx<T>* src = a.parent + ((size_t)(j + i * m) * NS + r0) * NS;
             tma::mbar_arrive_expect_tx(&full[b], SLAB_BYTES);
             tma::bulk_load(buf[b], src, SLAB_BYTES, &full[b]);
         };
         for (int i = 0; i < 2 && i < n_my; ++i) issue_load(i);
         for (int i = 0; i < n_my; ++i) {
-            const int t = first + i * stride, g = t / SPP, r0 = (t - g * SPP) * ROWS, b = i & 1;
+            const int b = i & 1;
+            const size_t g = (size_t)(j + i * m) * a.NF + fi;
             tma::mbar_wait(&done[b], (i >> 1) & 1);
-            tma::bulk_store(a.out + ((size_t)g * NS + r0) * NS, buf[b], SLAB_BYTES);
+            tma::bulk_store(a.out + (g * NS + r0) * NS, buf[b], SLAB_BYTES);
             tma::bulk_commit();
             if (i + 2 < n_my) { tma::bulk_wait_read<0>(); issue_load(i + 2); }
         }
@@ -96,37 +102,25 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k2d_rowprod_tma(RowProdArgs<fl
     }
     // ---------------- compute warps
     constexpr int R0 = ct_plan1(NS).radix[0], Q0 = NS / R0;
+    static_assert(Q0 * ROWS <= kTmaComputeThreads, "one first-pass butterfly per compute thread");
+    const T* __restrict__ fb = a.filt[fi];
+    const int row = min(tid / Q0, ROWS - 1), e = tid - (tid / Q0) * Q0;
+    T f0[R0];                                                   // this thread's filter values, resident for every image
+    {
+        const T* __restrict__ frow = fb + (size_t)(r0 + row) * NS + e;
+        static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; f0[k] = __ldg(frow + k * Q0) * a.scale; });
+    }
     for (int i = 0; i < n_my; ++i) {
-        const int t = first + i * stride, g = t / SPP, r0 = (t - g * SPP) * ROWS, b = i & 1;
-        const T* __restrict__ fb = a.filt[g % a.NF];
+        const int b = i & 1;
         cx<T>* s = buf[b];
-        // first radix pass with the filter multiply folded into its loads; the filter values of this thread's first
-        // butterfly are fetched BEFORE waiting for the slab (they do not depend on it)
-        T f0[R0];
-        {
-            const int row = min(tid / Q0, ROWS - 1), e = tid - (tid / Q0) * Q0;
-            const T* __restrict__ frow = fb + (size_t)(r0 + row) * NS + e;
-            static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; f0[k] = __ldg(frow + k * Q0) * a.scale; });
-        }
         tma::mbar_wait(&full[b], (i >> 1) & 1);
-        for (int it = tid; it < Q0 * ROWS; it += kTmaComputeThreads) {
-            const int row = it / Q0, e = it - row * Q0;
+        // first radix pass with the filter multiply folded into its loads
+        if (tid < Q0 * ROWS) {
             cx<T>* p0 = s + row * NS + e;
             cx<T> v[R0];
-            if (it == tid) {
-                static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; v[k] = scal(p0[k * Q0], f0[k]); });
-            } else {
-                const T* __restrict__ frow = fb + (size_t)(r0 + row) * NS + e;
-                static_for<0, R0>([&](auto k_) {
-                    constexpr int k = decltype(k_)::value;
-                    v[k] = scal(p0[k * Q0], __ldg(frow + k * Q0) * a.scale);
-                });
-            }
+            static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; v[k] = scal(p0[k * Q0], f0[k]); });
             butterfly_v<R0, false, +1, Q0, T>(v, e, tw);
-            static_for<0, R0>([&](auto k_) {
-                constexpr int k = decltype(k_)::value;
-                p0[k * Q0] = v[k];
-            });
+            static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; p0[k * Q0] = v[k]; });
         }
         tma::named_sync<1>(kTmaComputeThreads);
         slab_fft_rm<NS, false, +1, 1, T>(s, ROWS, tw, tid);
@@ -237,7 +231,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3) k2d_rowfwdh_tma(RowArgs<float>
 }
 
 // lookup / opt-in (instances in tma_inst.cu); null when there is no instance for the line length
-using RowProdTmaKernel = void (*)(RowProdArgs<float>, int);
+using RowProdTmaKernel = void (*)(RowProdArgs<float>, int, int);
 using RowFwdhTmaKernel = void (*)(RowArgs<float>, int);
 RowProdTmaKernel rowprod_tma_lookup(int n);
 RowFwdhTmaKernel rowfwdh_tma_lookup(int n);

@@ -41,6 +41,7 @@ struct Axis {
     int n = 0;
     Plan1 plan{};
     size_t tw_off = 0, pos_off = 0;   // byte offsets into the constant buffer
+    size_t pin_off = 0, ppos_off = 0; // prime-factor input / output position tables (plan_host.h: pfa_tables)
 };
 struct Level2D { Axis a0, a1; };
 
@@ -108,6 +109,8 @@ public:
                 ax[a]->plan = make_plan1(nn[a]);
                 ax[a]->tw_off = take((size_t)nn[a] * sizeof(cx<T>));
                 ax[a]->pos_off = take((size_t)nn[a] * sizeof(int));
+                ax[a]->pin_off = take((size_t)nn[a] * sizeof(int));
+                ax[a]->ppos_off = take((size_t)nn[a] * sizeof(int));
             }
         }
         tables_bytes_ = off;
@@ -119,6 +122,10 @@ public:
                 auto pos = scramble_table(ax[a]->plan);
                 std::memcpy(host_const_.data() + ax[a]->tw_off, tw.data(), (size_t)ax[a]->n * sizeof(cx<T>));
                 std::memcpy(host_const_.data() + ax[a]->pos_off, pos.data(), (size_t)ax[a]->n * sizeof(int));
+                std::vector<int> pin, ppos;
+                pfa_tables(ax[a]->n, pin, ppos);
+                std::memcpy(host_const_.data() + ax[a]->pin_off, pin.data(), (size_t)ax[a]->n * sizeof(int));
+                std::memcpy(host_const_.data() + ax[a]->ppos_off, ppos.data(), (size_t)ax[a]->n * sizeof(int));
             }
         }
         // filter-derived tables (filled by bind): pointer arrays, supports, FIR taps
@@ -162,6 +169,7 @@ public:
             stream_kernels_enable_smem<T>();
             enable_big_smem(k2d_lowpass<T>);
             tile_kernels_enable_smem<T>();
+            tile_spec_kernels_enable_smem<T>();
             tile2h_kernels_enable_smem<T>();
         });
         once_per_device("tma_rows", [] { tma_kernels_enable_smem(); });
@@ -415,9 +423,10 @@ private:
             // TMA-fed persistent variant (kernels2d_tma.cuh): same-size product (no aliases), square static line length
             if (use_tma_ && a.k == 1 && chain_static(out_res) && a.n0 == a.n1 && a.n0 % kTmaRows == 0) {
                 if (RowProdTmaKernel kt = rowprod_tma_lookup(a.n1)) {
-                    const int nslabs = Bp * NF * (a.n0 / kTmaRows);
-                    const int grid_t = std::max(1, std::min(nslabs, tma_ctas_per_sm_ * num_sms_));
-                    launch(label, bytes, st, [&] { kt<<<(unsigned)grid_t, kTmaThreads, tma_row_smem(a.n1), st>>>(a, nslabs); });
+                    // a CTA owns one (filter, 16-row block) pair and walks over the images: m CTAs per pair
+                    const int npairs = NF * (a.n0 / kTmaRows);
+                    const int m = std::max(1, std::min(Bp, (2 * num_sms_) / npairs));
+                    launch(label, bytes, st, [&] { kt<<<(unsigned)(npairs * m), kTmaThreads, tma_row_smem(a.n1), st>>>(a, Bp, m); });
                     return;
                 }
             }
@@ -467,6 +476,8 @@ private:
             a.in = data; a.out = data; a.n0 = n0; a.n1 = n1;
             const SlabCfg& c = col_cfg_[res];
             a.lines = c.lines; a.LP = c.LP; a.plan = lev_[res].a0.plan; a.tw = tw(lev_[res].a0); a.pos = pos(lev_[res].a0);
+            // prime-factor lengths: the kernel wants the prime-factor INPUT position table (kernels2d.cuh)
+            if (pfa_ok(n0)) a.pos = reinterpret_cast<const int*>(cbuf_ + lev_[res].a0.pin_off);
             dim3 grid((unsigned)G, n1 / kSLines);
             launch("colpass_inv_mod_rfwd:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
                    1.5 * G * n0 * n1 * sizeof(cx<T>), st,
@@ -591,14 +602,29 @@ private:
                 }
             }
         }
-        const size_t smem = tile_smem_layout<T>(a, nullptr);
         bool is_static = false;
         TileKernel<T> kern = gparent ? tile_bwd_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static)
                                      : tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
+        if (!gparent && spec_out && is_static)          // static instances with the forward transform compiled in
+            if (TileKernel<T> ks = tile_spec_kernel_lookup<T>(a.n0, a.n1, a.k)) kern = ks;
+        // CUDA-core low-pass of the static forward instances reads the taps from the [cnt][4] tables
+        a.tt = (!gparent && is_static && (a.k == 2 || a.k == 4) && !a.use_mma && (a.o0p >> 2) * a.o1p <= 256) ? 1 : 0;
+        a.TT0 = reinterpret_cast<const T*>(cbuf_ + F.TT0_off);
+        a.TT1 = reinterpret_cast<const T*>(cbuf_ + F.TT1_off);
+        // forward static instances of prime-factor sizes (136, 68, ...: tile_pfa) take the prime-factor position tables
+        if (!gparent && is_static && (a.k == 2 || a.k == 4) && tile_pfa(a.n0, a.n1)) {
+            a.pin0 = reinterpret_cast<const int*>(cbuf_ + lev_[res].a0.pin_off);
+            a.pin1 = reinterpret_cast<const int*>(cbuf_ + lev_[res].a1.pin_off);
+            a.pos0 = reinterpret_cast<const int*>(cbuf_ + lev_[res].a0.ppos_off);
+            a.pos1 = reinterpret_cast<const int*>(cbuf_ + lev_[res].a1.ppos_off);
+        }
+        const size_t smem = tile_smem_layout<T>(a, nullptr);
         // threads: every butterfly pass distributes (lines x butterflies) work items over the CTA in rounds;
         // pick the warp count that wastes the fewest (cost-weighted) partially filled rounds
         const int cap = std::min(tile_threads_cap_, is_static ? tile_max_threads(a.n0, a.n1) : tile_max_threads(0, 0));
-        const int lo = (2 * smem > kMaxDynSmem) ? std::max(64, cap / 2) : std::max(64, cap / 3);
+        int lo = (2 * smem > kMaxDynSmem) ? std::max(64, cap / 2) : std::max(64, cap / 3);
+        // the tap-table low-pass gives every (4 output rows, 1 output column) item its own thread
+        if (a.tt) lo = std::min(cap / 32 * 32, std::max(lo, ((a.o0p >> 2) * a.o1p + 31) / 32 * 32));
         auto pass_cost = [](int r) { return r >= 16 ? 30.0 * r : r >= 8 ? 15.0 * r : 12.0 * r; };
         int threads = cap / 32 * 32;
         double best = 1e300;

@@ -42,6 +42,23 @@ inline std::vector<int> scramble_table(const Plan1& P) {
     return pos;
 }
 
+// prime-factor tables (fft_core.cuh): pin[n] = position of natural INPUT index n of the DIF flow (= where the DIT flow
+// leaves natural output n), pout[k] = position of natural OUTPUT index k of the DIF flow (= DIT input).  Identity /
+// scramble_table for lengths without a prime-factor plan.
+inline bool pfa_ok(int n) { return n >= 2 && ct_pfa_ok(n); }
+inline void pfa_tables(int n, std::vector<int>& pin, std::vector<int>& pout) {
+    pin.resize(n); pout.resize(n);
+    const Plan1 P = ct_plan1(n);
+    if (!pfa_ok(n)) {
+        const std::vector<int> pos = scramble_table(P);
+        for (int i = 0; i < n; ++i) { pin[i] = i; pout[i] = pos[i]; }
+        return;
+    }
+    const int N1 = P.radix[0], N2 = P.radix[1];
+    const int inv21 = ct_modinv(N2, N1), inv12 = ct_modinv(N1, N2);
+    for (int i = 0; i < n; ++i) { pin[i] = pfa_in(i, N1, N2, inv21, inv12); pout[i] = pfa_out(i, N1, N2); }
+}
+
 // tw[j] = exp(-2*pi*i*j/n)
 template <typename T> inline std::vector<cx<T>> twiddle_table(int n) {
     std::vector<cx<T>> tw(n > 0 ? n : 1);

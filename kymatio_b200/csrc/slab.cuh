@@ -40,10 +40,12 @@ __device__ __noinline__ void slab_fft(cx<T>* s, int lines, int lstride, int estr
 // pass loop is fully unrolled and every butterfly access is base + immediate offset.
 //   DIT = false: decimation in frequency, natural -> scrambled;  DIT = true: scrambled -> natural
 //   SIGN = -1 forward, +1 inverse (unnormalised)
-// MODULUS = true replaces every output of the LAST pass by (|v|, 0) while it is still in registers.
-template <int N, bool DIT, int SIGN, int LS, int ES, typename T, bool MODULUS = false>
+// MODULUS = 1 (2) replaces every output of the LAST pass by (|v|, 0) ((|v|, |v|)) while it is still in registers.
+// PFA = true runs the prime-factor variant (fft_core.cuh: no twiddles between the two passes; positions pfa_in/pfa_out).
+template <int N, bool DIT, int SIGN, int LS, int ES, typename T, int MODULUS = 0, bool PFA = false>
 __device__ __forceinline__ void slab_fft_s(cx<T>* s, const int lines, const cx<T>* tw) {
     constexpr int NP = ct_plan1(N).npass;
+    static_assert(!PFA || ct_pfa_ok(N), "prime-factor variant needs N = 2^a * odd prime with one pass each");
     const int tid = flat_tid(), nt = flat_nt();
     static_for<0, NP>([&](auto pp_) {
         constexpr int pp = decltype(pp_)::value;
@@ -54,7 +56,7 @@ __device__ __forceinline__ void slab_fft_s(cx<T>* s, const int lines, const cx<T
         for (int it = tid; it < items; it += nt) {
             const int bf = it / lines, line = it - bf * lines;
             const int blk = bf / q, i = bf - blk * q;
-            butterfly_s<r, DIT, SIGN, q, ES, (MODULUS && pp == NP - 1), T>(s + line * LS + (blk * m + i) * ES, i * tws, tw);
+            butterfly_s<r, DIT, SIGN, q, ES, (pp == NP - 1 ? MODULUS : 0), T, (q > 1 && !PFA)>(s + line * LS + (blk * m + i) * ES, i * tws, tw);
         }
         __syncthreads();
     });

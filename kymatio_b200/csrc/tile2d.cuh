@@ -47,12 +47,17 @@ template <typename T> struct TileArgs {
     int P0, P1, k, n0, n1, W, NF;
     T scale;
     Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
+    // prime-factor forward instances (fft_core.cuh): input positions of the natural Fourier indices; pos0/pos1 then hold
+    // the matching prime-factor output positions
+    const int* pin0; const int* pin1;
     const T* G0; const T* G1;              // [n0][o0p], [n1][o1p] dense low-pass + decimation + unpad matrices
     int y0lo, y0cnt, x1lo, x1cnt;          // input window (start offset rel. to kl*(4*group+1), length) per 4-output group
     int kl, o0, o1, o0p, o1p;              // o?p = o? rounded up to a multiple of 4
     int PP, NFch, ch0, chs, K;
     int G;                                 // number of paths; CTAs are persistent and stride over them
     int use_mma;                           // 1: dense low-pass products on the tensor cores (3xTF32 mma.sync)
+    int tt;                                // 1: static forward, CUDA-core low-pass from the [cnt][4] tap tables TT0/TT1
+                                           //    (shift invariance, see tile2h.cuh) instead of the dense G0/G1 matrices
     int prefetch;                          // 1: bulk L2 prefetch of the next path's parent spectrum (kernels2d.cuh)
     int stagger_ns;                        // > 0: CTA i starts (i % 4) * stagger_ns late, so that the L2-bound load phases
                                            // of the persistent CTAs do not all coincide
@@ -66,6 +71,7 @@ template <typename T> struct TileArgs {
 
 template <typename T> struct TileSmem {
     cx<T>* tile; cx<T>* tw0; cx<T>* tw1; unsigned* supp; T* w1; T* G0; T* G1; int* pos0; int* pos1; T* gs; int2* xr;
+    int* pin0; int* pin1; T* pb;
 };
 template <typename T> __host__ __device__ inline size_t tile_smem_layout(const TileArgs<T>& a, TileSmem<T>* L) {
     size_t off = 0;
@@ -73,15 +79,18 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     const size_t o_tile = take(sizeof(cx<T>) * (size_t)a.n0 * a.W);
     const size_t o_tw0 = take(sizeof(cx<T>) * a.n0), o_tw1 = take(sizeof(cx<T>) * a.n1);
     const size_t o_supp = take(sizeof(unsigned) * 2 * a.P0);  // packed (start | len << 16), double buffered: the next path's rows are staged early
-    // pitches: +4 (CUDA-core path, 16-byte rows) or +8 (mma path, conflict-free fragment loads); K padded to 8
-    const size_t o_w1 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o1p + 8));
-    const size_t o_g0 = take(sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
-    const size_t o_g1 = take(sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
+    // pitches: +4 (CUDA-core path, 16-byte rows) or +8 (mma path, conflict-free fragment loads); K padded to 8.
+    // tt mode: two w1 halves (the x window is split over two work items) and the tap tables in place of G0/G1
+    const size_t o_w1 = take(a.tt ? sizeof(T) * 2 * (size_t)a.n0 * (a.o1p + 4) : sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o1p + 8));
+    const size_t o_g0 = take(a.tt ? sizeof(T) * 4 * (size_t)a.y0cnt : sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
+    const size_t o_g1 = take(a.tt ? sizeof(T) * 4 * (size_t)a.x1cnt : sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
     const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
     // backward only (the forward kernel must not pay for them: 68 x 68 tiles fit three per SM without)
     const bool bwd = a.gparent != nullptr;
     const size_t o_gs = take(bwd ? sizeof(T) * (size_t)a.o0p * a.o1p : 0);   // staged output-plane gradient
     const size_t o_xr = take(bwd ? sizeof(int2) * (size_t)a.n1 : 0);         // nonzero output range of each G1 row
+    const size_t o_i0 = take(a.pin0 ? sizeof(int) * a.n0 : 0), o_i1 = take(a.pin0 ? sizeof(int) * a.n1 : 0);
+    const size_t o_pb = take(a.tt ? sizeof(T) * (size_t)a.o0p * a.o1p : 0);    // 4b partial sums of the second half window
     if (L) {
 #ifdef __CUDA_ARCH__
         unsigned char* base = dyn_smem<unsigned char>();
@@ -93,6 +102,8 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
         L->pos0 = reinterpret_cast<int*>(base + o_p0); L->pos1 = reinterpret_cast<int*>(base + o_p1);
         L->gs = reinterpret_cast<T*>(base + o_gs);
         L->xr = reinterpret_cast<int2*>(base + o_xr);
+        L->pin0 = reinterpret_cast<int*>(base + o_i0); L->pin1 = reinterpret_cast<int*>(base + o_i1);
+        L->pb = reinterpret_cast<T*>(base + o_pb);
 #endif
     }
     return off;
@@ -113,6 +124,8 @@ __device__ __forceinline__ double fast_abs(double x, double y) { return sqrt(x *
 // threads per CTA / CTAs per SM the instances are compiled for: a field that fills more than half of
 // the SM's shared memory runs alone with up to 640 threads (<= 102 registers); smaller fields share
 // the SM three at a time with up to 320 threads each (<= 68 registers).
+// forward static instances of the 272-padded sizes run prime-factor transforms (fft_core.cuh)
+__host__ __device__ constexpr bool tile_pfa(int n0, int n1) { return n0 > 0 && n0 == n1 && ct_pfa_ok(n0 > 0 ? n0 : 2); }
 __host__ __device__ constexpr bool tile_is_big(int n0, int n1) { return n0 == 0 || (long long)n0 * n1 > 10000; }
 __host__ __device__ constexpr int tile_max_threads(int n0, int n1) { return tile_is_big(n0, n1) ? 640 : 320; }
 __host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_is_big(n0, n1) ? 1 : 3; }
@@ -120,9 +133,10 @@ __host__ __device__ constexpr int tile_min_blocks(int n0, int n1) { return tile_
 // Static instances (alias count KT and field size known at compile time, parent = KT*N0 x KT*N1): product + periodise of
 // the 4 adjacent columns e..e+3 of output row r.  One base address per operand, every alias at an immediate offset; the
 // loads of an alias outside the filter's support are predicated off (zero-filled).
-template <typename T, int N0, int N1, int KT>
+template <typename T, int N0, int N1, int KT, bool PFA>
 __device__ __forceinline__ void tile_load_item_s(cx<T>* s, const unsigned* supp, const cx<T>* __restrict__ pb,
-                                                 const T* __restrict__ fb, int r, int e, T scale, int lane) {
+                                                 const T* __restrict__ fb, int r, int e, T scale, int lane,
+                                                 const int* pin0, const int* pin1) {
     constexpr int P1 = N1 * KT, W = N1 | 1;
     T ax[4], ay[4];
 #pragma unroll
@@ -152,6 +166,15 @@ __device__ __forceinline__ void tile_load_item_s(cx<T>* s, const unsigned* supp,
             ax[2] += v1[d].a.x * f[d].c; ay[2] += v1[d].a.y * f[d].c;
             ax[3] += v1[d].b.x * f[d].d; ay[3] += v1[d].b.y * f[d].d;
         }
+    }
+    if constexpr (PFA) {
+        // prime-factor input order: Fourier bin (r, e + i) goes to position (pin0[r], pin1[e + i]); the four targets of a
+        // thread are scattered, which also spreads the banks - no store rotation needed
+        cx<T>* row = s + pin0[r] * W;
+        const int4 pc = *reinterpret_cast<const int4*>(pin1 + e);
+        row[pc.x] = mk<T>(ax[0] * scale, ay[0] * scale); row[pc.y] = mk<T>(ax[1] * scale, ay[1] * scale);
+        row[pc.z] = mk<T>(ax[2] * scale, ay[2] * scale); row[pc.w] = mk<T>(ax[3] * scale, ay[3] * scale);
+        return;
     }
     cx<T>* dst = s + r * W + e;
     // rotate which of its 4 columns a lane writes in each of the 4 store instructions by (lane>>2)&3:
@@ -307,9 +330,15 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float*
     }
 }
 
-template <typename T, int N0, int N1, int KT>
+// SPEC (static instances): the path has children - the modulus is stored as (|u|, 0) and the forward transform + spectrum
+// store are compiled in; leaf instances (SPEC = false) store (|u|, |u|) (packed FFMA2 operand of the low-pass) and contain
+// no forward transform.  The generic instance decides at run time (a.spec_out).
+template <typename T, int N0, int N1, int KT, bool SPEC>
 __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     constexpr bool ST = N0 > 0;
+    // prime-factor transforms (no twiddles between the 2^a and the 17 pass) for the 272-padded sizes; the host passes the
+    // matching position tables (plan2d.cuh: tile())
+    constexpr bool PFA = ST && KT > 0 && tile_pfa(N0, N1);
     const int n0 = ST ? N0 : a.n0, n1 = ST ? N1 : a.n1;
     const int W = ST ? (N1 | 1) : a.W;
     const int k = KT > 0 ? KT : a.k;
@@ -323,6 +352,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     // constants shared by every path this (persistent) CTA processes
     stage(m.tw0, a.tw0, n0); stage(m.tw1, a.tw1, n1);
     stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
+    if constexpr (PFA) { stage(m.pin0, a.pin0, n0); stage(m.pin1, a.pin1, n1); }
     const bool mma = ST && std::is_same<T, float>::value && a.use_mma;
     const int gp0 = a.o0p + 8, gp1 = a.o1p + 8;      // mma-path pitches of G0s / G1s (and of w1)
     if (mma) {
@@ -335,6 +365,9 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
         __syncthreads();
         for (int i = tid; i < n0 * a.o0p; i += nt) { const int y = i / a.o0p, o = i - y * a.o0p; m.G0[m.pos0[y] * gp0 + o] = a.G0[i]; }
         for (int i = tid; i < n1 * a.o1p; i += nt) { const int x = i / a.o1p, o = i - x * a.o1p; m.G1[m.pos1[x] * gp1 + o] = a.G1[i]; }
+    } else if (ST && a.tt) {
+        stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.TT0), a.y0cnt);
+        stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.TT1), a.x1cnt);
     } else {
         stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
         stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
@@ -371,7 +404,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 constexpr int per_row = N1 >> 2, items = N0 * per_row;
                 for (int it = tid; it < items; it += nt) {
                     const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
-                    tile_load_item_s<T, N0, N1, KT>(s, supp, pb, fb, r0, e0, a.scale, lane);
+                    tile_load_item_s<T, N0, N1, KT, PFA>(s, supp, pb, fb, r0, e0, a.scale, lane, m.pin0, m.pin1);
                 }
             } else if ((n1 & 3) == 0 && (P1 & 3) == 0) {
                 const int per_row = n1 >> 2, items = n0 * per_row;
@@ -394,9 +427,9 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
         //            the spatial field stays scrambled: U[y][x] lives at s[pos0[y]*W + pos1[x]]
         //   generic: DIT (scattered input -> natural spatial), separate modulus sweep
         if constexpr (ST) {
-            slab_fft_s<N1, false, +1, (N1 | 1), 1, T>(s, N0, m.tw1);
+            slab_fft_s<N1, false, +1, (N1 | 1), 1, T, false, PFA>(s, N0, m.tw1);
             SB_PHASE(2);
-            slab_fft_s<N0, false, +1, 1, (N1 | 1), T, true>(s, N1, m.tw0);
+            slab_fft_s<N0, false, +1, 1, (N1 | 1), T, (SPEC ? 1 : 2), PFA>(s, N1, m.tw0);
             SB_PHASE(3);
         } else {
             slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
@@ -451,7 +484,106 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             }
           }
         }
-        if (!mma) {
+        bool lowpass_done = mma;
+        if constexpr (ST) {
+          if (!mma && a.tt) {
+            lowpass_done = true;
+            // 4a (tap tables). w1[h][row][xo] = sum over half h of the x window of U[row][x] * g1[kl (xo+1) - x]:
+            //   4 storage rows x 4 outputs per work item, the window split in two so that every thread has an item;
+            //   leaf instances fetch (|u|, |u|) with one 64-bit load and issue two FFMA2 per row and tap
+            {
+                constexpr int rgroups = (N0 + 3) >> 2;
+                const int xgroups = a.o1p >> 2, half_items = rgroups * xgroups;
+                const int h0 = (a.x1cnt + 1) >> 1;
+                for (int it = tid; it < 2 * half_items; it += nt) {
+                    const int hf = it >= half_items ? 1 : 0;
+                    const int rem = it - hf * half_items;
+                    const int xg = rem / rgroups, rg = rem - xg * rgroups;
+                    int yy[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) yy[j] = min(rg + j * rgroups, N0 - 1) * W;
+                    const int st0 = hf ? h0 : 0, st1 = hf ? a.x1cnt : h0;
+                    int x = (a.kl * (4 * xg + 1) + a.x1lo + st0) % N1;
+                    if (x < 0) x += N1;
+                    cx<T> acc01[4], acc23[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { acc01[j] = mk<T>(T(0), T(0)); acc23[j] = mk<T>(T(0), T(0)); }
+#pragma unroll 4
+                    for (int st = st0; st < st1; ++st) {
+                        const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G1 + 4 * st);
+                        const cx<T> g01 = mk<T>(gq.a, gq.b), g23 = mk<T>(gq.c, gq.d);
+                        const int xs = m.pos1[x];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            cx<T> uu = s[yy[j] + xs];
+                            if constexpr (SPEC) uu.y = uu.x;
+                            acc01[j] = fma_cc(acc01[j], uu, g01);
+                            acc23[j] = fma_cc(acc23[j], uu, g23);
+                        }
+                        x = (x + 1 == N1) ? 0 : x + 1;
+                    }
+                    T* w1h = m.w1 + hf * N0 * wp;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int y = rg + j * rgroups;
+                        if (y < N0) {
+                            re4<T> o; o.a = acc01[j].x; o.b = acc01[j].y; o.c = acc23[j].x; o.d = acc23[j].y;
+                            *reinterpret_cast<re4<T>*>(w1h + y * wp + 4 * xg) = o;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            SB_PHASE(4);
+            // 4b (tap tables). S[yo][xo] = sum_y g0[kl (yo+1) - y] * (w1[0] + w1[1])[row(y)][xo]; the y window is split in two
+            //   work items as well: the second half leaves its partial sums in shared memory, the first adds them and stores
+            {
+                T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+                const int ygroups = a.o0p >> 2, nitem = ygroups * a.o1p;
+                const T* w1b = m.w1 + N0 * wp;
+                const int g0 = (a.y0cnt + 1) >> 1;
+                T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+                const bool two = 2 * nitem <= nt;                 // enough threads for both halves at once
+                const int hf = (two && tid >= nitem) ? 1 : 0;
+                const int it = tid - hf * nitem;
+                const bool active = it < nitem;
+                const int yg = active ? it / a.o1p : 0, xo = active ? it - yg * a.o1p : 0;
+                if (active) {
+                    const int st0 = two ? (hf ? g0 : 0) : 0, st1 = two ? (hf ? a.y0cnt : g0) : a.y0cnt;
+                    int y = (a.kl * (4 * yg + 1) + a.y0lo + st0) % N0;
+                    if (y < 0) y += N0;
+#pragma unroll 4
+                    for (int st = st0; st < st1; ++st) {
+                        const re4<T> gq = *reinterpret_cast<const re4<T>*>(m.G0 + 4 * st);
+                        const int ys = m.pos0[y] * wp + xo;
+                        const T w = m.w1[ys] + w1b[ys];
+                        acc0 += w * gq.a; acc1 += w * gq.b; acc2 += w * gq.c; acc3 += w * gq.d;
+                        y = (y + 1 == N0) ? 0 : y + 1;
+                    }
+                    if (hf) {
+                        re4<T> o; o.a = acc0; o.b = acc1; o.c = acc2; o.d = acc3;
+                        *reinterpret_cast<re4<T>*>(m.pb + 4 * it) = o;
+                    }
+                }
+                if (two) __syncthreads();
+                if (active && !hf) {
+                    if (two) {
+                        const re4<T> o = *reinterpret_cast<const re4<T>*>(m.pb + 4 * it);
+                        acc0 += o.a; acc1 += o.b; acc2 += o.c; acc3 += o.d;
+                    }
+                    if (xo < a.o1) {
+                        const int yo = 4 * yg;
+                        if (yo + 0 < a.o0) ob[(yo + 0) * a.o1 + xo] = acc0;
+                        if (yo + 1 < a.o0) ob[(yo + 1) * a.o1 + xo] = acc1;
+                        if (yo + 2 < a.o0) ob[(yo + 2) * a.o1 + xo] = acc2;
+                        if (yo + 3 < a.o0) ob[(yo + 3) * a.o1 + xo] = acc3;
+                    }
+                }
+                // (requires nitem <= nt: checked by the host, which otherwise leaves tt off)
+            }
+          }
+        }
+        if (!lowpass_done) {
         // 4a. horizontal low-pass + decimation + unpad: w1[row][xo] = sum_x U[row][x] * G1[x][xo]
         //     register tile: 4 (storage) rows x 4 outputs per thread, x restricted to the group's input window
         {
@@ -516,19 +648,25 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
                 }
             }
         }
-        }   // !mma
+        }   // dense CUDA-core low-pass
         SB_PHASE(5);
         // 5. forward 2-D FFT of U for the children of this path, natural-order store
         //    (static: DIT, scrambled spatial in -> natural Fourier out; generic: DIF + gather)
-        if (a.spec_out) {
+        if ((!ST || SPEC) && a.spec_out) {
             cx<T>* ob = a.spec_out + (size_t)g * n0 * n1;
             if constexpr (ST) {
-                slab_fft_s<N0, true, -1, 1, (N1 | 1), T>(s, N1, m.tw0);
-                slab_fft_s<N1, true, -1, (N1 | 1), 1, T>(s, N0, m.tw1);
+                slab_fft_s<N0, true, -1, 1, (N1 | 1), T, false, PFA>(s, N1, m.tw0);
+                slab_fft_s<N1, true, -1, (N1 | 1), 1, T, false, PFA>(s, N0, m.tw1);
                 constexpr int half = N1 / 2;
                 for (int it = tid; it < N0 * half; it += nt) {
                     const int r = it / half, e = 2 * (it - r * half);
-                    cx2<T> v; v.a = s[r * W + e]; v.b = s[r * W + e + 1];
+                    cx2<T> v;
+                    if constexpr (PFA) {      // natural bin (r, e) sits at the prime-factor input position
+                        const cx<T>* row = s + m.pin0[r] * W;
+                        v.a = row[m.pin1[e]]; v.b = row[m.pin1[e + 1]];
+                    } else {
+                        v.a = s[r * W + e]; v.b = s[r * W + e + 1];
+                    }
                     *reinterpret_cast<cx2<T>*>(ob + (size_t)r * N1 + e) = v;
                 }
             } else {
@@ -545,9 +683,9 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     }
 }
 
-template <typename T, int N0, int N1, int KT>
+template <typename T, int N0, int N1, int KT, bool SPEC = false>
 __global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, N1)) k2d_tile(TileArgs<T> a) {
-    tile_body<T, N0, N1, KT>(a);
+    tile_body<T, N0, N1, KT, SPEC>(a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -692,6 +830,8 @@ __global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, 
 // generic one
 template <typename T> using TileKernel = void (*)(TileArgs<T>);
 template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bool* is_static);
+template <typename T> TileKernel<T> tile_spec_kernel_lookup(int n0, int n1, int k);     // static instances with children
+template <typename T> void tile_spec_kernels_enable_smem();
 template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k, bool* is_static);
 template <typename T> void tile_kernels_enable_smem();
 int phase_prof_read(unsigned long long* out, int max_n, bool reset);

@@ -15,13 +15,13 @@ template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bo
         if (n0 == N) {                                       \
             if (k == 2) return k2d_tile<T, N, N, 2>;         \
             if (k == 4) return k2d_tile<T, N, N, 4>;         \
-            return k2d_tile<T, N, N, 0>;                     \
+            return k2d_tile<T, N, N, 0, true>;               \
         }
         SB_TILE_SIZES(SB_CASE)
 #undef SB_CASE
     }
     if (is_static) *is_static = false;
-    return k2d_tile<T, 0, 0, 0>;
+    return k2d_tile<T, 0, 0, 0, true>;
 }
 
 // backward instances: the generic alias-count version (K = 0) per static size keeps compile time in check
@@ -38,10 +38,10 @@ template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k
 
 template <typename T> void tile_kernels_enable_smem() {
 #define SB_EN(N) enable_big_smem(k2d_tile<T, N, N, 2>); enable_big_smem(k2d_tile<T, N, N, 4>); \
-                 enable_big_smem(k2d_tile<T, N, N, 0>);
+                 enable_big_smem(k2d_tile<T, N, N, 0, true>);
     SB_TILE_SIZES(SB_EN)
 #undef SB_EN
-    enable_big_smem(k2d_tile<T, 0, 0, 0>);
+    enable_big_smem(k2d_tile<T, 0, 0, 0, true>);
 #define SB_ENB(N) enable_big_smem(k2d_tile_bwd<T, N, N, 0>); enable_big_smem(k2d_tile_bwd<T, N, N, 2>);
     SB_TILE_SIZES(SB_ENB)
 #undef SB_ENB

@@ -206,6 +206,12 @@ class _Primitives2D:
             _lib.check(_lib.load().scat_real_part(y.data_ptr(), out.data_ptr(), out.numel(), _dtype_code(x), _stream(x)))
         return out
 
+
+
+class _Layout2D:
+    """The two pure-layout members of the 2-D protocol (kept out of _Primitives2D, which the 1-D / 3-D backends also
+    build on: their unpad / stack come from the reference's TorchBackend1D / from _Primitives3D)."""
+
     @staticmethod
     def unpad(in_):
         # kymatio/scattering2d/backend/torch_backend.py:158-176
@@ -560,6 +566,8 @@ def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
     B = S.shape[0]
     for kind, n1, n2, ch in eng.order:
         coef = S[:, ch].reshape(B, 1, eng.M, 1)
+        if glob:
+            coef = coef.contiguous()          # backend.average_global checks contiguity (a (B, 1, 1, 1) scalar per signal)
         if kind == "S0":
             yield {"coef": coef, "j": (), "n": ()}
         elif kind == "S1":
@@ -643,7 +651,7 @@ def _compose_backends():
     from kymatio.backend.torch_backend import TorchBackend as RefBackend
     from kymatio.scattering1d.backend.torch_backend import TorchBackend1D as RefBackend1D
     from kymatio.scattering3d.backend.torch_backend import TorchBackend3D as RefBackend3D
-    backend2d = type("TorchB200Backend2D", (_Primitives2D, RefBackend), {"name": NAME, "Pad": Pad, "__doc__": _Primitives2D.__doc__})
+    backend2d = type("TorchB200Backend2D", (_Layout2D, _Primitives2D, RefBackend), {"name": NAME, "Pad": Pad, "__doc__": _Primitives2D.__doc__})
     backend1d = type("TorchB200Backend1D", (_DifferentiableEager, _Primitives1D, _Primitives2D, RefBackend1D),
                      {"name": NAME, "Pad": None, "__doc__": _Primitives1D.__doc__})
     backend3d = type("TorchB200Backend3D", (_DifferentiableEager, _Primitives3D, _Primitives2D, RefBackend3D),

@@ -133,6 +133,61 @@ template <int N> static int check_static() {
     return bad;
 }
 
+// prime-factor variant (no twiddles between the pow2 and the odd-prime pass): DIF with pfa_in / pfa_out positions and the
+// transposed DIT flow, both signs, against the naive DFT
+template <int N, bool DIT, int SIGN, typename T> static void run_static_pfa(std::vector<cx<T>>& line, const std::vector<cx<T>>& tw) {
+    constexpr int NP = ct_plan1(N).npass;
+    static_for<0, NP>([&](auto pp_) {
+        constexpr int pp = decltype(pp_)::value;
+        constexpr int p = DIT ? NP - 1 - pp : pp;
+        constexpr int r = ct_plan1(N).radix[p], m = ct_plan1(N).blen[p];
+        constexpr int q = m / r, nbf = N / r, tws = N / m;
+        for (int bf = 0; bf < nbf; ++bf) {
+            const int blk = bf / q, i = bf - blk * q;
+            butterfly_s<r, DIT, SIGN, q, 1, false, T, false>(line.data() + blk * m + i, i * tws, tw.data());
+        }
+    });
+}
+template <int N> static int check_pfa() {
+    typedef float T;
+    static_assert(ct_pfa_ok(N), "not a prime-factor length");
+    auto tw = twiddle_table<T>(N);
+    std::vector<int> pin, pout;
+    pfa_tables(N, pin, pout);
+    std::vector<char> seen(N, 0);
+    for (int i = 0; i < N; ++i) { if (seen[pin[i]]) return 1; seen[pin[i]] = 1; }
+    std::vector<std::complex<long double>> x(N);
+    srand(99 + N);
+    for (int i = 0; i < N; ++i) x[i] = {(long double)rand() / RAND_MAX - 0.5L, (long double)rand() / RAND_MAX - 0.5L};
+    const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+    int bad = 0;
+    for (int sign = -1; sign <= 1; sign += 2) {
+        std::vector<std::complex<long double>> X(N);
+        double nrm = 0;
+        for (int f = 0; f < N; ++f) {
+            std::complex<long double> acc = 0;
+            for (int t = 0; t < N; ++t) {
+                long double a = sign * tau * (long double)((long long)f * t % N) / N;
+                acc += x[t] * std::complex<long double>(cosl(a), sinl(a));
+            }
+            X[f] = acc; nrm = std::max(nrm, (double)std::abs(acc));
+        }
+        std::vector<cx<T>> line(N);
+        for (int i = 0; i < N; ++i) line[pin[i]] = mk<T>((T)x[i].real(), (T)x[i].imag());
+        if (sign < 0) run_static_pfa<N, false, -1, T>(line, tw); else run_static_pfa<N, false, +1, T>(line, tw);
+        double e1 = 0, e2 = 0;
+        for (int f = 0; f < N; ++f)
+            e1 = std::max(e1, (double)std::abs(std::complex<long double>(line[pout[f]].x, line[pout[f]].y) - X[f]));
+        for (int i = 0; i < N; ++i) line[pout[i]] = mk<T>((T)x[i].real(), (T)x[i].imag());
+        if (sign < 0) run_static_pfa<N, true, -1, T>(line, tw); else run_static_pfa<N, true, +1, T>(line, tw);
+        for (int f = 0; f < N; ++f)
+            e2 = std::max(e2, (double)std::abs(std::complex<long double>(line[pin[f]].x, line[pin[f]].y) - X[f]));
+        printf("pfa N=%d sign=%+d DIF rel=%.3g DIT rel=%.3g\n", N, sign, e1 / nrm, e2 / nrm);
+        if (e1 / nrm > 2e-5 || e2 / nrm > 2e-5) ++bad;
+    }
+    return bad;
+}
+
 int main() {
     int sizes[] = {1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 16, 17, 18, 20, 24, 30, 32, 34, 36, 40, 48, 60, 64, 66, 68, 96,
                    120, 128, 136, 138, 240, 256, 272, 286, 290, 442, 512, 1016, 1024, 4096};
@@ -147,6 +202,7 @@ int main() {
     }
     bad += check_static<136>() + check_static<68>() + check_static<272>() + check_static<128>() +
            check_static<240>() + check_static<34>();
+    bad += check_pfa<136>() + check_pfa<68>() + check_pfa<272>() + check_pfa<34>();
     printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);
     return bad ? 1 : 0;
 }
