@@ -451,32 +451,44 @@ def run_b200_arm(args):
         clocks = sampler.stop(t_begin, t_end)
 
         # ---- end to end: pinned host in -> H2D -> forward -> D2H pinned host out, every step -------
+        # A double-buffered consumer: two sets of pinned host buffers, at most two steps in flight - step i+1 may start its
+        # copies and kernels while the last device->host copies of step i drain, but step i+2 waits until step i has fully
+        # landed in host memory (its buffers are reused).  Every step still moves all of its input and output.
         xh = torch.randn(B, *SHAPE, dtype=torch.float32).pin_memory()
-        yh = torch.empty((B,) + tuple(y.shape[1:]), dtype=torch.float32).pin_memory()
-        nchunk = int(os.environ.get("BENCH_E2E_CHUNKS", "8"))
+        yh = [torch.empty((B,) + tuple(y.shape[1:]), dtype=torch.float32).pin_memory() for _ in range(2)]
+        nchunk = int(os.environ.get("BENCH_E2E_CHUNKS", "4"))
         if B % nchunk or B < 4 * nchunk:
             nchunk = 1
         cb = B // nchunk
-        streams = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("BENCH_E2E_STREAMS", "3")), nchunk))]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("BENCH_E2E_STREAMS", "2")), nchunk))]
         yd_keep = torch.empty((cb,) + tuple(y.shape[1:]), dtype=torch.float32, device=dev)
+        landed = [None, None]           # per host buffer set: events of the step that last wrote it
 
-        def e2e_step(compute=True):
+        def e2e_step(i, compute=True):
+            buf = i & 1
+            if landed[buf] is not None:
+                for ev in landed[buf]:
+                    ev.synchronize()    # the host has this buffer set back (step i-2 fully landed)
+            evs = []
             for c in range(nchunk):
                 st = streams[c % len(streams)]
                 with torch.cuda.stream(st):
                     xd = xh[c * cb:(c + 1) * cb].to(dev, non_blocking=True)
                     yd = S(xd) if compute else yd_keep
-                    yh[c * cb:(c + 1) * cb].copy_(yd, non_blocking=True)
+                    yh[buf][c * cb:(c + 1) * cb].copy_(yd, non_blocking=True)
             for st in streams:
-                st.synchronize()
+                ev = torch.cuda.Event()
+                ev.record(st)
+                evs.append(ev)
+            landed[buf] = evs
 
         def time_e2e(compute):
-            for _ in range(2):
-                e2e_step(compute)
+            for i in range(2):
+                e2e_step(i, compute)
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                e2e_step(compute)
+            for i in range(args.steps):
+                e2e_step(i, compute)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             barrier()
@@ -505,6 +517,26 @@ def run_b200_arm(args):
                       "what": "ShardedScattering-style all_gather_into_tensor of the (B, K, 32, 32) fp32 blocks over NCCL, "
                               "every rank ends with the full tensor; device-timed, max over ranks"}
             del yfull
+            # the same gather FUSED into the producing kernels: peer stores over NVLink into symmetric memory
+            # (kymatio_b200.parallel.PeerGatherScattering, scat_plan2d_forward_peers)
+            try:
+                from kymatio_b200 import Scattering2D as OwnScattering2D
+                from kymatio_b200.parallel import PeerGatherScattering
+                P = PeerGatherScattering(OwnScattering2D(J, SHAPE, L=L).to(dev))
+                for _ in range(2):
+                    yp = P(x, world * B)
+                barrier()
+                f_ms, yp = timed_steps(lambda: P(x, world * B), nst, flush)
+                ft = torch.tensor([f_ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+                ok = bool(torch.equal(yp[rank * B:(rank + 1) * B], S(x)))
+                gather["peer_store"] = {"ms_per_step": float(ft[0]) / nst, "gather_ms": (float(ft[0]) - float(gt[1])) / nst,
+                                        "images_per_s": world * B * nst / (float(ft[0]) * 1e-3), "own_block_bit_exact": ok,
+                                        "what": "every coefficient plane stored by the producing kernel into all ranks' "
+                                                "symmetric-memory buffers (remote stores over NVLink) + one barrier"}
+                del yp, P
+            except Exception as e:                      # symmetric memory unavailable on this box / build
+                gather["peer_store"] = {"unavailable": repr(e)[:300]}
 
         # ---- live per-kernel timing for the roofline of the dominant kernel -----------------------
         kern = None
@@ -559,10 +591,11 @@ def run_b200_arm(args):
                    "l2": "flushed between timed steps (256 MiB write, untimed); step working set 3.6 GB >> L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": xh.numel() * 4,
-                "d2h_bytes_per_step": yh.numel() * 4,
+                "d2h_bytes_per_step": yh[0].numel() * 4,
                 "copy_only_ceiling": world * B * args.steps / (copy_ms * 1e-3),
-                "note": f"pinned host in/out through {route}, {nchunk} chunks pipelined on {len(streams)} streams, wall clock, "
-                        "max over ranks; copy_only_ceiling = the same pinned transfers with the compute removed"},
+                "note": f"pinned host in/out through {route}, {nchunk} chunks on {len(streams)} streams, two host buffer sets "
+                        "(at most two steps in flight), wall clock over all K steps incl. the final drain, max over ranks; "
+                        "copy_only_ceiling = the same pinned transfers with the compute removed"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": top["pass_model_GBps"], "peak": hbm_peak, "unit": "GB/s",
                      "frac": top["pass_model_frac"], "traffic": top.get("dram_bytes_per_launch"), "kernel": top["label"],

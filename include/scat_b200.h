@@ -77,6 +77,27 @@ size_t scat_plan2d_workspace_bytes(const scat_plan2d* plan, int64_t batch);
 /* x_dev: (batch, M, N) real [or (batch, Mp, Np) when pre_pad]; out_dev: (batch, K, out_h, out_w) */
 int  scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, void* workspace_dev,
                          size_t workspace_bytes, int64_t batch, void* stream);
+/* The same forward with every coefficient plane ALSO stored at the same offset of n_peers (<= 7) more buffers: the
+ * output tensors of the peer GPUs (symmetric memory mapped over NVLink).  Batch-sharded ranks that each pass the others'
+ * buffers end up with the full (total_batch, K, oh, ow) tensor without a separate all-gather pass; the caller places a
+ * cross-rank barrier after the call (kymatio_b200/parallel.py: PeerGatherScattering).  peer_out_dev is a HOST array of
+ * device pointers, each already offset to this rank's block. */
+int  scat_plan2d_forward_peers(scat_plan2d* plan, const void* x_dev, void* out_dev, void* const* peer_out_dev,
+                               int32_t n_peers, void* ws_dev, size_t ws_bytes, int64_t batch, void* stream);
+
+/* First-order block of scale j1 as a stand-alone differentiable operator on a caller-provided U0 = fft2(pad(x))
+ * (kymatio/scattering2d/core/scattering2d.py:30-51; gradients: SURVEY Appendix B, kymatio/backend/torch_backend.py:64-96).
+ * mode 1 (the field fits one CTA): forward returns S1 (batch, L, oh, ow) and, when u1_dev != NULL, U1 = fft2(|.|)
+ *   (batch*L, n0, n1) complex; backward takes gs1 and (optionally) gu1.
+ * mode 2 (full resolution, streaming chain): forward returns U1 only (s1_dev = NULL; the caller low-passes U1);
+ *   backward takes gu1.  mode 0: not available (caller uses the per-primitive ops).
+ * backward ACCUMULATES into gu0_dev (batch, Mp, Np) complex; ws_dev: scat_plan2d_order1_workspace_bytes. */
+int32_t scat_plan2d_order1_mode(const scat_plan2d* plan, int32_t j1);
+size_t scat_plan2d_order1_workspace_bytes(const scat_plan2d* plan, int32_t j1, int64_t batch);
+int  scat_plan2d_order1_forward(scat_plan2d* plan, int32_t j1, const void* u0_dev, void* s1_dev, void* u1_dev, int64_t batch,
+                                void* stream);
+int  scat_plan2d_order1_backward(scat_plan2d* plan, int32_t j1, const void* u0_dev, const void* gs1_dev, const void* gu1_dev,
+                                 void* gu0_dev, void* ws_dev, size_t ws_bytes, int64_t batch, void* stream);
 
 /* The second-order block of first-order scale j1 as a stand-alone differentiable operator (used by the
  * autograd path): u1_dev = (batch*L, n0_j1, n1_j1) complex natural-order spectra of the first-order moduli

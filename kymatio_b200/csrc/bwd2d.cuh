@@ -1,0 +1,178 @@
+// bwd2d.cuh - fused backward of the FIRST-order block of the 2-D cascade (the reference gets these
+// gradients by replaying torch autograd over every primitive, with kymatio/backend/torch_backend.py:64-96 for the modulus).
+//
+// One first-order path:   V = periodise_k(U0 * psi) * scale;  u = F^H V (unnormalised inverse);  A = |u|;  U1 = F A
+// with the gradient gU1 of everything downstream of U1 (the fused second-order block and, at the streaming level, the
+// Fourier low-pass) and - at tile levels - the gradient gS1 of the path's own low-passed output:
+//     gA  = Re(F^H gU1) [+ G0 gS1 G1^T]        adjoint of the forward transform of a REAL field (+ separable low-pass)
+//     gu  = gA u / |u|   (0 where u = 0)       ModulusStable.backward
+//     gV  = F gu                               adjoint of the unnormalised inverse transform
+//     gU0 += scale * psi * replicate_k(gV)     adjoint of periodisation and filter multiply
+//
+// Tile levels (field fits one CTA):
+//     k2d_tile_adj    R = Re(F^H gU1) of one path, written in the tile's STORAGE order (rows / columns at the scrambled
+//                     positions of the decimation-in-frequency inverse), so that
+//     k2d_tile_bwd    (tile2d.cuh; recomputes u in the same storage order) just adds R[q][x'] to its low-pass adjoint.
+// Streaming level (full resolution, field = 16-line slabs), mirror of the forward chain rowpass_prod -> colpass -> rowpass:
+//     (row pass)      Y = rows-inverse(U0 * psi)   and   GX = rows-inverse(gU1)         (k2d_rowpass_prod, unit filter)
+//     k2d_bwd_col     per 16-column slab: u = cols-inverse(Y), G = cols-inverse(GX), gu = Re(G) u/|u|, cols-forward(gu)
+//     k2d_bwd_row     per (image, 16-row slab): rows-forward of the L paths of the image one after the other,
+//                     multiply by psi_theta * scale and ACCUMULATE over theta in registers -> one deterministic
+//                     read-modify-write of gU0 (no atomics).
+#pragma once
+#include "kernels2d.cuh"
+#include "tile2d.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------ tile level: R = Re(F^H gU1) in storage order
+template <typename T> struct TileAdjArgs {
+    const cx<T>* gspec;        // [G][n0][n1] natural-order spectrum gradients
+    T* R;                      // [G][n0][n1] real, storage order
+    const cx<T>* tw0; const cx<T>* tw1;
+    int G;
+};
+template <typename T, int N0, int N1>
+__global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, N1)) k2d_tile_adj(TileAdjArgs<T> a) {
+    constexpr int W = N1 | 1;
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* tw0 = s + (size_t)N0 * W;
+    cx<T>* tw1 = tw0 + N0;
+    const int tid = flat_tid(), nt = flat_nt();
+    stage(tw0, a.tw0, N0); stage(tw1, a.tw1, N1);
+    constexpr int half = N1 / 2;
+    for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
+        const cx<T>* __restrict__ ib = a.gspec + (size_t)g * N0 * N1;
+        __syncthreads();
+        for (int it = tid; it < N0 * half; it += nt) {
+            const int r = it / half, e = 2 * (it - r * half);
+            const cx2<T> v = *reinterpret_cast<const cx2<T>*>(ib + (size_t)r * N1 + e);
+            s[r * W + e] = v.a; s[r * W + e + 1] = v.b;
+        }
+        __syncthreads();
+        slab_fft_s<N1, false, +1, W, 1, T>(s, N0, tw1);
+        slab_fft_s<N0, false, +1, 1, W, T>(s, N1, tw0);
+        T* __restrict__ ob = a.R + (size_t)g * N0 * N1;
+        for (int it = tid; it < N0 * N1; it += nt) {
+            const int q = it / N1, x = it - q * N1;
+            ob[it] = s[q * W + x].x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ streaming level, column pass
+template <typename T> struct BwdColArgs {
+    const cx<T>* Y;            // [G][n0][n1] rows-inverse of the product (rows: natural frequency, columns: scrambled x)
+    const cx<T>* GX;           // [G][n0][n1] rows-inverse of gU1, same layout
+    cx<T>* out;                // [G][n0][n1] cols-forward of gu (rows natural frequency, columns scrambled x); may alias Y
+    int n1;
+    const cx<T>* tw;
+};
+constexpr int kBwdThreads = 256;
+// grid (G, n1 / 16), kBwdThreads threads; two 16-column slabs in shared memory
+template <typename T, int NS> __global__ void __launch_bounds__(kBwdThreads, 3) k2d_bwd_col(BwdColArgs<T> a) {
+    constexpr int n0 = NS, LP = kSLP;
+    cx<T>* s1 = dyn_smem<cx<T>>();
+    cx<T>* s2 = s1 + (size_t)n0 * LP;
+    cx<T>* tw = s2 + (size_t)n0 * LP;
+    const int g = blockIdx.x, c0 = blockIdx.y * kSLines;
+    const int tid = flat_tid(), nt = flat_nt();
+    stage(tw, a.tw, n0);
+    const size_t off = (size_t)g * n0 * a.n1 + c0;
+    for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+        const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+        const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(a.Y + off + (size_t)e * a.n1 + l);
+        const cxpair<T> w = *reinterpret_cast<const cxpair<T>*>(a.GX + off + (size_t)e * a.n1 + l);
+        s1[e * LP + l] = v.a; s1[e * LP + l + 1] = v.b;
+        s2[e * LP + l] = w.a; s2[e * LP + l + 1] = w.b;
+    }
+    __syncthreads();
+    slab_fft_s<NS, false, +1, 1, kSLP, T>(s1, kSLines, tw);      // u   (rows scrambled)
+    slab_fft_s<NS, false, +1, 1, kSLP, T>(s2, kSLines, tw);      // F^H gU1, same positions
+    for (int idx = tid; idx < n0 * kSLines; idx += nt) {
+        const int e = idx / kSLines, l = idx - e * kSLines;
+        const cx<T> v = s1[e * LP + l];
+        const T gA = s2[e * LP + l].x;
+        const T mag = sqrt(v.x * v.x + v.y * v.y);
+        const T sc = mag > T(0) ? gA / mag : T(0);
+        s1[e * LP + l] = mk<T>(v.x * sc, v.y * sc);
+    }
+    __syncthreads();
+    slab_fft_s<NS, true, -1, 1, kSLP, T>(s1, kSLines, tw);       // cols-forward: scrambled in -> natural frequency out
+    for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+        const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+        cxpair<T> v; v.a = s1[e * LP + l]; v.b = s1[e * LP + l + 1];
+        *reinterpret_cast<cxpair<T>*>(a.out + off + (size_t)e * a.n1 + l) = v;
+    }
+}
+
+// ------------------------------------------------------------------ streaming level, row pass + reduction over theta
+template <typename T> struct BwdRowArgs {
+    const cx<T>* GV;           // [B*NF][n0][n1] output of k2d_bwd_col
+    const T* const* filt;      // [NF] real (n0, n1) filters, natural order
+    cx<T>* gU0;                // [B][n0][n1], accumulated into
+    int n0, NF;
+    T scale;
+    const cx<T>* tw;
+};
+// grid (B, ceil(n0 / 16)), kBwdThreads threads
+template <typename T, int NS> __global__ void __launch_bounds__(kBwdThreads, 2) k2d_bwd_row(BwdRowArgs<T> a) {
+    constexpr int n1 = NS, LP = kSLP, half = NS / 2;
+    constexpr int PAIRS = (kSLines * half + kBwdThreads - 1) / kBwdThreads;     // column pairs per thread
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* tw = s + (size_t)n1 * LP;
+    const int b = blockIdx.x, r0 = blockIdx.y * kSLines;
+    const int nl = min(kSLines, a.n0 - r0);
+    const int tid = flat_tid(), nt = flat_nt();
+    stage(tw, a.tw, n1);
+    cx<T> acc[PAIRS][2];
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) { acc[p][0] = mk<T>(T(0), T(0)); acc[p][1] = mk<T>(T(0), T(0)); }
+    for (int fi = 0; fi < a.NF; ++fi) {
+        const cx<T>* ib = a.GV + (((size_t)b * a.NF + fi) * a.n0 + r0) * n1;
+        __syncthreads();                                         // the previous filter's reads of s are done
+        for (int idx = tid; idx < nl * half; idx += nt) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(ib + (size_t)l * n1 + e);
+            s[e * LP + l] = v.a; s[(e + 1) * LP + l] = v.b;
+        }
+        __syncthreads();
+        slab_fft_s<NS, true, -1, 1, kSLP, T>(s, nl, tw);         // rows-forward: scrambled x in -> natural frequency out
+        const T* __restrict__ fb = a.filt[fi] + (size_t)r0 * n1;
+#pragma unroll
+        for (int p = 0; p < PAIRS; ++p) {
+            const int idx = tid + p * nt;
+            if (idx < nl * half) {
+                const int l = idx / half, e = 2 * (idx - l * half);
+                const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + (size_t)l * n1 + e);
+                const cx<T> v0 = s[e * LP + l], v1 = s[(e + 1) * LP + l];
+                acc[p][0] = fma_rc(acc[p][0], v0, f.a);
+                acc[p][1] = fma_rc(acc[p][1], v1, f.b);
+            }
+        }
+    }
+    cx<T>* ob = a.gU0 + ((size_t)b * a.n0 + r0) * n1;
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) {
+        const int idx = tid + p * nt;
+        if (idx < nl * half) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            cxpair<T>* dst = reinterpret_cast<cxpair<T>*>(ob + (size_t)l * n1 + e);
+            cxpair<T> o = *dst;
+            o.a = fma_rc(o.a, acc[p][0], a.scale);
+            o.b = fma_rc(o.b, acc[p][1], a.scale);
+            *dst = o;
+        }
+    }
+}
+
+// kernel lookup (instances in bwd_inst.cu); null when the size has no static instance
+template <typename T> using TileAdjKernel = void (*)(TileAdjArgs<T>);
+template <typename T> using BwdColKernel = void (*)(BwdColArgs<T>);
+template <typename T> using BwdRowKernel = void (*)(BwdRowArgs<T>);
+template <typename T> TileAdjKernel<T> tile_adj_lookup(int n0, int n1);
+template <typename T> BwdColKernel<T> bwd_col_lookup(int n);
+template <typename T> BwdRowKernel<T> bwd_row_lookup(int n);
+template <typename T> void bwd_kernels_enable_smem();
+
+}  // namespace sb

@@ -36,6 +36,27 @@ template <typename T> __device__ __forceinline__ T* dyn_smem() {
     return reinterpret_cast<T*>(sb_dyn_smem);
 }
 
+// Coefficient planes may be written to SEVERAL buffers at once: the caller's own output and the same location of the
+// output tensors of the peer GPUs (symmetric memory mapped over NVLink, parallel.py: PeerGatherScattering).  The final
+// low-pass stores are a few KB per path, so replicating them costs nothing and the all-gather of the batch-sharded
+// result needs no extra pass - the transfer rides on the kernels that produce the coefficients.
+constexpr int kMaxPeers = 7;
+template <typename T> struct OutPeers { T* p[kMaxPeers]; int n; };
+template <typename T> struct OutRef {
+    T* out; const OutPeers<T>* pe; size_t off;
+    struct Slot {
+        const OutRef& r; size_t i;
+        __device__ __forceinline__ void operator=(T v) const {
+            r.out[r.off + i] = v;
+            for (int k = 0; k < r.pe->n; ++k) r.pe->p[k][r.off + i] = v;
+        }
+    };
+    __device__ __forceinline__ Slot operator[](size_t i) const { return Slot{*this, i}; }
+};
+template <typename T> __device__ __forceinline__ OutRef<T> out_ref(T* out, const OutPeers<T>& pe, size_t off) {
+    OutRef<T> r; r.out = out; r.pe = &pe; r.off = off; return r;
+}
+
 template <typename U> __device__ __forceinline__ void stage(U* dst, const U* __restrict__ src, int n) {
     for (int i = flat_tid(); i < n; i += flat_nt()) dst[i] = src[i];
 }
@@ -245,7 +266,7 @@ template <typename T, int MODE, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_c
 // ------------------------------------------------------------------ row pass, product + periodise prologue
 template <typename T> struct RowProdArgs {
     const cx<T>* parent;      // [Bp][P0][P1] natural-order spectra
-    const T* const* filt;     // [NF] pointers to real (P0, P1) filters, natural order
+    const T* const* filt;     // [NF] pointers to real (P0, P1) filters, natural order; nullptr = unit filter (k = 1 only)
     const int2* supp;         // [NF][P0] per-row circular support (start, len)
     cx<T>* out;               // [Bp*NF][n0][n1]: Fourier rows (natural), spatial columns
     int P0, P1, k, n0, n1, NF;
@@ -267,7 +288,7 @@ template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_rowpass_pro
     stage(pos, a.pos, n1);
     __syncthreads();
     const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
-    const T* __restrict__ fb = a.filt[fi];
+    const T* __restrict__ fb = a.filt ? a.filt[fi] : nullptr;
     const int2* sp = a.supp + (size_t)fi * a.P0;
     const int tid = flat_tid(), nt = flat_nt();
     // static instances keep natural order in shared memory (the inverse runs as DIF and leaves the row
@@ -281,7 +302,8 @@ template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_rowpass_pro
                 // no aliases: plain vector loads (values outside the support interval are the true, tiny ones)
                 const size_t off = (size_t)(r0 + l) * P1 + e;
                 const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(pb + off);
-                const repair<T> f = *reinterpret_cast<const repair<T>*>(fb + off);
+                repair<T> f; f.a = T(1); f.b = T(1);
+                if (fb) f = *reinterpret_cast<const repair<T>*>(fb + off);
                 ax0 = v.a.x * f.a; ay0 = v.a.y * f.a; ax1 = v.b.x * f.b; ay1 = v.b.y * f.b;
             } else {
                 for (int c = 0; c < k; ++c) {
@@ -433,7 +455,9 @@ template <typename T, int NS> __global__ void SB_SLAB_BOUNDS(NS) k2d_colpass_imr
     // prime-factor transforms where the length allows (272 = 16 x 17): the rows are scattered to their prime-factor input
     // positions while staging (free), both transforms run without twiddles between their two passes, and the natural
     // output row v of the forward (DIT) transform is found at pin[v]   (fft_core.cuh)
-    constexpr bool PFA = ct_pfa_ok(NS);
+    // (measured at 272: 0.613 ms with the prime-factor variant against 0.589 ms without - the scattered staging stores and
+    //  the pin[] lookups of the untangling step cost more than the 255 twiddle multiplications per column save)
+    constexpr bool PFA = false && ct_pfa_ok(NS);
     cx<T>* s = dyn_smem<cx<T>>();
     cx<T>* tw = s + (size_t)n0 * LP;
     int* pin = reinterpret_cast<int*>(tw + n0);
@@ -541,6 +565,7 @@ template <typename T> struct LowArgs {
     T scale;
     Plan1 plan0, plan1; const cx<T>* tw0; const cx<T>* tw1; const int* pos0; const int* pos1;
     int row_folded;       // 1: `in` is [G][P0][m1], already multiplied by the filter and folded along rows
+    OutPeers<T> peers;    // additional destinations of the channel planes (peer GPUs)
 };
 // grid (G).  One CTA: periodise (in*filt) to m0 x m1, inverse 2-D DIT in shared memory,
 // keep the real part, crop one sample per side (unpad) and write the channel plane.
@@ -574,7 +599,7 @@ template <typename T> __global__ void __launch_bounds__(kMaxThreads) k2d_lowpass
     slab_fft<true, T>(s, a.m0, a.W, 1, a.plan1, tw1);   // along rows (length m1)
     slab_fft<true, T>(s, a.m1, 1, a.W, a.plan0, tw0);   // along columns (length m0)
     const int o0 = a.m0 - 2, o1 = a.m1 - 2;
-    T* ob = a.out + ((size_t)b * a.K + ch) * o0 * o1;
+    const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * o0 * o1);
     for (int idx = flat_tid(); idx < o0 * o1; idx += flat_nt()) {
         const int y = idx / o1, x = idx - y * o1;
         ob[idx] = s[(y + 1) * a.W + (x + 1)].x;
@@ -586,6 +611,7 @@ template <typename T> struct CropArgs {
     const cx<T>* in;   // [G][m0][m1] natural-order spatial field
     T* out;            // [B][K][m0-2][m1-2]
     int m0, m1, PP, NF, ch0, chs, K;
+    OutPeers<T> peers;
 };
 template <typename T> __global__ void k2d_crop_real(CropArgs<T> a) {
     const int g = blockIdx.x;
@@ -595,7 +621,7 @@ template <typename T> __global__ void k2d_crop_real(CropArgs<T> a) {
     const int idx = blockIdx.y * blockDim.x + threadIdx.x;
     if (idx >= o0 * o1) return;
     const int y = idx / o1, x = idx - y * o1;
-    a.out[((size_t)b * a.K + ch) * o0 * o1 + idx] = a.in[((size_t)g * a.m0 + y + 1) * a.m1 + x + 1].x;
+    out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * o0 * o1)[idx] = a.in[((size_t)g * a.m0 + y + 1) * a.m1 + x + 1].x;
 }
 
 }  // namespace sb

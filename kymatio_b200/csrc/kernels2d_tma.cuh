@@ -103,12 +103,13 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k2d_rowprod_tma(RowProdArgs<fl
     // ---------------- compute warps
     constexpr int R0 = ct_plan1(NS).radix[0], Q0 = NS / R0;
     static_assert(Q0 * ROWS <= kTmaComputeThreads, "one first-pass butterfly per compute thread");
-    const T* __restrict__ fb = a.filt[fi];
     const int row = min(tid / Q0, ROWS - 1), e = tid - (tid / Q0) * Q0;
     T f0[R0];                                                   // this thread's filter values, resident for every image
-    {
-        const T* __restrict__ frow = fb + (size_t)(r0 + row) * NS + e;
+    if (a.filt) {
+        const T* __restrict__ frow = a.filt[fi] + (size_t)(r0 + row) * NS + e;
         static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; f0[k] = __ldg(frow + k * Q0) * a.scale; });
+    } else {                                                    // unit filter (adjoint row pass of the backward chain)
+        static_for<0, R0>([&](auto k_) { constexpr int k = decltype(k_)::value; f0[k] = a.scale; });
     }
     for (int i = 0; i < n_my; ++i) {
         const int b = i & 1;

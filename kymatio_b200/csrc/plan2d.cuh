@@ -19,6 +19,7 @@
 #include "tile2d.cuh"
 #include "tile2h.cuh"
 #include "kernels2d_tma.cuh"
+#include "bwd2d.cuh"
 #include "plan_host.h"
 
 struct scat_plan2d {
@@ -29,10 +30,19 @@ struct scat_plan2d {
                       cudaStream_t st) = 0;
     virtual size_t workspace_bytes(int64_t batch) const = 0;
     virtual void forward(const void* x, void* out, void* ws, size_t ws_bytes, int64_t batch, cudaStream_t st) = 0;
+    // the same forward, every coefficient plane also stored at the same offset of n_peers more buffers (peer GPUs)
+    virtual void forward_peers(const void* x, void* out, void* const* peer_out, int n_peers, void* ws, size_t ws_bytes,
+                               int64_t batch, cudaStream_t st) = 0;
     // second-order block of first-order scale j1 on caller-provided parent spectra (autograd building block)
     virtual int order2_channels(int j1) const = 0;     // 0 when the fused block is not available for j1
     virtual void order2_forward(int j1, const void* u1, void* out, int64_t batch, cudaStream_t st) = 0;
     virtual void order2_backward(int j1, const void* u1, const void* gout, void* gu1, int64_t batch, cudaStream_t st) = 0;
+    // first-order block of scale j1 on a caller-provided U0 (autograd building block, bwd2d.cuh)
+    virtual int order1_mode(int j1) const = 0;          // 0 not fused, 1 tile level (S1 and U1), 2 streaming level (U1 only)
+    virtual size_t order1_workspace_bytes(int j1, int64_t batch) const = 0;
+    virtual void order1_forward(int j1, const void* u0, void* s1, void* u1, int64_t batch, cudaStream_t st) = 0;
+    virtual void order1_backward(int j1, const void* u0, const void* gs1, const void* gu1, void* gu0, void* ws, size_t ws_bytes,
+                                 int64_t batch, cudaStream_t st) = 0;
 };
 
 namespace sb {
@@ -173,6 +183,7 @@ public:
             tile2h_kernels_enable_smem<T>();
         });
         once_per_device("tma_rows", [] { tma_kernels_enable_smem(); });
+        once_per_device(sizeof(T) == 4 ? "bwd2d_f" : "bwd2d_d", [] { bwd_kernels_enable_smem<T>(); });
         {
             int dev = 0;
             SB_CUDA(cudaGetDevice(&dev));
@@ -257,9 +268,20 @@ public:
         const size_t out_img = (size_t)K_ * o0_ * o1_;
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int B = (int)std::min<int64_t>(chunk, batch - b0);
+            peers_.n = n_peer_base_;
+            for (int i = 0; i < n_peer_base_; ++i) peers_.p[i] = peer_base_[i] + b0 * out_img;
             forward_chunk(static_cast<const T*>(x) + b0 * in_img, static_cast<T*>(out) + b0 * out_img,
                           static_cast<cx<T>*>(ws), B, st);
         }
+        peers_.n = 0;
+    }
+    void forward_peers(const void* x, void* out, void* const* peer_out, int n_peers, void* ws, size_t ws_bytes,
+                       int64_t batch, cudaStream_t st) override {
+        if (n_peers < 0 || n_peers > kMaxPeers) throw std::runtime_error("at most 7 peer outputs");
+        n_peer_base_ = n_peers;
+        for (int i = 0; i < n_peers; ++i) peer_base_[i] = static_cast<T*>(peer_out[i]);
+        try { forward(x, out, ws, ws_bytes, batch, st); } catch (...) { n_peer_base_ = 0; throw; }
+        n_peer_base_ = 0;
     }
 
     // ---- second-order block as a stand-alone (differentiable) operator --------------------------------
@@ -290,6 +312,95 @@ public:
             tile(static_cast<const cx<T>*>(u1), psi_ptrs(j2, j1), psi_supp(j2, j1), j1, j2, (int)batch * L, L,
                  nullptr, L * L, L, (j2 - j1 - 1) * L, nchild, nullptr, "o2_bwd", st, C2,
                  static_cast<const T*>(gout), static_cast<cx<T>*>(gu1));
+    }
+
+    // ---- first-order block as a stand-alone (differentiable) operator ---------------------------------
+    int order1_mode(int j1) const override {
+        if (!bound_ || j1 < 0 || j1 >= d_.J) return 0;
+        const int n0 = lev_[j1].a0.n, n1 = lev_[j1].a1.n;
+        if (tile_ok_[j1]) {
+            bool st = false;
+            tile_bwd_kernel_lookup<T>(n0, n1, 1 << j1, &st);
+            return (st && tile_adj_lookup<T>(n0, n1)) ? 1 : 0;
+        }
+        if (j1 == 0 && hermitian_ok(0) && n0 == n1 && bwd_col_lookup<T>(n0) && bwd_row_lookup<T>(n1)) return 2;
+        return 0;
+    }
+    size_t order1_workspace_bytes(int j1, int64_t batch) const override {
+        const size_t G = (size_t)batch * d_.L;
+        return order1_mode(j1) == 2 ? 2 * G * fsize(j1) * sizeof(cx<T>) : G * fsize(j1) * sizeof(T);
+    }
+    // u0: [batch][P0][P1] spectra; s1: [batch][L][o0][o1] (tile levels, may be null at the streaming level);
+    // u1: [batch*L][n0][n1] natural-order spectra of the moduli (null: not needed)
+    void order1_forward(int j1, const void* u0, void* s1, void* u1, int64_t batch, cudaStream_t st) override {
+        const int mode = order1_mode(j1);
+        if (!mode) throw std::runtime_error("fused first-order block not available for this scale");
+        const int L = d_.L, B = (int)batch;
+        last_B_ = B;
+        const cx<T>* U0 = static_cast<const cx<T>*>(u0);
+        if (mode == 1) {
+            tile(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), 0, j1, B, L, static_cast<T*>(s1), L, L, 0, 0, static_cast<cx<T>*>(u1),
+                 u1 ? "o1p" : "o1", st, L);
+        } else {
+            if (!u1) throw std::runtime_error("the streaming first-order block returns U1");
+            const T sc1 = T(1) / (T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
+            row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), static_cast<cx<T>*>(u1), 0, j1, B, L, sc1, st);
+            hermitian_chain(static_cast<cx<T>*>(u1), j1, B * L, st, nullptr);
+        }
+    }
+    // gu0 ([batch][P0][P1], ACCUMULATED into) += gradient through the first-order block; gs1 as s1 (tile levels), gu1 as u1
+    void order1_backward(int j1, const void* u0, const void* gs1, const void* gu1, void* gu0, void* ws, size_t ws_bytes,
+                         int64_t batch, cudaStream_t st) override {
+        const int mode = order1_mode(j1);
+        if (!mode) throw std::runtime_error("fused first-order block not available for this scale");
+        if (ws_bytes < order1_workspace_bytes(j1, batch)) throw std::runtime_error("order1_backward: workspace too small");
+        const int L = d_.L, B = (int)batch, n0 = lev_[j1].a0.n, n1 = lev_[j1].a1.n;
+        last_B_ = B;
+        const cx<T>* U0 = static_cast<const cx<T>*>(u0);
+        if (mode == 1) {
+            if (!gs1) throw std::runtime_error("order1_backward: gs1 is required at tile levels");
+            T* R = nullptr;
+            if (gu1) {
+                R = static_cast<T*>(ws);
+                TileAdjArgs<T> a{};
+                a.gspec = static_cast<const cx<T>*>(gu1); a.R = R; a.tw0 = tw(lev_[j1].a0); a.tw1 = tw(lev_[j1].a1); a.G = B * L;
+                auto kern = tile_adj_lookup<T>(n0, n1);
+                const size_t smem = ((size_t)n0 * (n1 | 1) + n0 + n1) * sizeof(cx<T>);
+                const int threads = tile_is_big(n0, n1) ? 512 : 256;
+                int occ = 0;
+                SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+                const int grid = std::max(1, std::min(a.G, std::max(1, occ) * num_sms_));
+                launch("tile_adj:L" + std::to_string(j1), (double)a.G * n0 * n1 * (sizeof(cx<T>) + sizeof(T)), st,
+                       [&] { kern<<<(unsigned)grid, dim3(32, threads / 32), smem, st>>>(a); });
+            }
+            tile(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), 0, j1, B, L, nullptr, L, L, 0, 0, nullptr, "o1_bwd", st, L,
+                 static_cast<const T*>(gs1), static_cast<cx<T>*>(gu0), R);
+        } else {
+            if (!gu1) throw std::runtime_error("order1_backward: gu1 is required at the streaming level");
+            const size_t G = (size_t)B * L;
+            cx<T>* Y = static_cast<cx<T>*>(ws);
+            cx<T>* GX = Y + G * fsize(j1);
+            const T sc1 = T(1) / (T(n0) * T(n1));
+            row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), Y, 0, j1, B, L, sc1, st);
+            row_prod(static_cast<const cx<T>*>(gu1), nullptr, nullptr, GX, j1, j1, B * L, 1, T(1), st);
+            {
+                BwdColArgs<T> a{};
+                a.Y = Y; a.GX = GX; a.out = Y; a.n1 = n1; a.tw = tw(lev_[j1].a0);
+                const size_t smem = ((size_t)2 * n0 * kSLP + n0) * sizeof(cx<T>);
+                dim3 grid((unsigned)G, n1 / kSLines);
+                launch("bwd_col:L" + std::to_string(j1), 3.0 * G * n0 * n1 * sizeof(cx<T>), st,
+                       [&] { bwd_col_lookup<T>(n0)<<<grid, dim3(16, kBwdThreads / 16), smem, st>>>(a); });
+            }
+            {
+                BwdRowArgs<T> a{};
+                a.GV = Y; a.filt = psi_ptrs(j1, 0); a.gU0 = static_cast<cx<T>*>(gu0); a.n0 = n0; a.NF = L; a.scale = sc1;
+                a.tw = tw(lev_[j1].a1);
+                const size_t smem = ((size_t)n1 * kSLP + n1) * sizeof(cx<T>);
+                dim3 grid((unsigned)B, ceil_div(n0, kSLines));
+                launch("bwd_row:L" + std::to_string(j1), (double)(G + 2.0 * B) * n0 * n1 * sizeof(cx<T>), st,
+                       [&] { bwd_row_lookup<T>(n1)<<<grid, dim3(16, kBwdThreads / 16), smem, st>>>(a); });
+            }
+        }
     }
 
 private:
@@ -521,6 +632,7 @@ private:
             a.plan0 = lev_[J].a0.plan; a.plan1 = lev_[J].a1.plan;
             a.tw0 = tw(lev_[J].a0); a.tw1 = tw(lev_[J].a1); a.pos0 = pos(lev_[J].a0); a.pos1 = pos(lev_[J].a1);
             a.row_folded = row_folded ? 1 : 0;
+            a.peers = peers_;
             const double G = (double)B * PP;
             launch("lowpass:L" + std::to_string(res) + ":G" + std::to_string(PP),
                    G * a.P0 * a.P1 * sizeof(cx<T>) + (double)a.P0 * a.P1 * sizeof(T) + G * o0_ * o1_ * sizeof(T), st,
@@ -542,6 +654,7 @@ private:
             CropArgs<T> ca{};
             ca.in = tmp; ca.out = out; ca.m0 = m0_; ca.m1 = m1_; ca.PP = PP; ca.NF = NF; ca.ch0 = ch0; ca.chs = chs;
             ca.K = K_;
+            ca.peers = peers_;
             dim3 g2((unsigned)G, ceil_div(o0_ * o1_, 256));
             launch("crop_real", (double)G * (m0_ * m1_ * sizeof(cx<T>) + o0_ * o1_ * sizeof(T)), st,
                    [&] { k2d_crop_real<T><<<g2, 256, 0, st>>>(ca); });
@@ -556,10 +669,11 @@ private:
     // modulus, spatial low-pass to `out`, optional fft2 to `spec_out`
     void tile(const cx<T>* parent, const T* const* filt, const int2* supp, int parent_res, int res, int Bp, int NF,
               T* out, int PP, int NFch, int ch0, int chs, cx<T>* spec_out, const char* what, cudaStream_t st,
-              int Kstride = -1, const T* gout = nullptr, cx<T>* gparent = nullptr) {
+              int Kstride = -1, const T* gout = nullptr, cx<T>* gparent = nullptr, const T* radd = nullptr) {
         TileArgs<T> a{};
         a.parent = parent; a.filt = filt; a.supp = supp; a.spec_out = spec_out; a.out = out;
-        a.gout = gout; a.gparent = gparent;
+        a.gout = gout; a.gparent = gparent; a.radd = radd;
+        if (out) a.peers = peers_;
         a.P0 = lev_[parent_res].a0.n; a.P1 = lev_[parent_res].a1.n;
         a.k = 1 << (res - parent_res);
         a.n0 = lev_[res].a0.n; a.n1 = lev_[res].a1.n; a.W = a.n1 | 1; a.NF = NF;
@@ -755,6 +869,9 @@ private:
     unsigned char* cbuf_ = nullptr;
     bool bound_ = false;
     int last_B_ = 1;
+    OutPeers<T> peers_{};                 // peer destinations of the chunk being processed (forward_peers)
+    T* peer_base_[kMaxPeers] = {};
+    int n_peer_base_ = 0;
 };
 
 }  // namespace sb

@@ -102,12 +102,37 @@ int scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, voi
         plan->forward(x_dev, out_dev, workspace_dev, workspace_bytes, batch, static_cast<cudaStream_t>(stream));
     });
 }
+int scat_plan2d_forward_peers(scat_plan2d* plan, const void* x_dev, void* out_dev, void* const* peer_out_dev, int32_t n_peers,
+                              void* ws_dev, size_t ws_bytes, int64_t batch, void* stream) {
+    return guarded([&] {
+        if (!plan) throw std::runtime_error("null plan");
+        plan->forward_peers(x_dev, out_dev, peer_out_dev, n_peers, ws_dev, ws_bytes, batch, static_cast<cudaStream_t>(stream));
+    });
+}
 
 int32_t scat_plan2d_order2_channels(const scat_plan2d* plan, int32_t j1) { return plan ? plan->order2_channels(j1) : 0; }
 int scat_plan2d_order2_forward(scat_plan2d* plan, int32_t j1, const void* u1_dev, void* out_dev, int64_t batch, void* stream) {
     return guarded([&] {
         if (!plan) throw std::runtime_error("null plan");
         plan->order2_forward(j1, u1_dev, out_dev, batch, static_cast<cudaStream_t>(stream));
+    });
+}
+int32_t scat_plan2d_order1_mode(const scat_plan2d* plan, int32_t j1) { return plan ? plan->order1_mode(j1) : 0; }
+size_t scat_plan2d_order1_workspace_bytes(const scat_plan2d* plan, int32_t j1, int64_t batch) {
+    return plan ? plan->order1_workspace_bytes(j1, batch) : 0;
+}
+int scat_plan2d_order1_forward(scat_plan2d* plan, int32_t j1, const void* u0_dev, void* s1_dev, void* u1_dev, int64_t batch,
+                               void* stream) {
+    return guarded([&] {
+        if (!plan) throw std::runtime_error("null plan");
+        plan->order1_forward(j1, u0_dev, s1_dev, u1_dev, batch, static_cast<cudaStream_t>(stream));
+    });
+}
+int scat_plan2d_order1_backward(scat_plan2d* plan, int32_t j1, const void* u0_dev, const void* gs1_dev, const void* gu1_dev,
+                                void* gu0_dev, void* ws_dev, size_t ws_bytes, int64_t batch, void* stream) {
+    return guarded([&] {
+        if (!plan) throw std::runtime_error("null plan");
+        plan->order1_backward(j1, u0_dev, gs1_dev, gu1_dev, gu0_dev, ws_dev, ws_bytes, batch, static_cast<cudaStream_t>(stream));
     });
 }
 int scat_plan2d_order2_backward(scat_plan2d* plan, int32_t j1, const void* u1_dev, const void* gout_dev, void* gu1_dev,

@@ -63,7 +63,10 @@ template <typename T> struct TileArgs {
                                            // of the persistent CTAs do not all coincide
     // backward kernel only: gradient w.r.t. the output planes (same layout / channel mapping as `out`) and the
     // parent-gradient accumulator [NPAR][P0][P1] (atomically added to; zeroed by the caller)
+    OutPeers<T> peers;                     // additional destinations of the output planes (peer GPUs), see kernels2d.cuh
     const T* gout; cx<T>* gparent;
+    // backward of a path WITH children: R = Re(F^H gU1) per path in storage order (k2d_tile_adj, bwd2d.cuh), added to gA
+    const T* radd;
     // two-half leaf kernel only (tile2h.cuh): twiddles / scramble table of the half-length column transform and the
     // [cnt][4] tap tables of the shift-invariant low-pass
     const cx<T>* twh; const int* posh; const T* TT0; const T* TT1;
@@ -462,7 +465,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             __syncthreads();
             // 4b on tensor cores: S = G0s^T * W1; warp task = (16 output rows, 8 output columns)
             {
-                float* ob = reinterpret_cast<float*>(a.out) + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+                const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
                 const int mt = (a.o0p + 15) >> 4, ntl = (a.o1p + 7) >> 3;
                 for (int task = wid; task < mt * ntl; task += nwarp) {
                     const int m0 = (task / ntl) * 16, c0 = (task % ntl) * 8;
@@ -538,7 +541,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             // 4b (tap tables). S[yo][xo] = sum_y g0[kl (yo+1) - y] * (w1[0] + w1[1])[row(y)][xo]; the y window is split in two
             //   work items as well: the second half leaves its partial sums in shared memory, the first adds them and stores
             {
-                T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+                const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
                 const int ygroups = a.o0p >> 2, nitem = ygroups * a.o1p;
                 const T* w1b = m.w1 + N0 * wp;
                 const int g0 = (a.y0cnt + 1) >> 1;
@@ -625,7 +628,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
         // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
         //     S[yo][xo] = sum_y G0[y][yo] * w1[row(y)][xo]; 4 output rows per thread, lanes along xo
         {
-            T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+            const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
             const int ygroups = a.o0p >> 2;
             for (int it = tid; it < ygroups * a.o1p; it += nt) {
                 const int yg = it / a.o1p, xo = it - yg * a.o1p;
@@ -778,7 +781,9 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             T gA = T(0);
             const int2 rng = m.xr[x];
             for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gr[xo];
-            const int idx = q * W + (ST ? m.pos1[x] : x);
+            const int xs = ST ? m.pos1[x] : x;
+            if (a.radd) gA += a.radd[(size_t)g * n0 * n1 + q * n1 + xs];
+            const int idx = q * W + xs;
             const cx<T> v = s[idx];
             const T mag = sqrt(v.x * v.x + v.y * v.y);
             const T sc = mag > T(0) ? gA / mag : T(0);

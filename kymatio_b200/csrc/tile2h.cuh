@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kTile2hMaxThreads, 2) k2d_tile2h(TileArgs<T> a
         if (tid < ygroups * a.o1p) {
             const int yg = tid / a.o1p, xo = tid - yg * a.o1p;
             if (xo < a.o1) {
-                T* ob = a.out + ((size_t)b * a.K + ch) * a.o0 * a.o1;
+                const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
                 const int yo = 4 * yg;
                 if (yo + 0 < a.o0) ob[(yo + 0) * a.o1 + xo] = acc0;
                 if (yo + 1 < a.o0) ob[(yo + 1) * a.o1 + xo] = acc1;

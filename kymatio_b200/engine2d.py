@@ -6,6 +6,7 @@ allocates) and re-binds the filters whenever the frontend's buffers change
 (kymatio/scattering2d/frontend/torch_frontend.py:48-70 re-reads them on every call).
 """
 import ctypes
+import os
 
 import torch
 
@@ -82,18 +83,31 @@ class Engine2D:
         with torch.cuda.device(self.device):
             return torch.empty(need, dtype=torch.uint8, device=self.device)
 
-    def forward(self, x):
-        """x: (B, M, N) contiguous on self.device -> (B, K, out_h, out_w)."""
+    def forward(self, x, out=None, peer_ptrs=None):
+        """x: (B, M, N) contiguous on self.device -> (B, K, out_h, out_w).
+
+        out: optional preallocated contiguous result tensor (e.g. this rank's block of a symmetric-memory buffer);
+        peer_ptrs: device addresses of the SAME block inside the output tensors of peer GPUs - every coefficient plane is
+        then stored there as well by the kernels that produce it (scat_plan2d_forward_peers)."""
         B = x.shape[0]
-        out = torch.empty((B, self.K, self.out_h, self.out_w), dtype=self.dtype, device=self.device)
+        if out is None:
+            out = torch.empty((B, self.K, self.out_h, self.out_w), dtype=self.dtype, device=self.device)
+        elif tuple(out.shape) != (B, self.K, self.out_h, self.out_w) or not out.is_contiguous() or out.dtype != self.dtype:
+            raise ValueError("out must be a contiguous (B, K, out_h, out_w) tensor of the engine's dtype")
         if B == 0:
             return out
         ws = self.workspace(B)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.scat_plan2d_forward(
-                self._plan, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), B,
-                ctypes.c_void_p(stream)))
+            if peer_ptrs:
+                arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+                _lib.check(self.lib.scat_plan2d_forward_peers(
+                    self._plan, x.data_ptr(), out.data_ptr(), arr, len(peer_ptrs), ws.data_ptr(), ws.numel(), B,
+                    ctypes.c_void_p(stream)))
+            else:
+                _lib.check(self.lib.scat_plan2d_forward(
+                    self._plan, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), B,
+                    ctypes.c_void_p(stream)))
         return out
 
     # -- second-order block (autograd building block) --------------------------------------
@@ -116,12 +130,45 @@ class Engine2D:
                                                             gu1.data_ptr(), int(batch), ctypes.c_void_p(stream)))
         return gu1
 
+    # -- first-order block (autograd building block) ----------------------------------------
+    def order1_mode(self, j1):
+        """0: not fused; 1: tile level (S1 and U1 from one kernel); 2: streaming level (U1 only)."""
+        if os.environ.get("SCAT_B200_ORDER1_FUSED", "1") == "0":
+            return 0
+        return int(self.lib.scat_plan2d_order1_mode(self._plan, int(j1)))
+
+    def order1_forward(self, j1, u0, batch, want_u1):
+        """u0: (batch, Mp, Np, 2) -> (S1 (batch, L, oh, ow) or None, U1 (batch*L, n0, n1, 2) or None)."""
+        mode, L = self.order1_mode(j1), self.geometry["L"]
+        n0, n1 = self.Mp >> j1, self.Np >> j1
+        s1 = torch.empty((batch, L, self.out_h, self.out_w), dtype=self.dtype, device=self.device) if mode == 1 else None
+        u1 = torch.empty((batch * L, n0, n1, 2), dtype=self.dtype, device=self.device) if (want_u1 or mode == 2) else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_order1_forward(
+                self._plan, int(j1), u0.data_ptr(), s1.data_ptr() if s1 is not None else None,
+                u1.data_ptr() if u1 is not None else None, int(batch), ctypes.c_void_p(stream)))
+        return s1, u1
+
+    def order1_backward(self, j1, u0, gs1, gu1, batch):
+        """-> gradient w.r.t. u0, (batch, Mp, Np, 2)."""
+        gu0 = torch.zeros_like(u0)
+        need = self.lib.scat_plan2d_order1_workspace_bytes(self._plan, int(j1), int(batch))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.scat_plan2d_order1_backward(
+                self._plan, int(j1), u0.data_ptr(), gs1.data_ptr() if gs1 is not None else None,
+                gu1.data_ptr() if gu1 is not None else None, gu0.data_ptr(), ws.data_ptr(), ws.numel(), int(batch),
+                ctypes.c_void_p(stream)))
+        return gu0
+
     # -- backward --------------------------------------------------------------------
     def backward(self, x, grad_out):
         """Gradient of ``forward`` w.r.t. x: the cascade is recomputed on differentiable ops whose forward and
         adjoint kernels are this library's own (ops2d.py) and back-propagated; processed in batch chunks to
         bound the memory of the recomputed intermediates."""
-        from .ops2d import eager_scattering2d
+        from .ops2d import eager_scattering2d, _Recompute
         g = self.geometry
         phi, psi = self._filters
         pads = None
@@ -134,7 +181,11 @@ class Engine2D:
         for b0 in range(0, x.shape[0], chunk):
             with torch.enable_grad():
                 xc = x[b0:b0 + chunk].detach().requires_grad_(True)
-                y = eager_scattering2d(xc, g["J"], g["L"], g["max_order"], pads, phi, psi, eng=self)
+                _Recompute.active = True
+                try:
+                    y = eager_scattering2d(xc, g["J"], g["L"], g["max_order"], pads, phi, psi, eng=self)
+                finally:
+                    _Recompute.active = False
                 gx[b0:b0 + chunk] = torch.autograd.grad(y, xc, grad_out[b0:b0 + chunk])[0]
         return gx
 

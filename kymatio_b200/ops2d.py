@@ -172,6 +172,13 @@ class PadReflect(torch.autograd.Function):
         return gx, None
 
 
+class _Recompute:
+    """Set while Engine2D.backward re-runs the cascade only to rebuild the autograd graph: the VALUES of the leaf outputs
+    are then never read (their gradients come from the caller), so operators whose backward does not need their own
+    forward result skip the forward kernels."""
+    active = False
+
+
 class Order2(torch.autograd.Function):
     """All second-order paths below first-order scale j1, fused: U1 (B*L, n0, n1, 2) -> (B, C2, o0, o1).
     Forward and backward are one tile-kernel launch per (j1, j2) pair (csrc/tile2d.cuh)."""
@@ -181,12 +188,57 @@ class Order2(torch.autograd.Function):
         U1 = U1.contiguous()
         ctx.eng, ctx.j1, ctx.batch = eng, j1, batch
         ctx.save_for_backward(U1)
+        if _Recompute.active:       # graph rebuild: the second-order outputs are not needed, only their gradients are
+            return U1.new_empty((batch, eng.order2_channels(j1), eng.out_h, eng.out_w))
         return eng.order2_forward(j1, U1, batch)
 
     @staticmethod
     def backward(ctx, g):
         (U1,) = ctx.saved_tensors
         return ctx.eng.order2_backward(ctx.j1, U1, g.contiguous(), ctx.batch), None, None, None
+
+
+class Order1Tile(torch.autograd.Function):
+    """First-order block of a scale whose field fits one CTA, fused: U0 (B, Mp, Np, 2) -> S1 (B, L, oh, ow) and, for
+    scales with children, U1 (B*L, n0, n1, 2).  Forward = the tile kernel of the forward engine; backward = k2d_tile_adj
+    (Re F^H gU1) + the backward tile (recompute u, low-pass adjoint, modulus backward, forward transform, scatter into gU0)."""
+
+    @staticmethod
+    def forward(ctx, U0, eng, j1, batch, want_u1):
+        U0 = U0.contiguous()
+        ctx.eng, ctx.j1, ctx.batch, ctx.want_u1 = eng, j1, batch, want_u1
+        ctx.save_for_backward(U0)
+        s1, u1 = eng.order1_forward(j1, U0, batch, want_u1)
+        if not want_u1:
+            u1 = U0.new_zeros((0,))
+        ctx.mark_non_differentiable(*(() if want_u1 else (u1,)))
+        return s1, u1
+
+    @staticmethod
+    def backward(ctx, gs1, gu1):
+        (U0,) = ctx.saved_tensors
+        gs1 = gs1.contiguous() if gs1 is not None else torch.zeros(
+            (ctx.batch, ctx.eng.geometry["L"], ctx.eng.out_h, ctx.eng.out_w), dtype=U0.dtype, device=U0.device)
+        gu1 = gu1.contiguous() if (ctx.want_u1 and gu1 is not None) else None
+        return ctx.eng.order1_backward(ctx.j1, U0, gs1, gu1, ctx.batch), None, None, None, None
+
+
+class Order1Stream(torch.autograd.Function):
+    """First-order block at full resolution (streaming chain), fused: U0 -> U1 (B*L, n0, n1, 2).  Backward = mirrored
+    chain: row passes of the recomputed product and of gU1, one fused column kernel, one row kernel that reduces over
+    the angles (csrc/bwd2d.cuh)."""
+
+    @staticmethod
+    def forward(ctx, U0, eng, j1, batch):
+        U0 = U0.contiguous()
+        ctx.eng, ctx.j1, ctx.batch = eng, j1, batch
+        ctx.save_for_backward(U0)
+        return eng.order1_forward(j1, U0, batch, True)[1]
+
+    @staticmethod
+    def backward(ctx, gu1):
+        (U0,) = ctx.saved_tensors
+        return ctx.eng.order1_backward(ctx.j1, U0, None, gu1.contiguous(), ctx.batch), None, None, None
 
 
 def _to_complex(x):
@@ -200,14 +252,29 @@ def _low(U, phi_level, k):
     return Fft2.apply(Z, True)[..., 1:-1, 1:-1, 0]
 
 
+def _order2_per_op(U1, psi, phi, j1, J, L, B):
+    """All second-order paths below first-order scale j1 on the per-primitive differentiable ops (core:55-83)."""
+    per_j2 = []
+    for j2 in range(j1 + 1, J):
+        V2 = FilterBank.apply(U1, psi[j2][j1])
+        V2 = Periodize.apply(V2.reshape((B * L * L,) + tuple(V2.shape[2:])), 2 ** (j2 - j1))
+        A2 = Modulus.apply(Fft2.apply(V2, True))
+        U2 = Fft2.apply(_to_complex(A2), False)
+        s2 = _low(U2, phi[j2], 2 ** (J - j2))
+        per_j2.append(s2.reshape((B, L, 1, L) + tuple(s2.shape[1:])))
+    s2 = torch.cat(per_j2, dim=2)                           # (B, theta1, j2, theta2, o0, o1)
+    return s2.reshape((B, -1) + tuple(s2.shape[4:]))
+
+
 def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=None):
     """Angle-batched restatement of kymatio/scattering2d/core/scattering2d.py:14-86 on differentiable ops.
 
     x: (B, M, N) CUDA; pads: (top, bottom, left, right) or None when pre-padded;
     phi_levels: J tensors (n0, n1[, 1]); psi_levels: flattened in registration order.
     Returns (B, K, M/2^J, N/2^J) in the reference's channel order.
-    With ``eng`` (an Engine2D bound to the same filters) the second-order block of every first-order scale
-    runs as the fused tile kernels (forward and backward); orders 0 and 1 stay on the per-op graph.
+    With ``eng`` (an Engine2D bound to the same filters) the first-order block of every scale (Order1Tile / Order1Stream)
+    and the second-order block below it (Order2) run as fused kernels, forward and backward; what remains on the
+    per-primitive graph acts on ONE field per image (pad, U0, S0) or on the small low-pass of the full-resolution scale.
     """
     B = x.shape[0]
     phi = [p.reshape(p.shape[0], p.shape[1]) for p in phi_levels]
@@ -227,6 +294,23 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=Non
     S0 = _low(U0, phi[0], 2 ** J)[:, None]
     S1, S2 = [], []
     for j1 in range(J):
+        has_children = max_order >= 2 and j1 < J - 1
+        mode = eng.order1_mode(j1) if eng is not None else 0
+        if mode:
+            # fused first-order block (forward and backward): see Order1Tile / Order1Stream
+            if mode == 1:
+                s1, U1 = Order1Tile.apply(U0, eng, j1, B, has_children)
+            else:
+                U1 = Order1Stream.apply(U0, eng, j1, B)
+                s1 = _low(U1, phi[j1], 2 ** (J - j1))
+                s1 = s1.reshape((B, L) + tuple(s1.shape[1:]))
+            S1.append(s1)
+            if has_children:
+                if eng.order2_channels(j1) > 0:
+                    S2.append(Order2.apply(U1, eng, j1, B))
+                else:
+                    S2.append(_order2_per_op(U1, psi, phi, j1, J, L, B))
+            continue
         # the 1/N of the inverse transform is folded into the (small) filter tensor: the transform itself then runs
         # unnormalised in both directions of the graph, without a scaling pass over the full-size fields
         n_j1 = (U0.shape[1] >> j1) * (U0.shape[2] >> j1)
@@ -241,14 +325,5 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=Non
         if eng is not None and eng.order2_channels(j1) > 0:
             S2.append(Order2.apply(U1, eng, j1, B))         # fused second-order block (forward and backward)
             continue
-        per_j2 = []
-        for j2 in range(j1 + 1, J):
-            V2 = FilterBank.apply(U1, psi[j2][j1])
-            V2 = Periodize.apply(V2.reshape((B * L * L,) + tuple(V2.shape[2:])), 2 ** (j2 - j1))
-            A2 = Modulus.apply(Fft2.apply(V2, True))
-            U2 = Fft2.apply(_to_complex(A2), False)
-            s2 = _low(U2, phi[j2], 2 ** (J - j2))
-            per_j2.append(s2.reshape((B, L, 1, L) + tuple(s2.shape[1:])))
-        s2 = torch.cat(per_j2, dim=2)                       # (B, theta1, j2, theta2, o0, o1)
-        S2.append(s2.reshape((B, -1) + tuple(s2.shape[4:])))
+        S2.append(_order2_per_op(U1, psi, phi, j1, J, L, B))
     return torch.cat([S0] + S1 + S2, dim=1)

@@ -10,7 +10,7 @@ on every rank; its backward is the matching reduce-scatter.
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_batch", "gather_batch", "ShardedScattering"]
+__all__ = ["shard_bounds", "shard_batch", "gather_batch", "ShardedScattering", "PeerGatherScattering"]
 
 
 def shard_bounds(n, rank, world):
@@ -98,3 +98,62 @@ class ShardedScattering(torch.nn.Module):
             local, total = shard_batch(x, group=self.group).contiguous(), x.shape[0]
         y = self.scattering(local)
         return gather_batch(y, total, self.group) if self.gather else y
+
+
+class PeerGatherScattering(torch.nn.Module):
+    """Batch-sharded 2-D scattering whose all-gather is FUSED into the kernels that produce the coefficients.
+
+    Every rank owns a (total_batch, K, oh, ow) result buffer in symmetric memory (torch.distributed._symmetric_memory:
+    each rank's buffer is mapped into every other rank's address space over NVLink / NVSwitch).  A rank transforms its
+    slice of the batch with ``scat_plan2d_forward_peers``: the low-pass stages of the tile kernels store every coefficient
+    plane into the rank's own buffer AND into the same block of every peer's buffer (remote stores over NVLink, a few KB
+    per path, issued while the SMs are busy with the next paths).  One cross-rank barrier later every rank holds the full
+    tensor - there is no separate gather pass over the 227 MB per rank that NCCL's all_gather would read again.
+    No-grad / inference path (``ShardedScattering`` keeps the differentiable NCCL gather); float32; ``scattering`` is a
+    ``kymatio_b200.Scattering2D``.  Two buffers alternate so that a rank may still read step i while step i+1 is written.
+    """
+
+    def __init__(self, scattering, group=None):
+        super().__init__()
+        self.scattering, self.group = scattering, group
+        self._bufs, self._hdls, self._step = {}, {}, 0
+
+    def _buffers(self, total, eng, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (total, eng.K, eng.out_h, eng.out_w, device.index)
+        if key not in self._bufs:
+            group = self.group if self.group is not None else dist.group.WORLD
+            bufs, hdls = [], []
+            for _ in range(2):
+                t = symm_mem.empty((total, eng.K, eng.out_h, eng.out_w), dtype=torch.float32, device=device)
+                hdls.append(symm_mem.rendezvous(t, group))
+                bufs.append(t)
+            self._bufs[key], self._hdls[key] = bufs, hdls
+        return self._bufs[key], self._hdls[key]
+
+    @torch.no_grad()
+    def forward(self, x_local, total=None):
+        """x_local: this rank's contiguous slice (shard_bounds) of the batch -> the full (total, K, oh, ow) tensor."""
+        S = self.scattering
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return S(x_local)
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if total is None:
+            t = torch.tensor([x_local.shape[0]], device=x_local.device, dtype=torch.int64)
+            dist.all_reduce(t, group=self.group)
+            total = int(t.item())
+        lo, hi = shard_bounds(total, rank, world)
+        assert x_local.shape[0] == hi - lo, "local batch does not match shard_bounds"
+        x = x_local.reshape((-1,) + tuple(x_local.shape[-2:])).contiguous()
+        eng = S._engine(x.dtype, x.device)
+        phi, psi = S.load_filters()
+        eng.bind(phi, psi)
+        bufs, hdls = self._buffers(total, eng, x.device)
+        i = self._step & 1
+        self._step += 1
+        buf, hdl = bufs[i], hdls[i]
+        block = eng.K * eng.out_h * eng.out_w * 4
+        peers = [int(hdl.buffer_ptrs[r]) + lo * block for r in range(world) if r != rank]
+        eng.forward(x, out=buf[lo:hi], peer_ptrs=peers)
+        hdl.barrier(channel=0)          # every rank's kernels (and their remote stores) have completed
+        return buf
