@@ -502,14 +502,14 @@ def run_b200_arm(args):
         if world > 1:
             from kymatio_b200.parallel import gather_batch
             yfull = None
-            for _ in range(2):
+            for _ in range(5):          # NCCL sets its channels up lazily over the first calls
                 yfull = gather_batch(S(x), world * B)
             barrier()
-            g_ms, _ = timed_steps(lambda: gather_batch(S(x), world * B), max(3, args.steps // 4), flush)
-            p_ms, _ = timed_steps(lambda: S(x), max(3, args.steps // 4), flush)
+            g_ms, _ = timed_steps(lambda: gather_batch(S(x), world * B), max(5, args.steps // 2), flush)
+            p_ms, _ = timed_steps(lambda: S(x), max(5, args.steps // 2), flush)
             gt = torch.tensor([g_ms, p_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-            nst = max(3, args.steps // 4)
+            nst = max(5, args.steps // 2)
             gather = {"ms_per_step_with_gather": float(gt[0]) / nst, "ms_per_step_local_only": float(gt[1]) / nst,
                       "gather_ms": (float(gt[0]) - float(gt[1])) / nst,
                       "gathered_bytes_per_rank": int(yfull.numel() * 4),

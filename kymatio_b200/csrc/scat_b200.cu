@@ -16,6 +16,21 @@ template <typename F> int guarded(F&& f) {
 }
 }  // namespace
 
+// grid.y / grid.z are capped at 65535: entry points that put the batch there split larger batches into slices
+constexpr int64_t kMaxGridYZ = 65535;
+static inline size_t esize(int32_t dtype) { return dtype == 1 ? 8 : 4; }
+static inline const void* at(const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; }
+static inline void* at(void* p, size_t bytes) { return p ? static_cast<char*>(p) + bytes : nullptr; }
+#define SB_SPLIT_BATCH(B, CALL)                                                        \
+    if ((B) > kMaxGridYZ) {                                                            \
+        for (int64_t b0 = 0; b0 < (B); b0 += kMaxGridYZ) {                             \
+            const int64_t nb = std::min<int64_t>(kMaxGridYZ, (B) - b0);                \
+            const int rc = (CALL);                                                     \
+            if (rc) return rc;                                                         \
+        }                                                                              \
+        return 0;                                                                      \
+    }
+
 extern "C" {
 
 int scat_version(void) { return 100; }
@@ -168,6 +183,9 @@ int scat_fft2d_exec(const void* const_dev, const void* in_dev, void* out_dev, in
 }
 int scat_pad2d(const void* x_dev, void* out_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
                int32_t left, int32_t right, int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(B, scat_pad2d(at(x_dev, (size_t)b0 * M * N * esize(dtype)),
+                                 at(out_dev, (size_t)b0 * (M + top + bottom) * (N + left + right) * esize(dtype)), nb, M, N, top,
+                                 bottom, left, right, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const int P0 = M + top + bottom, P1 = N + left + right;
@@ -192,6 +210,9 @@ int scat_cdgmm(const void* a_dev, const void* b_dev, void* out_dev, int64_t batc
 }
 int scat_subsample_fourier2d(const void* in_dev, void* out_dev, int64_t G, int32_t n0, int32_t n1, int32_t k,
                              int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(G, scat_subsample_fourier2d(at(in_dev, (size_t)b0 * n0 * n1 * 2 * esize(dtype)),
+                                               at(out_dev, (size_t)b0 * (n0 / std::max(k, 1)) * (n1 / std::max(k, 1)) * 2 * esize(dtype)),
+                                               nb, n0, n1, k, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (k < 1 || n0 % k || n1 % k) throw std::runtime_error("subsample_fourier: k must divide both sizes");
@@ -249,6 +270,9 @@ int scat_fft1d_exec(const void* const_dev, const void* in_dev, void* tmp_dev, vo
 }
 int scat_pad1d(const void* x_dev, void* out_dev, int64_t G, int32_t N, int32_t pad_left, int32_t pad_right,
                int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(G, scat_pad1d(at(x_dev, (size_t)b0 * N * esize(dtype)),
+                                 at(out_dev, (size_t)b0 * (N + pad_left + pad_right) * esize(dtype)), nb, N, pad_left, pad_right,
+                                 dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const int P = N + pad_left + pad_right;
@@ -261,6 +285,9 @@ int scat_pad1d(const void* x_dev, void* out_dev, int64_t G, int32_t N, int32_t p
 }
 int scat_subsample_fourier1d(const void* in_dev, void* out_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
                              void* stream) {
+    SB_SPLIT_BATCH(G, scat_subsample_fourier1d(at(in_dev, (size_t)b0 * N * 2 * esize(dtype)),
+                                               at(out_dev, (size_t)b0 * (N / std::max(k, 1)) * 2 * esize(dtype)), nb, N, k, dtype,
+                                               stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (k < 1 || N % k) throw std::runtime_error("subsample_fourier: k must divide the length");
@@ -301,6 +328,8 @@ int scat_modulus_rotation(const void* x_dev, const void* prev_dev, void* out_dev
 }
 int scat_compute_integrals(const void* x_dev, void* out_f64_dev, int64_t B, int64_t n, const void* powers_f32_dev,
                            int32_t P, int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(B, scat_compute_integrals(at(x_dev, (size_t)b0 * n * esize(dtype)), at(out_f64_dev, (size_t)b0 * P * sizeof(double)),
+                                             nb, n, powers_f32_dev, P, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (P < 1 || P > 8) throw std::runtime_error("compute_integrals supports 1..8 powers");
@@ -333,6 +362,8 @@ int scat_cdgmm_bcast(const void* a_dev, const void* w_dev, void* out_dev, int64_
 }
 int scat_subsample_fourier2d_bwd(const void* gout_dev, void* gin_dev, int64_t G, int32_t n0, int32_t n1, int32_t k,
                                  int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(G, scat_subsample_fourier2d_bwd(at(gout_dev, (size_t)b0 * (n0 / std::max(k, 1)) * (n1 / std::max(k, 1)) * 2 * esize(dtype)),
+                                                   at(gin_dev, (size_t)b0 * n0 * n1 * 2 * esize(dtype)), nb, n0, n1, k, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (k < 1 || n0 % k || n1 % k) throw std::runtime_error("subsample_fourier: k must divide both sizes");
@@ -355,6 +386,8 @@ int scat_modulus_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t
 }
 int scat_pad2d_bwd(const void* gout_dev, void* gx_dev, int64_t B, int32_t M, int32_t N, int32_t top, int32_t bottom,
                    int32_t left, int32_t right, int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(B, scat_pad2d_bwd(at(gout_dev, (size_t)b0 * (M + top + bottom) * (N + left + right) * esize(dtype)),
+                                     at(gx_dev, (size_t)b0 * M * N * esize(dtype)), nb, M, N, top, bottom, left, right, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const int P0 = M + top + bottom, P1 = N + left + right;
@@ -460,6 +493,8 @@ int scat3d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int
 // ---------------------------------------------------------------- adjoints of the 1-D / 3-D eager primitives
 int scat_subsample_fourier1d_bwd(const void* gout_dev, void* gin_dev, int64_t G, int32_t N, int32_t k, int32_t dtype,
                                  void* stream) {
+    SB_SPLIT_BATCH(G, scat_subsample_fourier1d_bwd(at(gout_dev, (size_t)b0 * (N / std::max(k, 1)) * 2 * esize(dtype)),
+                                                   at(gin_dev, (size_t)b0 * N * 2 * esize(dtype)), nb, N, k, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (k < 1 || N % k) throw std::runtime_error("subsample_fourier: k must divide the length");
@@ -484,6 +519,8 @@ int scat_modulus_rotation_bwd(const void* x_dev, const void* prev_dev, const voi
 }
 int scat_compute_integrals_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t B, int64_t n,
                                const void* powers_f32_dev, int32_t P, int32_t dtype, void* stream) {
+    SB_SPLIT_BATCH(B, scat_compute_integrals_bwd(at(x_dev, (size_t)b0 * n * esize(dtype)), at(g_dev, (size_t)b0 * P * esize(dtype)),
+                                                 at(gx_dev, (size_t)b0 * n * esize(dtype)), nb, n, powers_f32_dev, P, dtype, stream))
     return guarded([&] {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (B <= 0 || n <= 0) return;

@@ -64,7 +64,8 @@ class _AllGatherBatch(torch.autograd.Function):
             out = grad.new_empty((hi - lo,) + tuple(grad.shape[1:]))
             dist.reduce_scatter_tensor(out, grad, op=dist.ReduceOp.SUM, group=group)
             return out, None, None
-        # gloo (CPU tests) / uneven shards: all-reduce then slice
+        # gloo (CPU tests) / uneven shards: all-reduce then slice (on a copy: `grad` may be the caller's own tensor)
+        grad = grad.clone()
         dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
         return grad[lo:hi].clone(), None, None
 
@@ -118,7 +119,7 @@ class PeerGatherScattering(torch.nn.Module):
         self.scattering, self.group = scattering, group
         self._bufs, self._hdls, self._step = {}, {}, 0
 
-    def _buffers(self, total, eng, device):
+    def _symm_buffers(self, total, eng, device):
         import torch.distributed._symmetric_memory as symm_mem
         key = (total, eng.K, eng.out_h, eng.out_w, device.index)
         if key not in self._bufs:
@@ -148,7 +149,7 @@ class PeerGatherScattering(torch.nn.Module):
         eng = S._engine(x.dtype, x.device)
         phi, psi = S.load_filters()
         eng.bind(phi, psi)
-        bufs, hdls = self._buffers(total, eng, x.device)
+        bufs, hdls = self._symm_buffers(total, eng, x.device)
         i = self._step & 1
         self._step += 1
         buf, hdl = bufs[i], hdls[i]

@@ -52,11 +52,11 @@ class Scattering2D(nn.Module):
         # torch_frontend.py:23-43: phi levels first, then psi in list order; (m, n, 1) buffers
         n = 0
         for level in self.phi["levels"]:
-            self.register_buffer("tensor" + str(n), torch.from_numpy(level).unsqueeze(-1))
+            self.register_buffer("tensor" + str(n), torch.from_numpy(level).clone().unsqueeze(-1))   # own copy: the bank is cached
             n += 1
         for psi in self.psi:
             for level in psi["levels"]:
-                self.register_buffer("tensor" + str(n), torch.from_numpy(level).unsqueeze(-1))
+                self.register_buffer("tensor" + str(n), torch.from_numpy(level).clone().unsqueeze(-1))   # own copy: the bank is cached
                 n += 1
 
     def load_filters(self):
