@@ -530,10 +530,11 @@ def run_b200_arm(args):
                 ft = torch.tensor([f_ms], dtype=torch.float64, device=dev)
                 dist.all_reduce(ft, op=dist.ReduceOp.MAX)
                 ok = bool(torch.equal(yp[rank * B:(rank + 1) * B], S(x)))
-                gather["peer_store"] = {"ms_per_step": float(ft[0]) / nst, "gather_ms": (float(ft[0]) - float(gt[1])) / nst,
+                gather["peer_store"] = {"mode": P.last_mode, "ms_per_step": float(ft[0]) / nst, "gather_ms": (float(ft[0]) - float(gt[1])) / nst,
                                         "images_per_s": world * B * nst / (float(ft[0]) * 1e-3), "own_block_bit_exact": ok,
                                         "what": "every coefficient plane stored by the producing kernel into all ranks' "
-                                                "symmetric-memory buffers (remote stores over NVLink) + one barrier"}
+                                                "symmetric-memory buffers (mode unicast: one remote store per peer; mode "
+                                                "multicast: one multimem.st replicated by the NVSwitch) + one barrier"}
                 del yp, P
             except Exception as e:                      # symmetric memory unavailable on this box / build
                 gather["peer_store"] = {"unavailable": repr(e)[:300]}

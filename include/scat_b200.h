@@ -81,7 +81,9 @@ int  scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, vo
  * output tensors of the peer GPUs (symmetric memory mapped over NVLink).  Batch-sharded ranks that each pass the others'
  * buffers end up with the full (total_batch, K, oh, ow) tensor without a separate all-gather pass; the caller places a
  * cross-rank barrier after the call (kymatio_b200/parallel.py: PeerGatherScattering).  peer_out_dev is a HOST array of
- * device pointers, each already offset to this rank's block. */
+ * device pointers, each already offset to this rank's block.  n_peers == -1: peer_out_dev[0] is the MULTICAST (NVLS)
+ * address of the block; every plane is then stored ONCE with multimem.st and replicated by the NVSwitch into all ranks'
+ * buffers, the caller's own included (out_dev is not written). */
 int  scat_plan2d_forward_peers(scat_plan2d* plan, const void* x_dev, void* out_dev, void* const* peer_out_dev,
                                int32_t n_peers, void* ws_dev, size_t ws_bytes, int64_t batch, void* stream);
 

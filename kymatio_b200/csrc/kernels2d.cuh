@@ -41,12 +41,22 @@ template <typename T> __device__ __forceinline__ T* dyn_smem() {
 // low-pass stores are a few KB per path, so replicating them costs nothing and the all-gather of the batch-sharded
 // result needs no extra pass - the transfer rides on the kernels that produce the coefficients.
 constexpr int kMaxPeers = 7;
+// n >= 0: p[0..n) are the peers' buffers (plain remote stores, one per peer, beside the local store);
+// n == -1: p[0] is the MULTICAST address of the block (NVLS): one multimem.st per value is replicated by the NVSwitch
+//          into every rank's buffer, the caller's own included - 1/8 of the NVLink egress of the unicast form at 8 GPUs.
 template <typename T> struct OutPeers { T* p[kMaxPeers]; int n; };
+__device__ __forceinline__ void multimem_st(float* mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(double* mc, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
 template <typename T> struct OutRef {
     T* out; const OutPeers<T>* pe; size_t off;
     struct Slot {
         const OutRef& r; size_t i;
         __device__ __forceinline__ void operator=(T v) const {
+            if (r.pe->n < 0) { multimem_st(r.pe->p[0] + r.off + i, v); return; }
             r.out[r.off + i] = v;
             for (int k = 0; k < r.pe->n; ++k) r.pe->p[k][r.off + i] = v;
         }

@@ -269,7 +269,7 @@ public:
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int B = (int)std::min<int64_t>(chunk, batch - b0);
             peers_.n = n_peer_base_;
-            for (int i = 0; i < n_peer_base_; ++i) peers_.p[i] = peer_base_[i] + b0 * out_img;
+            for (int i = 0; i < std::max(n_peer_base_, n_peer_base_ < 0 ? 1 : 0); ++i) peers_.p[i] = peer_base_[i] + b0 * out_img;
             forward_chunk(static_cast<const T*>(x) + b0 * in_img, static_cast<T*>(out) + b0 * out_img,
                           static_cast<cx<T>*>(ws), B, st);
         }
@@ -277,9 +277,10 @@ public:
     }
     void forward_peers(const void* x, void* out, void* const* peer_out, int n_peers, void* ws, size_t ws_bytes,
                        int64_t batch, cudaStream_t st) override {
-        if (n_peers < 0 || n_peers > kMaxPeers) throw std::runtime_error("at most 7 peer outputs");
+        // n_peers == -1: peer_out[0] is the multicast (NVLS) address of this rank's block, see OutPeers
+        if (n_peers < -1 || n_peers > kMaxPeers) throw std::runtime_error("at most 7 peer outputs");
         n_peer_base_ = n_peers;
-        for (int i = 0; i < n_peers; ++i) peer_base_[i] = static_cast<T*>(peer_out[i]);
+        for (int i = 0; i < (n_peers < 0 ? 1 : n_peers); ++i) peer_base_[i] = static_cast<T*>(peer_out[i]);
         try { forward(x, out, ws, ws_bytes, batch, st); } catch (...) { n_peer_base_ = 0; throw; }
         n_peer_base_ = 0;
     }

@@ -83,12 +83,13 @@ class Engine2D:
         with torch.cuda.device(self.device):
             return torch.empty(need, dtype=torch.uint8, device=self.device)
 
-    def forward(self, x, out=None, peer_ptrs=None):
+    def forward(self, x, out=None, peer_ptrs=None, multicast_ptr=None):
         """x: (B, M, N) contiguous on self.device -> (B, K, out_h, out_w).
 
         out: optional preallocated contiguous result tensor (e.g. this rank's block of a symmetric-memory buffer);
         peer_ptrs: device addresses of the SAME block inside the output tensors of peer GPUs - every coefficient plane is
-        then stored there as well by the kernels that produce it (scat_plan2d_forward_peers)."""
+        then stored there as well by the kernels that produce it (scat_plan2d_forward_peers);
+        multicast_ptr: the NVLS multicast address of the block instead - one multimem.st per value reaches every rank."""
         B = x.shape[0]
         if out is None:
             out = torch.empty((B, self.K, self.out_h, self.out_w), dtype=self.dtype, device=self.device)
@@ -99,7 +100,11 @@ class Engine2D:
         ws = self.workspace(B)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            if peer_ptrs:
+            if multicast_ptr:
+                arr = (ctypes.c_void_p * 1)(int(multicast_ptr))
+                _lib.check(self.lib.scat_plan2d_forward_peers(
+                    self._plan, x.data_ptr(), out.data_ptr(), arr, -1, ws.data_ptr(), ws.numel(), B, ctypes.c_void_p(stream)))
+            elif peer_ptrs:
                 arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
                 _lib.check(self.lib.scat_plan2d_forward_peers(
                     self._plan, x.data_ptr(), out.data_ptr(), arr, len(peer_ptrs), ws.data_ptr(), ws.numel(), B,

@@ -114,10 +114,13 @@ class PeerGatherScattering(torch.nn.Module):
     ``kymatio_b200.Scattering2D``.  Two buffers alternate so that a rank may still read step i while step i+1 is written.
     """
 
-    def __init__(self, scattering, group=None):
+    def __init__(self, scattering, group=None, multicast=None):
+        """multicast: True / False / None (= use NVLS multimem stores when the symmetric-memory handle offers a multicast
+        address and there are more than two ranks: one store per value instead of one per peer)."""
         super().__init__()
-        self.scattering, self.group = scattering, group
+        self.scattering, self.group, self.multicast = scattering, group, multicast
         self._bufs, self._hdls, self._step = {}, {}, 0
+        self.last_mode = None
 
     def _symm_buffers(self, total, eng, device):
         import torch.distributed._symmetric_memory as symm_mem
@@ -154,7 +157,14 @@ class PeerGatherScattering(torch.nn.Module):
         self._step += 1
         buf, hdl = bufs[i], hdls[i]
         block = eng.K * eng.out_h * eng.out_w * 4
-        peers = [int(hdl.buffer_ptrs[r]) + lo * block for r in range(world) if r != rank]
-        eng.forward(x, out=buf[lo:hi], peer_ptrs=peers)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        use_mc = (self.multicast if self.multicast is not None else world > 2) and mc != 0
+        if use_mc:
+            self.last_mode = "multicast"
+            eng.forward(x, out=buf[lo:hi], multicast_ptr=mc + lo * block)
+        else:
+            self.last_mode = "unicast"
+            peers = [int(hdl.buffer_ptrs[r]) + lo * block for r in range(world) if r != rank]
+            eng.forward(x, out=buf[lo:hi], peer_ptrs=peers)
         hdl.barrier(channel=0)          # every rank's kernels (and their remote stores) have completed
         return buf

@@ -40,6 +40,16 @@ try:
         torch.cuda.synchronize()
         assert y.shape == ref.shape and torch.allclose(y, ref, atol=1e-6), ("peer gather", total, float((y - ref).abs().max()))
     S3 = Scattering2D(3, (64, 64)).cuda()
+    for mcast in (True, False):
+        Pm = PeerGatherScattering(S3, multicast=mcast)
+        x = torch.randn(5 * world, 64, 64, device="cuda")
+        dist.broadcast(x, 0)
+        lo, hi = shard_bounds(5 * world, rank, world)
+        y = Pm(x[lo:hi].contiguous(), 5 * world)
+        torch.cuda.synchronize()
+        assert torch.allclose(y, S3(x), atol=1e-6), ("peer gather", mcast, Pm.last_mode)
+        if rank == 0:
+            print("peer_gather mode", Pm.last_mode, "ok")
     P3 = PeerGatherScattering(S3)
     x = torch.randn(6 * world, 64, 64, device="cuda")
     dist.broadcast(x, 0)
