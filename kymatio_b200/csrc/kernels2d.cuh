@@ -67,6 +67,33 @@ template <typename T> __device__ __forceinline__ OutRef<T> out_ref(T* out, const
     OutRef<T> r; r.out = out; r.pe = &pe; r.off = off; return r;
 }
 
+// Push a finished coefficient plane (n values at out + off, already stored locally and made visible by a CTA barrier) to
+// the peers with 16-byte stores issued by ONE warp: multicast -> one multimem.st.v4 per 16 bytes, unicast -> one st.v4 per
+// peer.  Decoupled from the low-pass tail that produced the plane: the other warps are already loading the next path.
+__device__ __forceinline__ void multimem_st4(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void push_plane(const T* out, const OutPeers<T>& pe, size_t off, int n, int lane) {
+    if constexpr (sizeof(T) == 4) {
+        if ((n & 3) == 0 && ((off & 3) == 0)) {
+            const float4* src = reinterpret_cast<const float4*>(out + off);
+            for (int i = lane; i < (n >> 2); i += 32) {
+                const float4 v = __ldcg(src + i);
+                if (pe.n < 0) multimem_st4(reinterpret_cast<float*>(pe.p[0] + off) + 4 * i, v);
+                else for (int k = 0; k < pe.n; ++k) reinterpret_cast<float4*>(pe.p[k] + off)[i] = v;
+            }
+            return;
+        }
+    }
+    for (int i = lane; i < n; i += 32) {
+        const T v = __ldcg(out + off + i);
+        if (pe.n < 0) multimem_st(pe.p[0] + off + i, v);
+        else for (int k = 0; k < pe.n; ++k) pe.p[k][off + i] = v;
+    }
+}
+
 template <typename U> __device__ __forceinline__ void stage(U* dst, const U* __restrict__ src, int n) {
     for (int i = flat_tid(); i < n; i += flat_nt()) dst[i] = src[i];
 }

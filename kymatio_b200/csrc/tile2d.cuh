@@ -377,6 +377,9 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
     }
 
     SB_PHASE_INIT((N0 == 136 ? 0 : N0 == 68 ? 1 : 2) * 8 + (KT == 4 ? 4 : 0) + (a.spec_out ? 2 : 0) + (a.PP != a.NFch ? 1 : 0))
+    // peer destinations (multi-GPU gather fused into this kernel): the low-pass tail stores the plane locally; after the
+    // barrier that ends the path, warp 0 pushes it to the peers with 16-byte (multicast) stores (kernels2d.cuh: push_plane)
+    OutPeers<T> local_only; local_only.n = 0;
     if ((int)blockIdx.x < a.G) stage_supp(m.supp, a.supp + (size_t)(blockIdx.x % a.NF) * a.P0, a.P0);
     if (a.stagger_ns > 0) {
         for (int i = (int)(blockIdx.x & 3); i > 0; --i) __nanosleep((unsigned)a.stagger_ns);
@@ -465,7 +468,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             __syncthreads();
             // 4b on tensor cores: S = G0s^T * W1; warp task = (16 output rows, 8 output columns)
             {
-                const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
+                const OutRef<T> ob = out_ref(a.out, local_only, ((size_t)b * a.K + ch) * a.o0 * a.o1);
                 const int mt = (a.o0p + 15) >> 4, ntl = (a.o1p + 7) >> 3;
                 for (int task = wid; task < mt * ntl; task += nwarp) {
                     const int m0 = (task / ntl) * 16, c0 = (task % ntl) * 8;
@@ -541,7 +544,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             // 4b (tap tables). S[yo][xo] = sum_y g0[kl (yo+1) - y] * (w1[0] + w1[1])[row(y)][xo]; the y window is split in two
             //   work items as well: the second half leaves its partial sums in shared memory, the first adds them and stores
             {
-                const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
+                const OutRef<T> ob = out_ref(a.out, local_only, ((size_t)b * a.K + ch) * a.o0 * a.o1);
                 const int ygroups = a.o0p >> 2, nitem = ygroups * a.o1p;
                 const T* w1b = m.w1 + N0 * wp;
                 const int g0 = (a.y0cnt + 1) >> 1;
@@ -628,7 +631,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
         // 4b. vertical low-pass + decimation + unpad, straight to the output plane:
         //     S[yo][xo] = sum_y G0[y][yo] * w1[row(y)][xo]; 4 output rows per thread, lanes along xo
         {
-            const OutRef<T> ob = out_ref(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1);
+            const OutRef<T> ob = out_ref(a.out, local_only, ((size_t)b * a.K + ch) * a.o0 * a.o1);
             const int ygroups = a.o0p >> 2;
             for (int it = tid; it < ygroups * a.o1p; it += nt) {
                 const int yg = it / a.o1p, xo = it - yg * a.o1p;
@@ -682,6 +685,7 @@ __device__ __forceinline__ void tile_body(const TileArgs<T>& a) {
             }
         }
         __syncthreads();   // the next path rewrites the tile, the support rows and w1
+        if (a.peers.n != 0 && warp == 0) push_plane(a.out, a.peers, ((size_t)b * a.K + ch) * a.o0 * a.o1, a.o0 * a.o1, lane);
         SB_PHASE(6);
     }
 }
