@@ -202,6 +202,14 @@ typedef struct scat1d_finseg {
     const void* chan_dev;             /* int32[NI] */
     int32_t which, nparts, N, Fc, NI, line0;
 } scat1d_finseg;
+/* T = 0 (no averaging: kymatio/scattering1d/core/scattering1d.py:75-76,104-105 yield the modulus fields themselves):
+ * the same path kernels, which also store |u| in NATURAL time order at mod_dev[g*N + t] (float); is_leaf: nothing else to
+ * do (no spectrum for children); scat1d_tile_t0 with spec_dev != NULL also writes the natural-order spectrum. */
+int scat1d_row_mod_t0(const void* tables_dev, void* y_dev, int64_t G, int32_t N, void* mod_dev, int32_t is_leaf,
+                      double algo_bytes, void* stream);
+int scat1d_tile_t0(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
+                   const void* supp_dev, void* spec_dev, void* mod_dev, int64_t G, int32_t NI, int32_t Npar, int32_t N,
+                   double algo_bytes, void* stream);
 /* average='global' tail (kymatio/scattering1d/frontend/base_frontend.py:137-138): out[b*os_b + chan] = bin 0 of the
  * path's spectrum = the sum over time of its modulus field; same segment table as scat1d_finish. */
 int scat1d_finish_global(const void* u0_dev, const void* u1_dev, const void* part_dev, const void* segs_dev, int32_t nseg,

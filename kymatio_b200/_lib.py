@@ -93,6 +93,10 @@ SIGNATURES = {
                                _c.c_void_p]),
     "scat1d_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int64,
                                  _c.c_int32, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_double, _c.c_void_p]),
+    "scat1d_row_mod_t0": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_double,
+                                     _c.c_void_p]),
+    "scat1d_tile_t0": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                  _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_double, _c.c_void_p]),
     "scat1d_finish_global": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int64,
                                         _c.c_void_p, _c.c_int64, _c.c_void_p]),
     "scat1d_finseg_bytes": (_c.c_size_t, []),

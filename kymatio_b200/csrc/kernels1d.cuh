@@ -151,6 +151,10 @@ template <typename T> struct RowMod1 {
     const cx<T>* twB; const int* invA;
     TwN<T> w;
     cx<T>* part; int Fc;                         // leaves: part[(g*nparts + cta)][Fc]
+    // T = 0 (unaveraged output, core/scattering1d.py:75-76,104-105): the modulus field itself is an output.  mod != null:
+    // |u| is stored in NATURAL time order t = t1 + NA*t2 at mod[g*N + t]; the CTA then takes the rows of 16 CONSECUTIVE t1
+    // (row of t1 = posA[t1]) so that its stores are 64-byte segments; skip_fwd: a leaf - nothing else to do.
+    T* mod; const int* posA; const int* posB; int skip_fwd;
 };
 // Shared-memory layout: line-major, line l at s + l*(NB+1) (odd pitch): both the staging (lanes along a line) and
 // the butterflies (lanes across lines) are bank-conflict free.
@@ -165,11 +169,13 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
     const int nl = min(k1L, a.NA - p0);
     const int tid = flat_tid(), nt = flat_nt();
     stage(twB, a.twB, NB);
-    if (tid < k1L) t1s[tid] = tid < nl ? a.invA[p0 + tid] : 0;
+    const bool gather = !LEAF && a.mod != nullptr;                    // rows of consecutive t1 instead of consecutive rows
+    if (tid < k1L) t1s[tid] = tid < nl ? (gather ? p0 + tid : a.invA[p0 + tid]) : 0;
     cx<T>* yb = a.Y + ((size_t)g * a.NA + p0) * NB;
+    cx<T>* yg = a.Y + (size_t)g * a.NA * NB;
     for (int idx = tid; idx < nl * NB; idx += nt) {
         const int l = idx / NB, e = idx - l * NB;
-        s[l * LS + e] = yb[idx];
+        s[l * LS + e] = gather ? yg[(size_t)__ldg(a.posA + p0 + l) * NB + e] : yb[idx];
     }
     __syncthreads();
     // the rows of one CTA hold t1 = base + stride*k, k < nl (DIF digit structure of the NA-point column transform; checked
@@ -179,11 +185,23 @@ template <typename T, int NB, bool LEAF> __global__ void __launch_bounds__(k1Thr
     const int stride = max(1, a.NA / k1L);
     if (LEAF && tid < nl) lk[(t1s[tid] - base) / stride] = tid;
     slab_fft_s<NB, false, +1, LS, 1, T, true>(s, nl, twB);            // inverse DIF + modulus: (|u|, 0), scrambled t2
+    if constexpr (!LEAF) {
+        if (gather) {
+            T* mb = a.mod + (size_t)g * a.N + p0;
+            for (int idx = tid; idx < NB * k1L; idx += nt) {
+                const int t2 = idx / k1L, l = idx - t2 * k1L;
+                if (l < nl) mb[(size_t)t2 * a.NA + l] = s[l * LS + __ldg(a.posB + t2)].x;
+            }
+            if (a.skip_fwd) return;
+            __syncthreads();
+        }
+    }
     slab_fft_s<NB, true, -1, LS, 1, T>(s, nl, twB);                   // forward DIT: natural f2'
     if constexpr (!LEAF) {
         for (int idx = tid; idx < nl * NB; idx += nt) {
             const int l = idx / NB, e = idx - l * NB;
-            yb[idx] = cmul(s[l * LS + e], twn(hi, lo, a.w.lb, t1s[l] * e));
+            const cx<T> v = cmul(s[l * LS + e], twn(hi, lo, a.w.lb, t1s[l] * e));
+            if (gather) yg[(size_t)__ldg(a.posA + p0 + l) * NB + e] = v; else yb[idx] = v;
         }
     } else {
         cx<T>* pb = a.part + ((size_t)g * gridDim.y + blockIdx.y) * a.Fc;
@@ -290,6 +308,7 @@ template <typename T> struct Tile1 {
     T scale;
     const cx<T>* twA; const cx<T>* twB; const int* invA;
     TwN<T> w;
+    T* mod; const int* posA; const int* posB;    // T = 0: |u| in natural time order at mod[g*N + t] (see RowMod1)
 };
 template <typename T, int NA, int NB> __global__ void __launch_bounds__(k1Threads, 4) k1d_tile(Tile1<T> a) {
     constexpr int W = NB + 1, N = NA * NB;
@@ -355,6 +374,15 @@ template <typename T, int NA, int NB> __global__ void __launch_bounds__(k1Thread
     }
     __syncthreads();
     slab_fft_s<NB, false, +1, W, 1, T, true>(s, NA, twB);              // inverse over f2 (rows) + modulus
+    if (a.mod) {
+        T* mb = a.mod + (size_t)g * N;
+        for (int t = tid; t < N; t += nt) {
+            const int t1 = t & (NA - 1), t2 = t / NA;
+            mb[t] = s[__ldg(a.posA + t1) * W + __ldg(a.posB + t2)].x;
+        }
+        if (!a.spec && !a.part) return;
+        __syncthreads();
+    }
     slab_fft_s<NB, true, -1, W, 1, T>(s, NA, twB);                     // forward over t2 (rows): natural f2'
     for (int idx = tid; idx < N; idx += nt) {
         const int p = idx / NB, e = idx - p * NB;

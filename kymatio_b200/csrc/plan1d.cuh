@@ -127,7 +127,8 @@ inline void col_prod1d(const void* tables, const void* parent, long long ps_b, l
            [&] { k.col_prod<<<grid, block1d(), smem, st>>>(a); });
 }
 
-inline void row_mod1d(const void* tables, void* Y, long long G, int N, void* part, int Fc, double algo_bytes, cudaStream_t st) {
+inline void row_mod1d(const void* tables, void* Y, long long G, int N, void* part, int Fc, double algo_bytes, cudaStream_t st,
+                      void* mod = nullptr, bool skip_fwd = false) {
     if (G <= 0) return;
     enable1d_once();
     Tables1d t(N);
@@ -140,9 +141,12 @@ inline void row_mod1d(const void* tables, void* Y, long long G, int N, void* par
     a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb); a.invA = reinterpret_cast<const int*>(cb + t.inva);
     a.w = twn_of(t, cb);
     a.part = static_cast<cx<float>*>(part); a.Fc = Fc;
+    if (mod && part) throw std::runtime_error("row_mod1d: the unaveraged output has no low-pass partial sums");
+    a.mod = static_cast<float*>(mod); a.skip_fwd = skip_fwd ? 1 : 0;
+    a.posA = reinterpret_cast<const int*>(cb + t.posa); a.posB = reinterpret_cast<const int*>(cb + t.posb);
     const size_t smem = ((size_t)(t.sp.Nb + 1) * k1L + t.sp.Nb) * sizeof(cx<float>) + 2 * k1L * sizeof(int);
     dim3 grid((unsigned)G, ceil_div(t.sp.Na, k1L));
-    launch(std::string(part ? "1d_row_mod_leaf:N" : "1d_row_mod:N") + std::to_string(N), algo_bytes, st,
+    launch(std::string(part ? "1d_row_mod_leaf:N" : mod ? "1d_row_mod_t0:N" : "1d_row_mod:N") + std::to_string(N), algo_bytes, st,
            [&] { (part ? k.leaf : k.parent)<<<grid, block1d(), smem, st>>>(a); });
 }
 
@@ -188,7 +192,7 @@ inline void rfft1d(const void* tables, const void* x, void* Z, void* out, long l
 
 inline void tile1d(const void* tables, const void* parent, long long ps_b, long long ps_i, const void* filt_dev,
                    const void* supp_dev, void* spec, void* part, int Fc, long long G, int NI, int Npar, int N,
-                   double algo_bytes, cudaStream_t st) {
+                   double algo_bytes, cudaStream_t st, void* mod = nullptr) {
     if (G <= 0) return;
     enable1d_once();
     Tables1d t(N);
@@ -206,9 +210,11 @@ inline void tile1d(const void* tables, const void* parent, long long ps_b, long 
     a.twA = reinterpret_cast<const cx<float>*>(cb + t.twa); a.twB = reinterpret_cast<const cx<float>*>(cb + t.twb);
     a.invA = reinterpret_cast<const int*>(cb + t.inva);
     a.w = twn_of(t, cb);
+    a.mod = static_cast<float*>(mod);
+    a.posA = reinterpret_cast<const int*>(cb + t.posa); a.posB = reinterpret_cast<const int*>(cb + t.posb);
     const size_t smem = ((size_t)t.sp.Na * (t.sp.Nb + 1) + t.sp.Na + t.sp.Nb) * sizeof(cx<float>);
     dim3 grid((unsigned)G);
-    launch(std::string(spec ? "1d_tile_parent:N" : "1d_tile_leaf:N") + std::to_string(N) + ":k" + std::to_string(a.k), algo_bytes,
+    launch(std::string(mod ? "1d_tile_t0:N" : spec ? "1d_tile_parent:N" : "1d_tile_leaf:N") + std::to_string(N) + ":k" + std::to_string(a.k), algo_bytes,
            st, [&] { kern<<<grid, block1d(), smem, st>>>(a); });
 }
 

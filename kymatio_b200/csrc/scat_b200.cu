@@ -430,6 +430,13 @@ int scat1d_row_mod(const void* tables_dev, void* y_dev, int64_t G, int32_t N, vo
                    void* stream) {
     return guarded([&] { row_mod1d(tables_dev, y_dev, G, N, part_dev, Fc, algo_bytes, static_cast<cudaStream_t>(stream)); });
 }
+int scat1d_row_mod_t0(const void* tables_dev, void* y_dev, int64_t G, int32_t N, void* mod_dev, int32_t is_leaf,
+                      double algo_bytes, void* stream) {
+    return guarded([&] {
+        if (!mod_dev) throw std::runtime_error("scat1d_row_mod_t0: mod_dev is null");
+        row_mod1d(tables_dev, y_dev, G, N, nullptr, 0, algo_bytes, static_cast<cudaStream_t>(stream), mod_dev, is_leaf != 0);
+    });
+}
 int scat1d_col_fwd(const void* tables_dev, const void* z_dev, void* out_dev, int64_t G, int32_t N, double algo_bytes,
                    void* stream) {
     return guarded([&] { col_fwd1d(tables_dev, z_dev, out_dev, G, N, algo_bytes, static_cast<cudaStream_t>(stream)); });
@@ -444,6 +451,15 @@ int scat1d_tile(const void* tables_dev, const void* parent_dev, int64_t ps_b, in
     return guarded([&] {
         tile1d(tables_dev, parent_dev, ps_b, ps_i, filt_ptrs_dev, supp_dev, spec_dev, part_dev, Fc, G, NI, Npar, N, algo_bytes,
                static_cast<cudaStream_t>(stream));
+    });
+}
+int scat1d_tile_t0(const void* tables_dev, const void* parent_dev, int64_t ps_b, int64_t ps_i, const void* filt_ptrs_dev,
+                   const void* supp_dev, void* spec_dev, void* mod_dev, int64_t G, int32_t NI, int32_t Npar, int32_t N,
+                   double algo_bytes, void* stream) {
+    return guarded([&] {
+        if (!mod_dev) throw std::runtime_error("scat1d_tile_t0: mod_dev is null");
+        tile1d(tables_dev, parent_dev, ps_b, ps_i, filt_ptrs_dev, supp_dev, spec_dev, nullptr, 0, G, NI, Npar, N, algo_bytes,
+               static_cast<cudaStream_t>(stream), mod_dev);
     });
 }
 int scat1d_finish(const void* fin_tables_dev, const void* u0_dev, const void* u1_dev, const void* part_dev,

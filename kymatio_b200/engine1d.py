@@ -152,27 +152,30 @@ class Engine1D:
     the SUM over time of its modulus field = bin 0 of the spectrum the cascade already computes; the low-pass tail is
     replaced by scat1d_finish_global and the output is (B, K, 1)."""
 
-    def __init__(self, Np, log2_stride, phi, psi1, psi2, device, average_global=False):
+    def __init__(self, Np, log2_stride, phi, psi1, psi2, device, average_global=False, unaveraged=False):
         self.lib = _lib.load()
         assert self.lib.scat1d_finseg_bytes() == _FINSEG.itemsize
         self.device = torch.device(device)
         self.Np, self.ls = int(Np), int(log2_stride)
         self.average_global = bool(average_global)
+        # unaveraged = the reference's T=0: every path's modulus field at its own resolution 2^-j is an output
+        # (core/scattering1d.py:75-76,104-105); same subsampling rule as 'global', no low-pass tail at all
+        self.unaveraged = bool(unaveraged)
         if self.Np & (self.Np - 1):
             raise Unsupported("padded length must be a power of two")
-        if self.average_global:
+        if self.average_global or self.unaveraged:
             # k1 = j1 and k2 = j2 - j1 (core/scattering1d.py:63,88-89 with average_local=False): a stride that never caps
             self.ls = max([p["j"] for p in psi1] + ([p["j"] for p in psi2] if psi2 is not None else []) + [0])
         sch = schedule(self.Np, self.ls, phi, psi1, psi2)
         self.M, self.K, self.order = sch["M"], sch["K"], sch["order"]
-        if self.average_global:
+        if self.average_global or self.unaveraged:
             self.M = 1
         self.tables = _Tables(self.device)
         # transforms up to this length run as ONE launch with the whole path in shared memory (scat1d_tile)
         self.tile_max = self.lib.scat1d_tile_max() if os.environ.get("SCAT_B200_1D_TILE", "1") != "0" else 0
         with torch.cuda.device(self.device):
             self._keep = []                        # tensors the device arrays point into
-            if self.average_global:
+            if self.average_global or self.unaveraged:
                 # only bin 0 is needed: the leaves' pruned transform keeps its minimum of 16 bins, phi is never read
                 self.fin_tab, self.phi_lv, self.Fc = None, None, [16] * (self.ls + 2)
             else:
@@ -282,6 +285,58 @@ class Engine1D:
                 _lib.check(self.lib.scat1d_rfft(self.tables.for_length(self.Np).data_ptr(), U0.data_ptr(), out.data_ptr(),
                                                 out.data_ptr(), B, self.Np, _stream(self.device)))
         return out
+
+    def forward_unaveraged(self, U0_hat):
+        """T=0: -> (mods1, mods2): mods1[gi] is the (B, NI, N1) float32 modulus of first-order group gi in natural time
+        order, mods2[(gi, ci)] the (B, NI, N2) modulus of its ci-th second-order child group."""
+        lib, dev = self.lib, self.device
+        B, Np = U0_hat.shape[0], self.Np
+        mods1 = [torch.empty((B, g["NI"], g["N1"]), dtype=torch.float32, device=dev) for g in self.groups]
+        mods2 = {(gi, ci): torch.empty((B, g["NI"], c["N2"]), dtype=torch.float32, device=dev)
+                 for gi, g in enumerate(self.groups) for ci, c in enumerate(g["children"])}
+        if B == 0:
+            return mods1, mods2
+        Bc = self.chunk_size(B)
+        ps = self.per_signal
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            Y = torch.empty(max(1, Bc * ps["Y"]) * 8, dtype=torch.uint8, device=dev)
+            U1 = torch.empty(max(1, Bc * ps["U1"]) * 8, dtype=torch.uint8, device=dev)
+            yp, up = Y.data_ptr(), U1.data_ptr()
+            for b0 in range(0, B, Bc):
+                nb = min(Bc, B - b0)
+                u0 = U0_hat.data_ptr() + b0 * Np * 8
+                for gi, g in enumerate(self.groups):
+                    NI, N1, G = g["NI"], g["N1"], nb * g["NI"]
+                    tab = g["tab"].data_ptr()
+                    leaf = not g["children"]
+                    u1 = up + nb * g.get("u1_off", 0) * 8
+                    m1 = mods1[gi].data_ptr() + b0 * NI * N1 * 4
+                    rd1 = float(nb) * 8 * sum(g["supp_len"])
+                    if g["tile"]:
+                        _lib.check(lib.scat1d_tile_t0(tab, u0, Np, 0, g["filt_dev"].data_ptr(), g["supp_dev"].data_ptr(),
+                                                      None if leaf else u1, m1, G, NI, Np, N1,
+                                                      rd1 + float(G) * N1 * (4 if leaf else 12), st))
+                    else:
+                        _lib.check(lib.scat1d_col_prod(tab, u0, Np, 0, g["filt_dev"].data_ptr(), g["supp_dev"].data_ptr(),
+                                                       yp, G, NI, Np, N1, rd1 + float(G) * 8 * N1, st))
+                        _lib.check(lib.scat1d_row_mod_t0(tab, yp, G, N1, m1, int(leaf), float(G) * N1 * (12 if leaf else 20), st))
+                        if not leaf:
+                            _lib.check(lib.scat1d_col_fwd(tab, yp, u1, G, N1, float(G) * N1 * 16, st))
+                    for ci, c in enumerate(g["children"]):
+                        N2, ctab = c["N2"], c["tab"].data_ptr()
+                        m2 = mods2[(gi, ci)].data_ptr() + b0 * NI * N2 * 4
+                        rd2 = float(nb) * 8 * sum(c["supp_len"])
+                        if c["tile"]:
+                            _lib.check(lib.scat1d_tile_t0(ctab, u1, NI * N1, N1, c["filt_dev"].data_ptr(),
+                                                          c["supp_dev"].data_ptr(), None, m2, G, NI, N1, N2,
+                                                          rd2 + float(G) * 4 * N2, st))
+                        else:
+                            _lib.check(lib.scat1d_col_prod(ctab, u1, NI * N1, N1, c["filt_dev"].data_ptr(),
+                                                           c["supp_dev"].data_ptr(), yp, G, NI, N1, N2,
+                                                           rd2 + float(G) * 8 * N2, st))
+                            _lib.check(lib.scat1d_row_mod_t0(ctab, yp, G, N2, m2, 1, float(G) * N2 * 12, st))
+        return mods1, mods2
 
     def forward(self, U0_hat):
         """U0_hat: (B, Np, 2) float32 natural-order spectrum of the padded signals -> (B, K, M) float32:

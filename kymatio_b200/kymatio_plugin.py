@@ -559,10 +559,33 @@ def _fused_scattering1d(U_0, backend_, filters, log2_stride, average_local):
     tensors = list(phi["levels"]) + [lv for p in psi1 for lv in p["levels"]]
     if psi2 is not None:
         tensors += [lv for p in psi2 for lv in p["levels"]]
-    glob = not average_local
-    key = (U_0.device.index, Np, int(log2_stride), psi2 is None, glob) + tuple((t.data_ptr(), t._version) for t in tensors)
-    eng = _engines1d.get(key, lambda: Engine1D(Np, log2_stride, phi, psi1, psi2, U_0.device, average_global=glob))
-    S = eng.forward(eng.rfft(U_0.reshape(-1, Np).contiguous()))
+    owner = getattr(_tls, "frontend1d", None)
+    glob = (not average_local) and getattr(owner, "average", None) == "global"
+    unav = (not average_local) and not glob                      # T=0: the modulus fields themselves
+    key = (U_0.device.index, Np, int(log2_stride), psi2 is None, glob, unav) + tuple((t.data_ptr(), t._version) for t in tensors)
+    eng = _engines1d.get(key, lambda: Engine1D(Np, log2_stride, phi, psi1, psi2, U_0.device, average_global=glob,
+                                               unaveraged=unav))
+    U0_hat = eng.rfft(U_0.reshape(-1, Np).contiguous())
+    if unav:
+        mods1, mods2 = eng.forward_unaveraged(U0_hat)
+        where1, where2 = {}, {}
+        for gi, g in enumerate(eng.groups):
+            for i, n1 in enumerate(g["n1"]):
+                where1[n1] = (mods1[gi], i)
+                for ci, c in enumerate(g["children"]):
+                    where2[(n1, c["n2"])] = (mods2[(gi, ci)], i)
+        B = U0_hat.shape[0]
+        for kind, n1, n2, ch in eng.order:
+            if kind == "S0":
+                yield {"coef": U_0, "j": (), "n": ()}
+            elif kind == "S1":
+                t, i = where1[n1]
+                yield {"coef": t[:, i].reshape(B, 1, -1, 1), "j": (psi1[n1]["j"],), "n": (n1,)}
+            else:
+                t, i = where2[(n1, n2)]
+                yield {"coef": t[:, i].reshape(B, 1, -1, 1), "j": (psi1[n1]["j"], psi2[n2]["j"]), "n": (n1, n2)}
+        return
+    S = eng.forward(U0_hat)
     B = S.shape[0]
     for kind, n1, n2, ch in eng.order:
         coef = S[:, ch].reshape(B, 1, eng.M, 1)
@@ -580,13 +603,12 @@ def _fusable1d(U_0, backend_, filters, log2_stride, average_local):
     if getattr(backend_, "name", None) != NAME:
         return False
     if not average_local:
-        # average_local=False is either average='global' (sum over time: fused, scat1d_finish_global) or T=0 (the
-        # full-resolution modulus of every path, unpadded by the frontend: eager primitives).  install() records the
-        # running frontend, which knows which one it is.
+        # average_local=False is either average='global' (sum over time: scat1d_finish_global) or T=0 (the modulus field
+        # of every path at its own resolution: scat1d_*_t0).  install() records the running frontend, which knows which.
         owner = getattr(_tls, "frontend1d", None)
-        if getattr(owner, "average", None) != "global":
+        if owner is None or getattr(owner, "average", None) not in ("global", False):
             if torch.is_tensor(U_0) and U_0.is_cuda:
-                _warn_fallback("Scattering1D", "T=0 returns unaveraged full-resolution paths")
+                _warn_fallback("Scattering1D", "scattering1d() was not called through the frontend: averaging mode unknown")
             return False
     if _wants_grad(U_0):
         return False                      # gradients: the unchanged core drives the differentiable eager primitives

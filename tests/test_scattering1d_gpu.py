@@ -272,22 +272,31 @@ def test_fused1d_average_global(plugin, kw):
     assert_parity(y.cpu().numpy(), ref, channel_axis=-2, what=str(kw))
 
 
-def test_1d_T0_falls_back_loudly(plugin):
-    """T=0 (unaveraged full-resolution paths) is outside the fused schedule: the unchanged core drives the eager
-    primitives, the result matches the reference, and the fall-back is announced once."""
-    import warnings
+@pytest.mark.parametrize("kw", [dict(J=4, shape=1024, Q=(4, 1), T=0, out_type="list"),
+                                dict(J=6, shape=2 ** 15, Q=(8, 1), T=0, out_type="dict"),
+                                dict(J=5, shape=3000, Q=(4, 2), T=0, out_type="list", max_order=1)])
+def test_fused1d_T0_unaveraged(plugin, kw):
+    """T=0 (core/scattering1d.py:75-76,104-105: the modulus field of every path at its own resolution, unpadded by the
+    frontend) through the fused kernels (scat1d_tile_t0 / scat1d_row_mod_t0 store |u| in natural time order); against the
+    reference's numpy frontend in float64, path by path."""
     from kymatio.torch import Scattering1D
     from kymatio.scattering1d.frontend.numpy_frontend import ScatteringNumPy1D
-    kw = dict(J=4, shape=1024, Q=(4, 1), T=0, out_type="list")
-    x = np.random.RandomState(4).randn(2, 1024)
+    from kymatio_b200 import _lib
+    x = np.random.RandomState(4).randn(2, kw["shape"])
     S = Scattering1D(backend="torch_b200", **kw).cuda()
-    plugin._warned.clear()
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        y = S(torch.from_numpy(x).float().cuda())
-    assert any("eager per-primitive kernels" in str(m.message) for m in w)
+    _lib.timing_enable(True)
+    y = S(torch.from_numpy(x).float().cuda())
+    labels = {r["label"].split(":")[0] for r in _lib.timing_report()}
+    _lib.timing_enable(False)
+    assert labels & {"1d_tile_t0", "1d_row_mod_t0"}, labels
+    assert not any(l.startswith("prim_") for l in labels if l not in ("prim_pad1d",)), labels
     ref = ScatteringNumPy1D(**kw)(x)
-    assert len(y) == len(ref)
-    for a, b in zip(y, ref):
-        assert a["n"] == b["n"] and tuple(a["coef"].shape) == b["coef"].shape
-        assert np.abs(a["coef"].cpu().numpy() - b["coef"]).max() <= 1e-4 * max(np.abs(b["coef"]).max(), 1e-12)
+    if kw["out_type"] == "dict":
+        assert set(y.keys()) == set(ref.keys())
+        pairs = [(y[k], ref[k]) for k in ref]
+    else:
+        assert [a["n"] for a in y] == [b["n"] for b in ref]
+        pairs = [(a["coef"], b["coef"]) for a, b in zip(y, ref)]
+    for a, b in pairs:
+        assert tuple(a.shape) == b.shape
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-12)
