@@ -723,7 +723,8 @@ private:
         if (!gparent && spec_out && is_static)          // static instances with the forward transform compiled in
             if (TileKernel<T> ks = tile_spec_kernel_lookup<T>(a.n0, a.n1, a.k)) kern = ks;
         // CUDA-core low-pass of the static forward instances reads the taps from the [cnt][4] tables
-        a.tt = (!gparent && is_static && (a.k == 2 || a.k == 4) && !a.use_mma && (a.o0p >> 2) * a.o1p <= 256) ? 1 : 0;
+        a.tt = (!gparent && is_static && (a.k == 2 || a.k == 4) && !a.use_mma && (a.o0p >> 2) * a.o1p <= 256 &&
+                (a.o0p >> 2) * a.o1p <= std::max(64, (a.n0 * a.n1 / 4 + 31) / 32 * 32)) ? 1 : 0;
         a.TT0 = reinterpret_cast<const T*>(cbuf_ + F.TT0_off);
         a.TT1 = reinterpret_cast<const T*>(cbuf_ + F.TT1_off);
         // forward static instances of prime-factor sizes (136, 68, ...: tile_pfa) take the prime-factor position tables
@@ -736,9 +737,13 @@ private:
         const size_t smem = tile_smem_layout<T>(a, nullptr);
         // threads: every butterfly pass distributes (lines x butterflies) work items over the CTA in rounds;
         // pick the warp count that wastes the fewest (cost-weighted) partially filled rounds
-        const int cap = std::min(tile_threads_cap_, is_static ? tile_max_threads(a.n0, a.n1) : tile_max_threads(0, 0));
+        int cap = std::min(tile_threads_cap_, is_static ? tile_max_threads(a.n0, a.n1) : tile_max_threads(0, 0));
+        // small fields (e.g. the 40 x 40 / 20 x 20 tiles of a 32 x 32 image): no more threads than 4-column work items, so
+        // that many CTAs share an SM instead of one 600-thread CTA idling on a 400-point field
+        cap = std::min(cap, std::max(64, (a.n0 * a.n1 / 4 + 31) / 32 * 32));
         int lo = (2 * smem > kMaxDynSmem) ? std::max(64, cap / 2) : std::max(64, cap / 3);
         // the tap-table low-pass gives every (4 output rows, 1 output column) item its own thread
+        lo = std::min(lo, cap / 32 * 32);
         if (a.tt) lo = std::min(cap / 32 * 32, std::max(lo, ((a.o0p >> 2) * a.o1p + 31) / 32 * 32));
         auto pass_cost = [](int r) { return r >= 16 ? 30.0 * r : r >= 8 ? 15.0 * r : 12.0 * r; };
         int threads = cap / 32 * 32;
