@@ -60,13 +60,51 @@ __global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, 
     }
 }
 
+// ------------------------------------------------------------------ streaming level, adjoint of the low-pass (horizontal half)
+// The forward S1 = unpad(Re ifft2(periodise(U1 * phi))) of the full-resolution band equals the separable spatial low-pass
+// S1 = G0^T A G1 of A = |u| (plan2d.cuh: analyse_lowpass; the fused backward is only offered when that holds), so
+//     gA[y][x] = sum_yo G0[y][yo] * Tl[yo][x],     Tl[yo][x] = sum_xo gS1[yo][xo] * G1[x][xo].
+// This kernel computes Tl for one path, stored with the columns at the SCRAMBLED positions x' = pos1[x] of the row passes;
+// k2d_bwd_col applies the vertical half for its 16 columns.
+template <typename T> struct HlowBwdArgs {
+    const T* gs1;              // [G][o0][o1]
+    const T* G1;               // [n1][o1p] dense
+    const int* pos1;           // [n1]
+    T* Tl;                     // [G][o0][n1]
+    int n1, o0, o1, o1p;
+};
+template <typename T> __global__ void __launch_bounds__(256) k2d_hlow_bwd(HlowBwdArgs<T> a) {
+    T* gs = dyn_smem<T>();                                      // [o0][o1]
+    const int g = blockIdx.x;
+    const T* __restrict__ gb = a.gs1 + (size_t)g * a.o0 * a.o1;
+    for (int i = threadIdx.x; i < a.o0 * a.o1; i += blockDim.x) gs[i] = gb[i];
+    __syncthreads();
+    T* ob = a.Tl + (size_t)g * a.o0 * a.n1;
+    for (int x = threadIdx.x; x < a.n1; x += blockDim.x) {
+        const T* __restrict__ gr = a.G1 + (size_t)x * a.o1p;
+        int lo = a.o1, hi = -1;
+        for (int xo = 0; xo < a.o1; ++xo) if (gr[xo] != T(0)) { if (lo == a.o1) lo = xo; hi = xo; }
+        const int xs = a.pos1[x];
+        for (int yo = 0; yo < a.o0; ++yo) {
+            T acc = T(0);
+            for (int xo = lo; xo <= hi; ++xo) acc += gs[yo * a.o1 + xo] * gr[xo];
+            ob[(size_t)yo * a.n1 + xs] = acc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ streaming level, column pass
 template <typename T> struct BwdColArgs {
     const cx<T>* Y;            // [G][n0][n1] rows-inverse of the product (rows: natural frequency, columns: scrambled x)
-    const cx<T>* GX;           // [G][n0][n1] rows-inverse of gU1, same layout
+    const cx<T>* GX;           // [G][n0][n1] rows-inverse of gU1, same layout; nullptr: no gradient through U1
     cx<T>* out;                // [G][n0][n1] cols-forward of gu (rows natural frequency, columns scrambled x); may alias Y
     int n1;
     const cx<T>* tw;
+    // vertical half of the low-pass adjoint (nullptr: the path's own S1 carries no gradient here)
+    const T* Tl;               // [G][o0][n1] from k2d_hlow_bwd
+    const T* G0;               // [n0][o0p] dense
+    const int* pos0;           // [n0] storage row of natural row y
+    int o0, o0p, kl, R;        // R = tap radius (>= n0/2: every output touches every row)
 };
 constexpr int kBwdThreads = 256;
 // grid (G, n1 / 16), kBwdThreads threads; two 16-column slabs in shared memory
@@ -75,24 +113,50 @@ template <typename T, int NS> __global__ void __launch_bounds__(kBwdThreads, 3) 
     cx<T>* s1 = dyn_smem<cx<T>>();
     cx<T>* s2 = s1 + (size_t)n0 * LP;
     cx<T>* tw = s2 + (size_t)n0 * LP;
+    int* ipos = reinterpret_cast<int*>(tw + n0);                 // natural row held at storage row q
+    T* tl = reinterpret_cast<T*>(ipos + n0);                     // [o0][16] slice of Tl
     const int g = blockIdx.x, c0 = blockIdx.y * kSLines;
     const int tid = flat_tid(), nt = flat_nt();
     stage(tw, a.tw, n0);
     const size_t off = (size_t)g * n0 * a.n1 + c0;
+    const cxpair<T> zero2 = {mk<T>(T(0), T(0)), mk<T>(T(0), T(0))};
     for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
         const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
         const cxpair<T> v = *reinterpret_cast<const cxpair<T>*>(a.Y + off + (size_t)e * a.n1 + l);
-        const cxpair<T> w = *reinterpret_cast<const cxpair<T>*>(a.GX + off + (size_t)e * a.n1 + l);
+        const cxpair<T> w = a.GX ? *reinterpret_cast<const cxpair<T>*>(a.GX + off + (size_t)e * a.n1 + l) : zero2;
         s1[e * LP + l] = v.a; s1[e * LP + l + 1] = v.b;
         s2[e * LP + l] = w.a; s2[e * LP + l + 1] = w.b;
     }
+    if (a.Tl) {
+        for (int y = tid; y < n0; y += nt) ipos[a.pos0[y]] = y;
+        const T* __restrict__ tb = a.Tl + (size_t)g * a.o0 * a.n1 + c0;
+        for (int i = tid; i < a.o0 * kSLines; i += nt) { const int yo = i / kSLines, l = i - yo * kSLines; tl[i] = tb[(size_t)yo * a.n1 + l]; }
+    }
     __syncthreads();
     slab_fft_s<NS, false, +1, 1, kSLP, T>(s1, kSLines, tw);      // u   (rows scrambled)
-    slab_fft_s<NS, false, +1, 1, kSLP, T>(s2, kSLines, tw);      // F^H gU1, same positions
+    if (a.GX) slab_fft_s<NS, false, +1, 1, kSLP, T>(s2, kSLines, tw);      // F^H gU1, same positions
+    const int mper = n0 / a.kl;                                  // outputs per period before unpadding (= o0 + 2)
     for (int idx = tid; idx < n0 * kSLines; idx += nt) {
         const int e = idx / kSLines, l = idx - e * kSLines;
         const cx<T> v = s1[e * LP + l];
-        const T gA = s2[e * LP + l].x;
+        T gA = s2[e * LP + l].x;
+        if (a.Tl) {
+            // + sum_yo G0[y][yo] * Tl[yo][x]: G0[y][yo] = a0[(kl (yo+1) - y) mod n0] is nonzero within R of a multiple of kl
+            const int y = ipos[e];
+            const T* __restrict__ g0 = a.G0 + (size_t)y * a.o0p;
+            if (2 * a.R + 1 >= n0) {
+                for (int yo = 0; yo < a.o0; ++yo) gA += g0[yo] * tl[yo * kSLines + l];
+            } else {
+                int j0 = y - a.R, j1 = y + a.R;                  // kl*(yo+1) in [j0, j1] (mod n0)
+                j0 = (j0 >= 0) ? (j0 + a.kl - 1) / a.kl : -((-j0) / a.kl);
+                j1 = (j1 >= 0) ? j1 / a.kl : -((-j1 + a.kl - 1) / a.kl);
+                for (int jj = j0; jj <= j1; ++jj) {
+                    int j = jj % mper; if (j < 0) j += mper;
+                    const int yo = j - 1;
+                    if (yo >= 0 && yo < a.o0) gA += g0[yo] * tl[yo * kSLines + l];
+                }
+            }
+        }
         const T mag = sqrt(v.x * v.x + v.y * v.y);
         const T sc = mag > T(0) ? gA / mag : T(0);
         s1[e * LP + l] = mk<T>(v.x * sc, v.y * sc);
@@ -173,6 +237,9 @@ template <typename T> using BwdRowKernel = void (*)(BwdRowArgs<T>);
 template <typename T> TileAdjKernel<T> tile_adj_lookup(int n0, int n1);
 template <typename T> BwdColKernel<T> bwd_col_lookup(int n);
 template <typename T> BwdRowKernel<T> bwd_row_lookup(int n);
+template <typename T> size_t bwd_col_smem(int n0, int o0) {
+    return ((size_t)2 * n0 * kSLP + n0) * sizeof(cx<T>) + (size_t)n0 * sizeof(int) + (size_t)o0 * kSLines * sizeof(T);
+}
 template <typename T> void bwd_kernels_enable_smem();
 
 }  // namespace sb

@@ -324,15 +324,17 @@ public:
             tile_bwd_kernel_lookup<T>(n0, n1, 1 << j1, &st);
             return (st && tile_adj_lookup<T>(n0, n1)) ? 1 : 0;
         }
-        if (j1 == 0 && hermitian_ok(0) && n0 == n1 && bwd_col_lookup<T>(n0) && bwd_row_lookup<T>(n1)) return 2;
+        if (j1 == 0 && hermitian_ok(0) && n0 == n1 && bwd_col_lookup<T>(n0) && bwd_row_lookup<T>(n1) && low_tile_ && fir_[0].ok)
+            return 2;
         return 0;
     }
     size_t order1_workspace_bytes(int j1, int64_t batch) const override {
         const size_t G = (size_t)batch * d_.L;
-        return order1_mode(j1) == 2 ? 2 * G * fsize(j1) * sizeof(cx<T>) : G * fsize(j1) * sizeof(T);
+        if (order1_mode(j1) != 2) return G * fsize(j1) * sizeof(T);
+        return 2 * G * fsize(j1) * sizeof(cx<T>) + G * o0_ * lev_[j1].a1.n * sizeof(T);
     }
-    // u0: [batch][P0][P1] spectra; s1: [batch][L][o0][o1] (tile levels, may be null at the streaming level);
-    // u1: [batch*L][n0][n1] natural-order spectra of the moduli (null: not needed)
+    // u0: [batch][P0][P1] spectra; s1: [batch][L][o0][o1] (null: not needed, streaming level only);
+    // u1: [batch*L][n0][n1] natural-order spectra of the moduli (null: not needed, tile levels only)
     void order1_forward(int j1, const void* u0, void* s1, void* u1, int64_t batch, cudaStream_t st) override {
         const int mode = order1_mode(j1);
         if (!mode) throw std::runtime_error("fused first-order block not available for this scale");
@@ -347,9 +349,11 @@ public:
             const T sc1 = T(1) / (T(lev_[j1].a0.n) * T(lev_[j1].a1.n));
             row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), static_cast<cx<T>*>(u1), 0, j1, B, L, sc1, st);
             hermitian_chain(static_cast<cx<T>*>(u1), j1, B * L, st, nullptr);
+            if (s1) low_pass(static_cast<const cx<T>*>(u1), j1, static_cast<T*>(s1), B, L, L, 0, 0, nullptr, st, false, L);
         }
     }
-    // gu0 ([batch][P0][P1], ACCUMULATED into) += gradient through the first-order block; gs1 as s1 (tile levels), gu1 as u1
+    // gu0 ([batch][P0][P1], ACCUMULATED into) += gradient through the first-order block; gs1 as s1, gu1 as u1.
+    // At the streaming level either may be null; the low-pass adjoint there is the separable spatial one (bwd2d.cuh)
     void order1_backward(int j1, const void* u0, const void* gs1, const void* gu1, void* gu0, void* ws, size_t ws_bytes,
                          int64_t batch, cudaStream_t st) override {
         const int mode = order1_mode(j1);
@@ -377,17 +381,30 @@ public:
             tile(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), 0, j1, B, L, nullptr, L, L, 0, 0, nullptr, "o1_bwd", st, L,
                  static_cast<const T*>(gs1), static_cast<cx<T>*>(gu0), R);
         } else {
-            if (!gu1) throw std::runtime_error("order1_backward: gu1 is required at the streaming level");
+            if (!gu1 && !gs1) throw std::runtime_error("order1_backward: no incoming gradient");
             const size_t G = (size_t)B * L;
             cx<T>* Y = static_cast<cx<T>*>(ws);
             cx<T>* GX = Y + G * fsize(j1);
+            T* Tl = reinterpret_cast<T*>(GX + G * fsize(j1));
             const T sc1 = T(1) / (T(n0) * T(n1));
             row_prod(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), Y, 0, j1, B, L, sc1, st);
-            row_prod(static_cast<const cx<T>*>(gu1), nullptr, nullptr, GX, j1, j1, B * L, 1, T(1), st);
+            if (gu1) row_prod(static_cast<const cx<T>*>(gu1), nullptr, nullptr, GX, j1, j1, B * L, 1, T(1), st);
+            const FirLevel& F = fir_[j1];
+            if (gs1) {
+                HlowBwdArgs<T> a{};
+                a.gs1 = static_cast<const T*>(gs1); a.G1 = reinterpret_cast<const T*>(cbuf_ + F.G1_off); a.pos1 = pos(lev_[j1].a1);
+                a.Tl = Tl; a.n1 = n1; a.o0 = o0_; a.o1 = o1_; a.o1p = o1p();
+                launch("hlow_bwd:L" + std::to_string(j1), (double)G * (o0_ * o1_ + o0_ * n1) * sizeof(T), st,
+                       [&] { k2d_hlow_bwd<T><<<(unsigned)G, 256, (size_t)o0_ * o1_ * sizeof(T), st>>>(a); });
+            }
             {
                 BwdColArgs<T> a{};
-                a.Y = Y; a.GX = GX; a.out = Y; a.n1 = n1; a.tw = tw(lev_[j1].a0);
-                const size_t smem = ((size_t)2 * n0 * kSLP + n0) * sizeof(cx<T>);
+                a.Y = Y; a.GX = gu1 ? GX : nullptr; a.out = Y; a.n1 = n1; a.tw = tw(lev_[j1].a0);
+                if (gs1) {
+                    a.Tl = Tl; a.G0 = reinterpret_cast<const T*>(cbuf_ + F.G0_off); a.pos0 = pos(lev_[j1].a0);
+                    a.o0 = o0_; a.o0p = o0p(); a.kl = 1 << (d_.J - j1); a.R = -F.y0lo;
+                }
+                const size_t smem = bwd_col_smem<T>(n0, o0_);
                 dim3 grid((unsigned)G, n1 / kSLines);
                 launch("bwd_col:L" + std::to_string(j1), 3.0 * G * n0 * n1 * sizeof(cx<T>), st,
                        [&] { bwd_col_lookup<T>(n0)<<<grid, dim3(16, kBwdThreads / 16), smem, st>>>(a); });
@@ -621,7 +638,7 @@ private:
 
     // Fourier low-pass: S[b][ch] = unpad(Re ifft2(periodise(spec * phi[res]))) for G = B*PP spectra
     void low_pass(const cx<T>* spec, int res, T* out, int B, int PP, int NF, int ch0, int chs, cx<T>* tmp,
-                  cudaStream_t st, bool row_folded = false) {
+                  cudaStream_t st, bool row_folded = false, int Kout = -1) {
         const int k = 1 << (d_.J - res);
         const T scale = T(1) / (T(k) * T(k) * T(m0_) * T(m1_));
         const int J = d_.J;
@@ -629,11 +646,11 @@ private:
             LowArgs<T> a{};
             a.in = spec; a.filt = phi(res); a.supp = phi_supp(res); a.out = out;
             a.P0 = lev_[res].a0.n; a.P1 = lev_[res].a1.n; a.k = k; a.m0 = m0_; a.m1 = m1_; a.W = lowW_;
-            a.PP = PP; a.NF = NF; a.ch0 = ch0; a.chs = chs; a.K = K_; a.scale = scale;
+            a.PP = PP; a.NF = NF; a.ch0 = ch0; a.chs = chs; a.K = Kout > 0 ? Kout : K_; a.scale = scale;
             a.plan0 = lev_[J].a0.plan; a.plan1 = lev_[J].a1.plan;
             a.tw0 = tw(lev_[J].a0); a.tw1 = tw(lev_[J].a1); a.pos0 = pos(lev_[J].a0); a.pos1 = pos(lev_[J].a1);
             a.row_folded = row_folded ? 1 : 0;
-            a.peers = peers_;
+            if (Kout <= 0) a.peers = peers_;
             const double G = (double)B * PP;
             launch("lowpass:L" + std::to_string(res) + ":G" + std::to_string(PP),
                    G * a.P0 * a.P1 * sizeof(cx<T>) + (double)a.P0 * a.P1 * sizeof(T) + G * o0_ * o1_ * sizeof(T), st,

@@ -137,16 +137,17 @@ class Engine2D:
 
     # -- first-order block (autograd building block) ----------------------------------------
     def order1_mode(self, j1):
-        """0: not fused; 1: tile level (S1 and U1 from one kernel); 2: streaming level (U1 only)."""
+        """0: not fused; 1: tile level (S1 and U1 from one kernel); 2: streaming level (three-kernel chain + low-pass)."""
         if os.environ.get("SCAT_B200_ORDER1_FUSED", "1") == "0":
             return 0
         return int(self.lib.scat_plan2d_order1_mode(self._plan, int(j1)))
 
-    def order1_forward(self, j1, u0, batch, want_u1):
+    def order1_forward(self, j1, u0, batch, want_u1, want_s1=True):
         """u0: (batch, Mp, Np, 2) -> (S1 (batch, L, oh, ow) or None, U1 (batch*L, n0, n1, 2) or None)."""
         mode, L = self.order1_mode(j1), self.geometry["L"]
         n0, n1 = self.Mp >> j1, self.Np >> j1
-        s1 = torch.empty((batch, L, self.out_h, self.out_w), dtype=self.dtype, device=self.device) if mode == 1 else None
+        s1 = (torch.empty((batch, L, self.out_h, self.out_w), dtype=self.dtype, device=self.device)
+              if (mode == 1 or want_s1) else None)
         u1 = torch.empty((batch * L, n0, n1, 2), dtype=self.dtype, device=self.device) if (want_u1 or mode == 2) else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):

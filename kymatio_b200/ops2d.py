@@ -224,21 +224,37 @@ class Order1Tile(torch.autograd.Function):
 
 
 class Order1Stream(torch.autograd.Function):
-    """First-order block at full resolution (streaming chain), fused: U0 -> U1 (B*L, n0, n1, 2).  Backward = mirrored
-    chain: row passes of the recomputed product and of gU1, one fused column kernel, one row kernel that reduces over
-    the angles (csrc/bwd2d.cuh)."""
+    """First-order block at full resolution (streaming chain), fused: U0 -> S1 (B, L, oh, ow) and, for scales with
+    children, U1 (B*L, n0, n1, 2).  Backward = mirrored chain: row passes of the recomputed product and of gU1, the
+    horizontal half of the low-pass adjoint of gS1, one fused column kernel (vertical half + modulus backward), one row
+    kernel that reduces over the angles (csrc/bwd2d.cuh)."""
 
     @staticmethod
-    def forward(ctx, U0, eng, j1, batch):
+    def forward(ctx, U0, eng, j1, batch, want_u1):
         U0 = U0.contiguous()
-        ctx.eng, ctx.j1, ctx.batch = eng, j1, batch
+        ctx.eng, ctx.j1, ctx.batch, ctx.want_u1 = eng, j1, batch, want_u1
         ctx.save_for_backward(U0)
-        return eng.order1_forward(j1, U0, batch, True)[1]
+        ctx.set_materialize_grads(False)
+        if _Recompute.active and not want_u1:      # graph rebuild of a leaf: neither value is read
+            s1 = U0.new_empty((batch, eng.geometry["L"], eng.out_h, eng.out_w))
+            u1 = U0.new_zeros((0,))
+        else:
+            s1, u1 = eng.order1_forward(j1, U0, batch, True, want_s1=not _Recompute.active)
+            if s1 is None:
+                s1 = U0.new_empty((batch, eng.geometry["L"], eng.out_h, eng.out_w))
+            if not want_u1:
+                u1 = U0.new_zeros((0,))
+        ctx.mark_non_differentiable(*(() if want_u1 else (u1,)))
+        return s1, u1
 
     @staticmethod
-    def backward(ctx, gu1):
+    def backward(ctx, gs1, gu1):
         (U0,) = ctx.saved_tensors
-        return ctx.eng.order1_backward(ctx.j1, U0, None, gu1.contiguous(), ctx.batch), None, None, None
+        gs1 = gs1.contiguous() if gs1 is not None else None
+        gu1 = gu1.contiguous() if (ctx.want_u1 and gu1 is not None) else None
+        if gs1 is None and gu1 is None:
+            return None, None, None, None, None
+        return ctx.eng.order1_backward(ctx.j1, U0, gs1, gu1, ctx.batch), None, None, None, None
 
 
 def _to_complex(x):
@@ -274,7 +290,7 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=Non
     Returns (B, K, M/2^J, N/2^J) in the reference's channel order.
     With ``eng`` (an Engine2D bound to the same filters) the first-order block of every scale (Order1Tile / Order1Stream)
     and the second-order block below it (Order2) run as fused kernels, forward and backward; what remains on the
-    per-primitive graph acts on ONE field per image (pad, U0, S0) or on the small low-pass of the full-resolution scale.
+    per-primitive graph acts on ONE field per image (pad, U0, S0).
     """
     B = x.shape[0]
     phi = [p.reshape(p.shape[0], p.shape[1]) for p in phi_levels]
@@ -301,9 +317,7 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=Non
             if mode == 1:
                 s1, U1 = Order1Tile.apply(U0, eng, j1, B, has_children)
             else:
-                U1 = Order1Stream.apply(U0, eng, j1, B)
-                s1 = _low(U1, phi[j1], 2 ** (J - j1))
-                s1 = s1.reshape((B, L) + tuple(s1.shape[1:]))
+                s1, U1 = Order1Stream.apply(U0, eng, j1, B, has_children)
             S1.append(s1)
             if has_children:
                 if eng.order2_channels(j1) > 0:
