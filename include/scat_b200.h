@@ -277,6 +277,27 @@ int  scat_modulus_rotation_bwd(const void* x_dev, const void* prev_dev, const vo
 int  scat_compute_integrals_bwd(const void* x_dev, const void* g_dev, void* gx_dev, int64_t B, int64_t n,
                                 const void* powers_f32_dev, int32_t P, int32_t dtype, void* stream);
 
+/* filter synthesis on the device (constructor path) -----------------------------------------
+ * 2-D Morlet / Gabor bank, replaces the numpy loops of kymatio/scattering2d/filter_bank.py:5-53 (bank), :94-175 (wavelets):
+ *   params_dev: n_filters x 8 doubles {c00, cross, c11, fu, fv, 1/norm, zero_mean flag, 0}: the filter is
+ *     exp(-(c00 u^2 + cross u v + c11 v^2) + i (fu u + fv v)) / norm summed over the 5x5 neighbouring periods, minus
+ *     beta * (the same with fu = fv = 0) when the flag is set, beta chosen so that the filter sums to zero;
+ *   carrier_dev: (n_filters, M, N) complex128 out (the spatial filters); envelope_dev: (n_filters, M, N) float64 scratch;
+ *   sums_dev: n_filters x 3 float64 scratch.
+ * scat_filters2d_fold: band-limit + alias fold of the real part of one (M, N) complex128 spectrum to resolution res,
+ *   (M/2^res, N/2^res) float32 out  - periodize_filter_fft, filter_bank.py:56-91. */
+int scat_filters2d_spatial(const void* params_dev, int32_t n_filters, int32_t M, int32_t N, void* carrier_dev,
+                           void* envelope_dev, void* sums_dev, void* stream);
+int scat_filters2d_fold(const void* spec_dev, void* out_dev, int32_t M, int32_t N, int32_t res, void* stream);
+/* 3-D solid harmonic wavelets of order l at n_scales widths, Fourier domain, closed form
+ * (kymatio/scattering3d/filter_bank.py:100-166): out_dev (n_scales, 2l+1, M, N, O) complex64; sigmas_dev: n_scales float64;
+ * norm: the real normalisation c_l (2 pi)^(3/2) (the factor (-i)^l is applied by the kernel).
+ * scat_filters3d_gaussian: out_dev (n_scales, M, N, O) complex64 (filter_bank.py:39-97). */
+int scat_filters3d_solid_harmonic(void* out_dev, const void* sigmas_dev, int32_t n_scales, int32_t l, double norm, int32_t M,
+                                  int32_t N, int32_t O, void* stream);
+int scat_filters3d_gaussian(void* out_dev, const void* sigmas_dev, int32_t n_scales, int32_t M, int32_t N, int32_t O,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,13 @@ SIGNATURES = {
                                               _c.c_int32, _c.c_int32, _c.c_void_p]),
     "scat_modulus_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_void_p]),
     "scat_pad2d_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int32] * 7 + [_c.c_void_p]),
+    "scat_filters2d_spatial": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p, _c.c_void_p]),
+    "scat_filters2d_fold": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_filters3d_solid_harmonic": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_double, _c.c_int32,
+                                                 _c.c_int32, _c.c_int32, _c.c_void_p]),
+    "scat_filters3d_gaussian": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32,
+                                           _c.c_void_p]),
 }
 
 

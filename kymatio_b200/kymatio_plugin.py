@@ -23,6 +23,7 @@ reference's own GPU-only backend (torch_skcuda) the primitives are CUDA-only and
 gradients are provided by the fused path.
 """
 import collections
+import os
 import ctypes
 import importlib
 import sys
@@ -713,6 +714,7 @@ def install(fused=True):
     if "scattering2d" not in _originals:
         _originals["scattering2d"] = tf2d.scattering2d
     reference_core = _originals["scattering2d"]
+    _install_filter_hooks()
 
     import kymatio.scattering1d.frontend.base_frontend as bf1d
     if "scattering1d" not in _originals:
@@ -791,7 +793,49 @@ def install(fused=True):
     return backend2d
 
 
+def _gpu_filters(frontend):
+    """Filter banks of torch_b200 frontends are synthesised on the GPU (filter_bank_gpu.py) unless SCAT_B200_GPU_FILTERS=0."""
+    return (getattr(getattr(frontend, "backend", None), "name", None) == NAME and torch.cuda.is_available()
+            and os.environ.get("SCAT_B200_GPU_FILTERS", "1") != "0")
+
+
+def _install_filter_hooks():
+    """Constructor path: ``create_filters`` of the 2-D / 3-D base frontends (kymatio/scattering2d/frontend/base_frontend.py:34-36,
+    kymatio/scattering3d/frontend/base_frontend.py:25-30) is wrapped so that a frontend bound to this backend gets the same
+    containers filled by the device-side synthesis; any other backend runs the reference's numpy code."""
+    import kymatio.scattering2d.frontend.base_frontend as bf2d
+    import kymatio.scattering3d.frontend.base_frontend as bf3d
+    if "create_filters2d" not in _originals:
+        _originals["create_filters2d"] = bf2d.ScatteringBase2D.create_filters
+        _originals["create_filters3d"] = bf3d.ScatteringBase3D.create_filters
+    ref2d, ref3d = _originals["create_filters2d"], _originals["create_filters3d"]
+
+    def create_filters2d(self):
+        if not _gpu_filters(self):
+            return ref2d(self)
+        from .filter_bank_gpu import filter_bank_2d_gpu
+        bank = filter_bank_2d_gpu(self._M_padded, self._N_padded, self.J, self.L, as_numpy=True)
+        self.phi, self.psi = bank["phi"], bank["psi"]
+    create_filters2d.__wrapped__ = ref2d
+
+    def create_filters3d(self):
+        if not _gpu_filters(self):
+            return ref3d(self)
+        from .filter_bank_gpu import solid_harmonic_filter_bank_gpu, gaussian_filter_bank_gpu
+        self.filters = solid_harmonic_filter_bank_gpu(self.M, self.N, self.O, self.J, self.L, self.sigma_0, as_numpy=True)
+        self.gaussian_filters = gaussian_filter_bank_gpu(self.M, self.N, self.O, self.J + 1, self.sigma_0, as_numpy=True)
+    create_filters3d.__wrapped__ = ref3d
+
+    bf2d.ScatteringBase2D.create_filters = create_filters2d
+    bf3d.ScatteringBase3D.create_filters = create_filters3d
+
+
 def uninstall():
+    if "create_filters2d" in _originals:
+        import kymatio.scattering2d.frontend.base_frontend as bf2d
+        import kymatio.scattering3d.frontend.base_frontend as bf3d
+        bf2d.ScatteringBase2D.create_filters = _originals["create_filters2d"]
+        bf3d.ScatteringBase3D.create_filters = _originals["create_filters3d"]
     if "scattering2d" in _originals:
         import kymatio.scattering2d.frontend.torch_frontend as tf2d
         tf2d.scattering2d = _originals["scattering2d"]

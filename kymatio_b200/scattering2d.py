@@ -9,6 +9,8 @@ loop of core/scattering2d.py:14-86 does not run here: ``forward`` is one call in
 libscat_b200.so.  CUDA only - CPU tensors raise, as kymatio's own GPU-only backend does
 (kymatio/scattering2d/backend/torch_skcuda_backend.py:68-69).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -45,7 +47,13 @@ class Scattering2D(nn.Module):
         self._M_padded, self._N_padded = padded_size_2d(M, N, self.J)
 
     def create_filters(self):
-        filters = filter_bank_2d(self._M_padded, self._N_padded, self.J, self.L)
+        # synthesised on the device when one is visible (filter_bank_gpu.py, milliseconds); the numpy bank (seconds at
+        # 272 x 272) is the construction path of CPU-only hosts - both match the reference's filters to float32 rounding
+        if torch.cuda.is_available() and os.environ.get("SCAT_B200_GPU_FILTERS", "1") != "0":
+            from .filter_bank_gpu import filter_bank_2d_gpu
+            filters = filter_bank_2d_gpu(self._M_padded, self._N_padded, self.J, self.L, as_numpy=True)
+        else:
+            filters = filter_bank_2d(self._M_padded, self._N_padded, self.J, self.L)
         self.phi, self.psi = filters["phi"], filters["psi"]
 
     def register_filters(self):

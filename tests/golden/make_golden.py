@@ -10,6 +10,7 @@ Outputs (all small .npz, committed):
   golden_2d_*.npz            reference numpy frontend on seeded inputs
                              (float64 input -> float64 oracle)
   golden_filters_2d.npz      checksums + samples of the reference filter bank
+  golden_filters_3d.npz      reference solid-harmonic / Gaussian banks (small: full arrays; 32^3: checksums + samples)
   golden_1d_*.npz, golden_3d_*.npz  the same for the 1D / 3D frontends
 
 The reference is imported with the sph_harm shim (scipy >= 1.15 removed
@@ -133,6 +134,28 @@ def golden_3d_c4():
          shape=np.array((128, 128, 128)), x_first8=x.ravel()[:8], x_sum=np.float64(x.astype(np.float64).sum()))
 
 
+def golden_filters_3d():
+    """Reference solid-harmonic / Gaussian banks: full arrays at small (even and odd) sizes, checksums at 32^3."""
+    from kymatio.scattering3d.filter_bank import solid_harmonic_filter_bank, gaussian_filter_bank
+    out = {}
+    for (M, N, O, J, L, s0) in [(8, 10, 12, 2, 3, 1.0), (9, 8, 7, 1, 2, 1.5), (32, 32, 32, 2, 2, 1.0)]:
+        key = f"{M}x{N}x{O}_J{J}_L{L}"
+        bank = solid_harmonic_filter_bank(M, N, O, J, L, s0)
+        gauss = gaussian_filter_bank(M, N, O, J, s0)
+        out[key + "_cfg"] = np.array([M, N, O, J, L, s0], dtype=np.float64)
+        if M * N * O <= 1000:
+            for l, b in enumerate(bank):
+                out[key + f"_l{l}"] = b
+            out[key + "_gauss"] = gauss
+        else:
+            for l, b in enumerate(bank):
+                out[key + f"_l{l}_sum"] = b.reshape(b.shape[0], b.shape[1], -1).astype(np.complex128).sum(-1)
+                out[key + f"_l{l}_l2"] = np.sqrt((np.abs(b.reshape(b.shape[0], b.shape[1], -1).astype(np.complex128)) ** 2).sum(-1))
+                out[key + f"_l{l}_samples"] = b.reshape(b.shape[0], b.shape[1], -1)[:, :, ::997]
+            out[key + "_gauss_samples"] = gauss.reshape(gauss.shape[0], -1)[:, ::997]
+    save("golden_filters_3d.npz", **out)
+
+
 def golden_3d():
     rng = np.random.RandomState(11)
     cases = [
@@ -153,6 +176,7 @@ def golden_3d():
 if __name__ == "__main__":
     resave_fixtures()
     golden_filters_2d()
+    golden_filters_3d()
     golden_2d()
     golden_1d()
     golden_3d()

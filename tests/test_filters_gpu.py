@@ -1,0 +1,118 @@
+"""Device-side filter synthesis (csrc/filters.cuh) against reference-generated fixtures and the numpy product bank."""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat(fb):
+    out = list(fb["phi"]["levels"])
+    for p in fb["psi"]:
+        out.extend(p["levels"])
+    return out
+
+
+@pytest.mark.parametrize("cfg", [(40, 40, 2, 8), (48, 64, 2, 6), (64, 64, 4, 8), (272, 272, 3, 8)])
+def test_gpu_bank_2d_matches_reference_checksums(golden_dir, cfg):
+    """Same gate as tests/test_filter_bank_2d.py applies to the numpy product bank (fixtures: tests/golden/make_golden.py,
+    from kymatio/scattering2d/filter_bank.py:5-53)."""
+    from kymatio_b200.filter_bank_gpu import filter_bank_2d_gpu
+    Mp, Np, J, L = cfg
+    g = np.load(os.path.join(golden_dir, "golden_filters_2d.npz"))
+    key = f"{Mp}x{Np}_J{J}_L{L}"
+    fb = filter_bank_2d_gpu(Mp, Np, J, L, as_numpy=True)
+    assert [p["j"] for p in fb["psi"]] == [n // L for n in range(J * L)]
+    assert [p["theta"] for p in fb["psi"]] == [n % L for n in range(J * L)]
+    levels = _flat(fb)
+    assert len(levels) == len(g[key + "_sum"])
+    for i, lev in enumerate(levels):
+        assert lev.dtype == np.float32
+        scale = max(1.0, g[key + "_l2"][i])
+        assert abs(lev.sum(dtype=np.float64) - g[key + "_sum"][i]) <= 2e-5 * scale
+        assert abs(np.sqrt((lev.astype(np.float64) ** 2).sum()) - g[key + "_l2"][i]) <= 1e-6 * scale
+        samp = lev.ravel()[:: max(1, lev.size // 16)][:16]
+        assert np.abs(samp - g[key + "_samples"][i]).max() <= 1e-6
+    if Mp <= 64:
+        assert np.abs(fb["phi"]["levels"][0] - g[key + "_phi0"]).max() <= 1e-6
+        assert np.abs(fb["psi"][-1]["levels"][0] - g[key + "_psi_last_l0"]).max() <= 1e-6
+        assert np.abs(fb["psi"][3]["levels"][0] - g[key + "_psi3_l0"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("cfg", [(40, 48, 3, 4), (272, 272, 3, 8), (256, 256, 4, 8)])
+def test_gpu_bank_2d_matches_numpy_bank_elementwise(cfg):
+    from kymatio_b200.filter_bank2d import filter_bank_2d
+    from kymatio_b200.filter_bank_gpu import filter_bank_2d_gpu
+    Mp, Np, J, L = cfg
+    a, b = _flat(filter_bank_2d_gpu(Mp, Np, J, L, as_numpy=True)), _flat(filter_bank_2d(Mp, Np, J, L))
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape
+        assert np.abs(x - y).max() <= 2e-6 * max(1.0, np.abs(y).max())
+
+
+def test_gpu_bank_2d_chunked_equals_one_shot():
+    from kymatio_b200.filter_bank_gpu import filter_bank_2d_gpu
+    a = _flat(filter_bank_2d_gpu(48, 64, 3, 8, as_numpy=True))
+    b = _flat(filter_bank_2d_gpu(48, 64, 3, 8, as_numpy=True, max_bytes=3 * 48 * 64 * 40))
+    for x, y in zip(a, b):          # equal up to the summation order of the zero-mean correction's atomics
+        assert np.abs(x - y).max() <= 1e-9
+
+
+@pytest.mark.parametrize("key", ["8x10x12_J2_L3", "9x8x7_J1_L2", "32x32x32_J2_L2"])
+def test_gpu_bank_3d_matches_reference(golden_dir, key):
+    """Fixtures from kymatio/scattering3d/filter_bank.py:5-166 (even and odd axis lengths; 32^3 by checksums + samples)."""
+    from kymatio_b200.filter_bank_gpu import solid_harmonic_filter_bank_gpu, gaussian_filter_bank_gpu
+    g = np.load(os.path.join(golden_dir, "golden_filters_3d.npz"))
+    M, N, O, J, L, s0 = g[key + "_cfg"]
+    M, N, O, J, L = int(M), int(N), int(O), int(J), int(L)
+    bank = solid_harmonic_filter_bank_gpu(M, N, O, J, L, float(s0), as_numpy=True)
+    gauss = gaussian_filter_bank_gpu(M, N, O, J, float(s0), as_numpy=True)
+    assert len(bank) == L + 1
+    for l, b in enumerate(bank):
+        assert b.dtype == np.complex64 and b.shape == (J + 1, 2 * l + 1, M, N, O)
+        if key + f"_l{l}" in g.files:
+            assert np.abs(b - g[key + f"_l{l}"]).max() <= 5e-7
+        else:
+            flat = b.reshape(J + 1, 2 * l + 1, -1)
+            # float32 rounding of every voxel of the reference (6e-8 relative): |sum of errors| <= sqrt(n) * |errors|_2
+            tol = 2e-7 * np.sqrt(flat.shape[-1]) * g[key + f"_l{l}_l2"]
+            assert (np.abs(flat.astype(np.complex128).sum(-1) - g[key + f"_l{l}_sum"]) <= tol).all()
+            assert np.abs(np.sqrt((np.abs(flat.astype(np.complex128)) ** 2).sum(-1)) - g[key + f"_l{l}_l2"]).max() <= 1e-5
+            assert np.abs(flat[:, :, ::997] - g[key + f"_l{l}_samples"]).max() <= 5e-7
+    assert gauss.dtype == np.complex64 and gauss.shape == (J + 1, M, N, O)
+    if key + "_gauss" in g.files:
+        assert np.abs(gauss - g[key + "_gauss"]).max() <= 5e-7
+    else:
+        assert np.abs(gauss.reshape(J + 1, -1)[:, ::997] - g[key + "_gauss_samples"]).max() <= 5e-7
+
+
+def test_plugin_frontends_use_gpu_synthesis(golden_dir):
+    """kymatio.torch frontends bound to torch_b200 build their banks through the device kernels (launch counter moves,
+    constructor is fast) and still reproduce the reference-generated golden outputs."""
+    from conftest import import_reference
+    if not import_reference():
+        pytest.skip("reference not installed under baseline/_ref")
+    from kymatio_b200 import _lib, kymatio_plugin
+    kymatio_plugin.install()
+    from kymatio.torch import Scattering2D, HarmonicScattering3D
+    n0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    g = np.load(os.path.join(golden_dir, "golden_2d_J3_240.npz"))
+    S = Scattering2D(J=int(g["J"]), shape=tuple(int(v) for v in g["shape"]), L=int(g["L"]), backend="torch_b200").cuda()
+    dt = time.perf_counter() - t0
+    assert _lib.launch_count() > n0
+    y = S(torch.from_numpy(g["x"]).cuda()).double().cpu().numpy()
+    assert np.abs(y - g["Sx64"]).max() <= 1e-4 * np.abs(g["Sx64"]).max()
+    print(f"constructor with device-side synthesis: {dt * 1e3:.1f} ms")
+
+    g3 = np.load(os.path.join(golden_dir, "golden_3d_J2_L2_16.npz"))
+    n0 = _lib.launch_count()
+    S3 = HarmonicScattering3D(J=2, shape=(16, 16, 16), L=2, backend="torch_b200").cuda()
+    assert _lib.launch_count() > n0
+    y3 = S3(torch.from_numpy(g3["x"]).cuda()).double().cpu().numpy()
+    assert np.abs(y3 - g3["Sx64"]).max() <= 1e-4 * np.abs(g3["Sx64"]).max()
+    kymatio_plugin.uninstall()
