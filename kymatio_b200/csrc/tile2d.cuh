@@ -24,7 +24,7 @@ namespace sb {
 // every CTA adds the cycles between phase boundaries to g_phase_cycles[kernel id][phase]; read back through
 // scat_phase_prof_read (tile_inst.cu).  The production build compiles none of it.
 #ifdef SB_PHASE_PROF
-constexpr int kPhaseKinds = 24, kPhaseSlots = 8;
+constexpr int kPhaseKinds = 32, kPhaseSlots = 8;   // 0..23 forward tiles, 24..31 backward tiles
 static __device__ unsigned long long g_phase_cycles[kPhaseKinds * kPhaseSlots];
 #define SB_PHASE_INIT(kid_expr) const int sb_kid = (kid_expr); long long sb_t_last = clock64();
 #define SB_PHASE(i)                                                                            \
@@ -720,17 +720,25 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
     stage(m.tw0, a.tw0, n0); stage(m.tw1, a.tw1, n1);
     stage(m.pos0, a.pos0, n0); stage(m.pos1, a.pos1, n1);
     stage(reinterpret_cast<re4<T>*>(m.G0), reinterpret_cast<const re4<T>*>(a.G0), n0 * a.o0p / 4);
-    stage(reinterpret_cast<re4<T>*>(m.G1), reinterpret_cast<const re4<T>*>(a.G1), n1 * a.o1p / 4);
     __syncthreads();
-    // the low-pass is banded: row x of G1 touches only outputs [first, last] (a few of them, all for the
-    // full-circle level); found once per persistent CTA
+    // G1 is held TRANSPOSED and in the storage order of the tile's columns, G1s[xo][xs] = G1[x][xo] with xs = pos1[x]:
+    // step 3b walks the tile in storage order, so its three shared-memory streams (tile, G1s, xr) are all unit-stride
+    // across a warp (the natural-order [x][o1p] layout put a whole warp on one or two banks).
+    // The low-pass is banded: column x touches only outputs [first, last] (a few of them, all for the full-circle
+    // level); found once per persistent CTA
     for (int x = tid; x < n1; x += nt) {
+        const int xs = ST ? m.pos1[x] : x;
+        const T* __restrict__ gr = a.G1 + (size_t)x * a.o1p;
         int first = a.o1, last = -1;
-        for (int xo = 0; xo < a.o1; ++xo)
-            if (m.G1[x * a.o1p + xo] != T(0)) { if (first == a.o1) first = xo; last = xo; }
-        m.xr[x] = make_int2(first, last);
+        for (int xo = 0; xo < a.o1p; ++xo) {
+            const T v = xo < a.o1 ? gr[xo] : T(0);
+            m.G1[xo * n1 + xs] = v;
+            if (v != T(0)) { if (first == a.o1) first = xo; last = xo; }
+        }
+        m.xr[xs] = make_int2(first, last);
     }
 
+    SB_PHASE_INIT(24 + (n0 >= 128 ? 0 : n0 >= 64 ? 1 : n0 >= 32 ? 2 : 3) * 2 + (k > 2 ? 1 : 0))
     for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
         const int fi = g % a.NF, pg = g / a.NF;
         const int b = g / a.PP, path = g - b * a.PP;
@@ -744,6 +752,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             }
         }
         __syncthreads();
+        SB_PHASE(0);
         const cx<T>* __restrict__ pb = a.parent + (size_t)pg * a.P0 * a.P1;
         const T* __restrict__ fb = a.filt[fi];
         const int P1 = a.P1;
@@ -761,6 +770,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
                 tile_load_item<T, 2, KT, ST>(s, m, m.supp, pb, fb, r0, e0, k, n0, n1, W, P1, a.scale, lane);
             }
         }
+        SB_PHASE(1);
         // 3a. T[row][xo] = sum_yo G0[y][yo] * gS[yo][xo]   (row = storage row of y) - independent of the tile
         for (int it = tid; it < n0 * a.o1p; it += nt) {
             const int y = it / a.o1p, xo = it - y * a.o1p;
@@ -769,6 +779,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             m.w1[(ST ? m.pos0[y] : y) * wp + xo] = acc;
         }
         __syncthreads();
+        SB_PHASE(2);
         // 2. inverse 2-D FFT (no modulus): static -> scrambled spatial order, generic -> natural
         if constexpr (ST) {
             slab_fft_s<N1, false, +1, (N1 | 1), 1, T>(s, N0, m.tw1);
@@ -777,23 +788,26 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             slab_fft<true, T>(s, n0, W, 1, a.plan1, m.tw1);
             slab_fft<true, T>(s, n1, 1, W, a.plan0, m.tw0);
         }
+        SB_PHASE(3);
         // 3b. gu = (sum_xo T[row][xo] G1[x][xo]) * u / |u|
         for (int it = tid; it < n0 * n1; it += nt) {
-            const int q = it / n1, x = it - q * n1;
+            const int q = it / n1, xs = it - q * n1;
             const T* __restrict__ tr = m.w1 + q * wp;
-            const T* __restrict__ gr = m.G1 + x * a.o1p;
+            const T* __restrict__ gc = m.G1 + xs;
             T gA = T(0);
-            const int2 rng = m.xr[x];
-            for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gr[xo];
-            const int xs = ST ? m.pos1[x] : x;
-            if (a.radd) gA += a.radd[(size_t)g * n0 * n1 + q * n1 + xs];
+            const int2 rng = m.xr[xs];
+            for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gc[xo * n1];
+            if (a.radd) gA += a.radd[(size_t)g * n0 * n1 + it];
             const int idx = q * W + xs;
             const cx<T> v = s[idx];
-            const T mag = sqrt(v.x * v.x + v.y * v.y);
-            const T sc = mag > T(0) ? gA / mag : T(0);
+            const T m2 = v.x * v.x + v.y * v.y;
+            T sc;
+            if constexpr (std::is_same<T, float>::value) sc = m2 > 0.f ? gA * rsqrtf(m2) : 0.f;
+            else sc = m2 > T(0) ? gA / sqrt(m2) : T(0);
             s[idx] = mk<T>(v.x * sc, v.y * sc);
         }
         __syncthreads();
+        SB_PHASE(4);
         // 4. forward 2-D FFT: static DIT(-) -> natural Fourier order; generic DIF -> scrambled (read through pos)
         if constexpr (ST) {
             slab_fft_s<N0, true, -1, 1, (N1 | 1), T>(s, N1, m.tw0);
@@ -802,6 +816,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             slab_fft<false, T>(s, n0, W, 1, a.plan1, m.tw1);
             slab_fft<false, T>(s, n1, 1, W, a.plan0, m.tw0);
         }
+        SB_PHASE(5);
         // 5. adjoint of periodise + filter multiply, accumulated into the parent gradient.  float, even sizes: TWO adjacent
         //    bins per thread and one 16-byte vector reduction (red.global.add.v4.f32, sm_90+) instead of four scalar
         //    atomics - the scatter of the children of one parent is bound by the number of L2 reduction operations
@@ -859,6 +874,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             }
         }
         __syncthreads();
+        SB_PHASE(6);
     }
 }
 
