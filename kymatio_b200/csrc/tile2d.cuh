@@ -86,10 +86,13 @@ template <typename T> __host__ __device__ inline size_t tile_smem_layout(const T
     // tt mode: two w1 halves (the x window is split over two work items) and the tap tables in place of G0/G1
     const size_t o_w1 = take(a.tt ? sizeof(T) * 2 * (size_t)a.n0 * (a.o1p + 4) : sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o1p + 8));
     const size_t o_g0 = take(a.tt ? sizeof(T) * 4 * (size_t)a.y0cnt : sizeof(T) * (size_t)((a.n0 + 7) & ~7) * (a.o0p + 8));
-    const size_t o_g1 = take(a.tt ? sizeof(T) * 4 * (size_t)a.x1cnt : sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8));
-    const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
     // backward only (the forward kernel must not pay for them: 68 x 68 tiles fit three per SM without)
     const bool bwd = a.gparent != nullptr;
+    // the backward kernel keeps G1 transposed, [o1p][n1 rounded up to 32] (tile_bwd_body)
+    const size_t g1_fwd = a.tt ? sizeof(T) * 4 * (size_t)a.x1cnt : sizeof(T) * (size_t)((a.n1 + 7) & ~7) * (a.o1p + 8);
+    const size_t g1_bwd = bwd ? sizeof(T) * (size_t)a.o1p * ((a.n1 + 31) & ~31) : 0;
+    const size_t o_g1 = take(g1_fwd > g1_bwd ? g1_fwd : g1_bwd);
+    const size_t o_p0 = take(sizeof(int) * a.n0), o_p1 = take(sizeof(int) * a.n1);
     const size_t o_gs = take(bwd ? sizeof(T) * (size_t)a.o0p * a.o1p : 0);   // staged output-plane gradient
     const size_t o_xr = take(bwd ? sizeof(int2) * (size_t)a.n1 : 0);         // nonzero output range of each G1 row
     const size_t o_i0 = take(a.pin0 ? sizeof(int) * a.n0 : 0), o_i1 = take(a.pin0 ? sizeof(int) * a.n1 : 0);
@@ -726,13 +729,14 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
     // across a warp (the natural-order [x][o1p] layout put a whole warp on one or two banks).
     // The low-pass is banded: column x touches only outputs [first, last] (a few of them, all for the full-circle
     // level); found once per persistent CTA
+    const int g1p = (n1 + 31) & ~31;           // pitch = 0 mod 32 banks: lanes with different xo never collide
     for (int x = tid; x < n1; x += nt) {
         const int xs = ST ? m.pos1[x] : x;
         const T* __restrict__ gr = a.G1 + (size_t)x * a.o1p;
         int first = a.o1, last = -1;
         for (int xo = 0; xo < a.o1p; ++xo) {
             const T v = xo < a.o1 ? gr[xo] : T(0);
-            m.G1[xo * n1 + xs] = v;
+            m.G1[xo * g1p + xs] = v;
             if (v != T(0)) { if (first == a.o1) first = xo; last = xo; }
         }
         m.xr[xs] = make_int2(first, last);
@@ -757,7 +761,13 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
         const T* __restrict__ fb = a.filt[fi];
         const int P1 = a.P1;
         // 1. recompute the product + periodise
-        if ((n1 & 3) == 0 && (P1 & 3) == 0) {
+        if constexpr (ST && KT > 0 && (N1 & 3) == 0) {
+            constexpr int per_row = N1 >> 2, items = N0 * per_row;
+            for (int it = tid; it < items; it += nt) {
+                const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
+                tile_load_item_s<T, N0, N1, KT, false>(s, m.supp, pb, fb, r0, e0, a.scale, lane, nullptr, nullptr);
+            }
+        } else if ((n1 & 3) == 0 && (P1 & 3) == 0) {
             const int per_row = n1 >> 2, items = n0 * per_row;
             for (int it = tid; it < items; it += nt) {
                 const int r0 = it / per_row, e0 = 4 * (it - r0 * per_row);
@@ -796,7 +806,7 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             const T* __restrict__ gc = m.G1 + xs;
             T gA = T(0);
             const int2 rng = m.xr[xs];
-            for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gc[xo * n1];
+            for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gc[xo * g1p];
             if (a.radd) gA += a.radd[(size_t)g * n0 * n1 + it];
             const int idx = q * W + xs;
             const cx<T> v = s[idx];

@@ -24,11 +24,12 @@ template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bo
     return k2d_tile<T, 0, 0, 0, true>;
 }
 
-// backward instances: the generic alias-count version (K = 0) per static size keeps compile time in check
+// backward instances: alias counts 2 and 4 static, the generic alias-count version (K = 0) for the rest
 template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k, bool* is_static) {
     if (is_static) *is_static = true;
     if (n0 == n1) {
-#define SB_CASE(N) if (n0 == N) { if (k == 2) return k2d_tile_bwd<T, N, N, 2>; return k2d_tile_bwd<T, N, N, 0>; }
+#define SB_CASE(N) if (n0 == N) { if (k == 2) return k2d_tile_bwd<T, N, N, 2>; if (k == 4) return k2d_tile_bwd<T, N, N, 4>; \
+                                 return k2d_tile_bwd<T, N, N, 0>; }
         SB_TILE_SIZES(SB_CASE)
 #undef SB_CASE
     }
@@ -42,7 +43,8 @@ template <typename T> void tile_kernels_enable_smem() {
     SB_TILE_SIZES(SB_EN)
 #undef SB_EN
     enable_big_smem(k2d_tile<T, 0, 0, 0, true>);
-#define SB_ENB(N) enable_big_smem(k2d_tile_bwd<T, N, N, 0>); enable_big_smem(k2d_tile_bwd<T, N, N, 2>);
+#define SB_ENB(N) enable_big_smem(k2d_tile_bwd<T, N, N, 0>); enable_big_smem(k2d_tile_bwd<T, N, N, 2>); \
+                  enable_big_smem(k2d_tile_bwd<T, N, N, 4>);
     SB_TILE_SIZES(SB_ENB)
 #undef SB_ENB
     enable_big_smem(k2d_tile_bwd<T, 0, 0, 0>);

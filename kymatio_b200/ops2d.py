@@ -268,6 +268,44 @@ def _low(U, phi_level, k):
     return Fft2.apply(Z, True)[..., 1:-1, 1:-1, 0]
 
 
+class LowPassLeaf(torch.autograd.Function):
+    """``_low`` as ONE graph node for an output that nothing else consumes (S0): the forward is skipped while the graph is
+    only being rebuilt (``_Recompute``), the backward is the hand-written adjoint chain - zero-embed, forward transform / N,
+    replicate / k^2 (adjoint of the periodisation), multiply by phi."""
+
+    @staticmethod
+    def forward(ctx, U, phi_level, k):
+        U = U.contiguous()
+        ctx.k, ctx.shape = k, U.shape
+        ctx.save_for_backward(phi_level)
+        G, n0, n1 = U.shape[0], U.shape[1], U.shape[2]
+        if _Recompute.active:
+            return U.new_empty((G, n0 // k - 2, n1 // k - 2))
+        with torch.no_grad():
+            return _low(U, phi_level, k).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        (phi_level,) = ctx.saved_tensors
+        G, n0, n1, _ = ctx.shape
+        k, m0, m1 = ctx.k, n0 // ctx.k, n1 // ctx.k
+        lib = _lib.load()
+        gz = g.new_zeros((G, m0, m1, 2))
+        gz[:, 1:-1, 1:-1, 0] = g
+        gZ = _fft2_raw(gz, False)
+        gZ.mul_(1.0 / (m0 * m1))
+        gV = torch.empty(ctx.shape, dtype=g.dtype, device=g.device)
+        gU = torch.empty(ctx.shape, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            if k > 1:
+                _lib.check(lib.scat_subsample_fourier2d_bwd(gZ.data_ptr(), gV.data_ptr(), G, n0, n1, k, _code(g), _st(g)))
+            else:
+                gV = gZ
+            W = phi_level.contiguous()
+            _lib.check(lib.scat_cdgmm_bcast(gV.data_ptr(), W.data_ptr(), gU.data_ptr(), G, 1, n0 * n1, 1, _code(g), _st(g)))
+        return gU, None, None
+
+
 def _order2_per_op(U1, psi, phi, j1, J, L, B):
     """All second-order paths below first-order scale j1 on the per-primitive differentiable ops (core:55-83)."""
     per_j2 = []
@@ -307,7 +345,7 @@ def eager_scattering2d(x, J, L, max_order, pads, phi_levels, psi_levels, eng=Non
 
     xp = PadReflect.apply(x, tuple(pads)) if pads is not None else x
     U0 = Fft2.apply(_to_complex(xp), False)
-    S0 = _low(U0, phi[0], 2 ** J)[:, None]
+    S0 = LowPassLeaf.apply(U0, phi[0], 2 ** J)[:, None]
     S1, S2 = [], []
     for j1 in range(J):
         has_children = max_order >= 2 and j1 < J - 1
