@@ -730,6 +730,9 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
     // The low-pass is banded: column x touches only outputs [first, last] (a few of them, all for the full-circle
     // level); found once per persistent CTA
     const int g1p = (n1 + 31) & ~31;           // pitch = 0 mod 32 banks: lanes with different xo never collide
+    int* s_maxband = reinterpret_cast<int*>(m.gs);      // scratch word (gs is staged per path, later); no static shared
+    if (tid == 0) *s_maxband = 0;                       // memory: the kernels opt in to the full dynamic carve-out
+    __syncthreads();
     for (int x = tid; x < n1; x += nt) {
         const int xs = ST ? m.pos1[x] : x;
         const T* __restrict__ gr = a.G1 + (size_t)x * a.o1p;
@@ -740,7 +743,22 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             if (v != T(0)) { if (first == a.o1) first = xo; last = xo; }
         }
         m.xr[xs] = make_int2(first, last);
+        if (last >= first) atomicMax(s_maxband, last - first + 1);
     }
+    __syncthreads();
+    const int maxband = *s_maxband;
+    __syncthreads();
+    // step 3b work split: a thread owns ONE column xs and a group of rows, so the column's taps stay in registers.
+    // RG row groups: minimise (rounds over the threads) x (rows per group)
+    int RG = 1;
+    {
+        int best = 1 << 30;
+        for (int rg = 1; rg <= 16 && rg <= n0; ++rg) {
+            const int cost = ((n1 * rg + nt - 1) / nt) * ((n0 + rg - 1) / rg);
+            if (cost < best) { best = cost; RG = rg; }
+        }
+    }
+    const int RP = (n0 + RG - 1) / RG;
 
     SB_PHASE_INIT(24 + (n0 >= 128 ? 0 : n0 >= 64 ? 1 : n0 >= 32 ? 2 : 3) * 2 + (k > 2 ? 1 : 0))
     for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
@@ -800,14 +818,8 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
         }
         SB_PHASE(3);
         // 3b. gu = (sum_xo T[row][xo] G1[x][xo]) * u / |u|
-        for (int it = tid; it < n0 * n1; it += nt) {
-            const int q = it / n1, xs = it - q * n1;
-            const T* __restrict__ tr = m.w1 + q * wp;
-            const T* __restrict__ gc = m.G1 + xs;
-            T gA = T(0);
-            const int2 rng = m.xr[xs];
-            for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gc[xo * g1p];
-            if (a.radd) gA += a.radd[(size_t)g * n0 * n1 + it];
+        auto modulus_bwd = [&](int q, int xs, T gA) {
+            if (a.radd) gA += a.radd[(size_t)g * n0 * n1 + q * n1 + xs];
             const int idx = q * W + xs;
             const cx<T> v = s[idx];
             const T m2 = v.x * v.x + v.y * v.y;
@@ -815,6 +827,40 @@ __device__ __forceinline__ void tile_bwd_body(const TileArgs<T>& a) {
             if constexpr (std::is_same<T, float>::value) sc = m2 > 0.f ? gA * rsqrtf(m2) : 0.f;
             else sc = m2 > T(0) ? gA / sqrt(m2) : T(0);
             s[idx] = mk<T>(v.x * sc, v.y * sc);
+        };
+        // banded low-pass (every level but the full-circle one): MT taps of the thread's column in registers, static inner
+        // loop; the tap window is clamped into [0, o1p - MT] (G1 is zero outside the band, so the extra taps are zeros)
+        auto cols = [&](auto mt_) {
+            constexpr int MT = decltype(mt_)::value;
+            for (int it = tid; it < n1 * RG; it += nt) {
+                const int rg = it / n1, xs = it - rg * n1;
+                const int lo = min(max(m.xr[xs].x, 0), a.o1p - MT);
+                T tap[MT];
+#pragma unroll
+                for (int j = 0; j < MT; ++j) tap[j] = m.G1[(lo + j) * g1p + xs];
+                const int q1 = min(n0, (rg + 1) * RP);
+#pragma unroll 2
+                for (int q = rg * RP; q < q1; ++q) {
+                    const T* __restrict__ tr = m.w1 + q * wp + lo;
+                    T gA = T(0);
+#pragma unroll
+                    for (int j = 0; j < MT; ++j) gA += tr[j] * tap[j];
+                    modulus_bwd(q, xs, gA);
+                }
+            }
+        };
+        if (maxband <= 8 && a.o1p >= 8) cols(std::integral_constant<int, 8>{});
+        else if (maxband <= 16 && a.o1p >= 16) cols(std::integral_constant<int, 16>{});
+        else {
+            for (int it = tid; it < n0 * n1; it += nt) {
+                const int q = it / n1, xs = it - q * n1;
+                const T* __restrict__ tr = m.w1 + q * wp;
+                const T* __restrict__ gc = m.G1 + xs;
+                T gA = T(0);
+                const int2 rng = m.xr[xs];
+                for (int xo = rng.x; xo <= rng.y; ++xo) gA += tr[xo] * gc[xo * g1p];
+                modulus_bwd(q, xs, gA);
+            }
         }
         __syncthreads();
         SB_PHASE(4);
