@@ -87,6 +87,13 @@ int  scat_plan2d_forward(scat_plan2d* plan, const void* x_dev, void* out_dev, vo
 int  scat_plan2d_forward_peers(scat_plan2d* plan, const void* x_dev, void* out_dev, void* const* peer_out_dev,
                                int32_t n_peers, void* ws_dev, size_t ws_bytes, int64_t batch, void* stream);
 
+/* The same forward that KEEPS the first-order spectra for a later backward pass (what an autograd engine saves between
+ * kymatio/scattering2d/core/scattering2d.py:43-45 and its backward): saved_u1_dev is a HOST array of J device pointers;
+ * entry j1 (NULL: not kept) receives U1 of scale j1 for the whole batch, (batch*L, Mp/2^j1, Np/2^j1) complex, natural order -
+ * the `u1_dev` operand of scat_plan2d_order2_backward and the tensor scat_plan2d_order1_forward would recompute. */
+int  scat_plan2d_forward_save(scat_plan2d* plan, const void* x_dev, void* out_dev, void* const* saved_u1_dev, void* ws_dev,
+                              size_t ws_bytes, int64_t batch, void* stream);
+
 /* First-order block of scale j1 as a stand-alone differentiable operator on a caller-provided U0 = fft2(pad(x))
  * (kymatio/scattering2d/core/scattering2d.py:30-51; gradients: SURVEY Appendix B, kymatio/backend/torch_backend.py:64-96).
  * mode 1 (the field fits one CTA): forward returns S1 (batch, L, oh, ow) and, when u1_dev != NULL, U1 = fft2(|.|)

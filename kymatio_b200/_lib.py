@@ -46,6 +46,8 @@ SIGNATURES = {
                                        _c.c_int64, _c.c_void_p]),
     "scat_plan2d_forward_peers": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_int32,
                                              _c.c_void_p, _c.c_size_t, _c.c_int64, _c.c_void_p]),
+    "scat_plan2d_forward_save": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_void_p,
+                                            _c.c_size_t, _c.c_int64, _c.c_void_p]),
     "scat_plan2d_order1_mode": (_c.c_int32, [_c.c_void_p, _c.c_int32]),
     "scat_plan2d_order1_workspace_bytes": (_c.c_size_t, [_c.c_void_p, _c.c_int32, _c.c_int64]),
     "scat_plan2d_order1_forward": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64,

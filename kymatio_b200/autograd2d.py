@@ -13,13 +13,16 @@ class _Scattering2DFn(torch.autograd.Function):
     def forward(ctx, x, eng):
         ctx.eng = eng
         ctx.save_for_backward(x)
-        return eng.forward(x)
+        # the first-order spectra are kept for the backward when they fit (Engine2D.saved_u1_buffers)
+        out, ctx.saved_u1 = eng.forward_saving(x)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
         (x,) = ctx.saved_tensors
         eng = ctx.eng
-        return eng.backward(x, grad_out.contiguous()), None
+        saved, ctx.saved_u1 = ctx.saved_u1, None
+        return eng.backward(x, grad_out.contiguous(), saved), None
 
 
 def scattering2d_apply(eng, x):

@@ -31,6 +31,8 @@ struct scat_plan2d {
     virtual size_t workspace_bytes(int64_t batch) const = 0;
     virtual void forward(const void* x, void* out, void* ws, size_t ws_bytes, int64_t batch, cudaStream_t st) = 0;
     // the same forward, every coefficient plane also stored at the same offset of n_peers more buffers (peer GPUs)
+    virtual void forward_save(const void* x, void* out, void* const* saved_u1, void* ws, size_t ws_bytes, int64_t batch,
+                              cudaStream_t st) = 0;
     virtual void forward_peers(const void* x, void* out, void* const* peer_out, int n_peers, void* ws, size_t ws_bytes,
                                int64_t batch, cudaStream_t st) = 0;
     // second-order block of first-order scale j1 on caller-provided parent spectra (autograd building block)
@@ -270,10 +272,22 @@ public:
             const int B = (int)std::min<int64_t>(chunk, batch - b0);
             peers_.n = n_peer_base_;
             for (int i = 0; i < std::max(n_peer_base_, n_peer_base_ < 0 ? 1 : 0); ++i) peers_.p[i] = peer_base_[i] + b0 * out_img;
+            for (int j = 0; j < d_.J; ++j)
+                save_cur_[j] = (j < (int)save_base_.size() && save_base_[j]) ? save_base_[j] + (size_t)b0 * d_.L * fsize(j) : nullptr;
             forward_chunk(static_cast<const T*>(x) + b0 * in_img, static_cast<T*>(out) + b0 * out_img,
                           static_cast<cx<T>*>(ws), B, st);
         }
         peers_.n = 0;
+    }
+    // forward that KEEPS the first-order spectra: saved_u1[j1] (null: not kept) receives U1 of scale j1 for the whole batch,
+    // [batch*L][n0_j1][n1_j1] - the operands the backward blocks (order1_backward / order2_backward) would otherwise recompute
+    void forward_save(const void* x, void* out, void* const* saved_u1, void* ws, size_t ws_bytes, int64_t batch,
+                      cudaStream_t st) override {
+        save_base_.assign(d_.J, nullptr);
+        for (int j = 0; j < d_.J; ++j) save_base_[j] = static_cast<cx<T>*>(saved_u1[j]);
+        try { forward(x, out, ws, ws_bytes, batch, st); } catch (...) { save_base_.clear(); throw; }
+        save_base_.clear();
+        for (auto& p : save_cur_) p = nullptr;
     }
     void forward_peers(const void* x, void* out, void* const* peer_out, int n_peers, void* ws, size_t ws_bytes,
                        int64_t batch, cudaStream_t st) override {
@@ -811,8 +825,11 @@ private:
         // S0 (core/scattering2d.py:18-28)
         low_pass(U0, 0, out, B, 1, 1, 0, 0, TL, st);
         int ch2 = 1 + L * J;   // first second-order channel
+        cx<T>* const U1ws = U1;
         for (int j1 = 0; j1 < J; ++j1) {
-            const bool need_spec = d_.max_order == 2 && j1 < J - 1;
+            // the first-order spectra of this scale live in the workspace, or in the caller's buffer when they are kept
+            U1 = save_cur_[j1] ? save_cur_[j1] : U1ws;
+            const bool need_spec = (d_.max_order == 2 && j1 < J - 1) || save_cur_[j1];
             // U1 = fft2(|ifft2(periodise(U0 * psi_j1))|), S1 = low(U1)   (core:30-51)
             if (tile_ok_[j1]) {
                 tile(U0, psi_ptrs(j1, 0), psi_supp(j1, 0), 0, j1, B, L, out, L, L, 1 + j1 * L, 0,
@@ -861,6 +878,8 @@ private:
         }
     }
 
+    std::vector<cx<T>*> save_base_;
+    cx<T>* save_cur_[32] = {};
     scat_plan2d_desc d_;
     int P0_ = 0, P1_ = 0, top_ = 0, left_ = 0, m0_ = 0, m1_ = 0, o0_ = 0, o1_ = 0, K_ = 0;
     std::vector<Level2D> lev_;

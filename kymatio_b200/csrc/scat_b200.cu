@@ -125,6 +125,15 @@ int scat_plan2d_forward_peers(scat_plan2d* plan, const void* x_dev, void* out_de
     });
 }
 
+int scat_plan2d_forward_save(scat_plan2d* plan, const void* x_dev, void* out_dev, void* const* saved_u1_dev, void* ws_dev,
+                             size_t ws_bytes, int64_t batch, void* stream) {
+    return guarded([&] {
+        if (!plan) throw std::runtime_error("null plan");
+        if (!saved_u1_dev) throw std::runtime_error("forward_save: null table of U1 buffers");
+        plan->forward_save(x_dev, out_dev, saved_u1_dev, ws_dev, ws_bytes, batch, static_cast<cudaStream_t>(stream));
+    });
+}
+
 int32_t scat_plan2d_order2_channels(const scat_plan2d* plan, int32_t j1) { return plan ? plan->order2_channels(j1) : 0; }
 int scat_plan2d_order2_forward(scat_plan2d* plan, int32_t j1, const void* u1_dev, void* out_dev, int64_t batch, void* stream) {
     return guarded([&] {

@@ -83,6 +83,40 @@ class Engine2D:
         with torch.cuda.device(self.device):
             return torch.empty(need, dtype=torch.uint8, device=self.device)
 
+    def saved_u1_buffers(self, B):
+        """Buffers for the first-order spectra a later backward pass needs (one per scale with children whose blocks are
+        fused; None elsewhere), or None when they would not fit comfortably (the backward then recomputes them)."""
+        g = self.geometry
+        if g["max_order"] < 2 or os.environ.get("SCAT_B200_SAVE_U1", "1") == "0":
+            return None
+        shapes = [((B * g["L"], self.Mp >> j, self.Np >> j, 2) if (j < g["J"] - 1 and self.order1_mode(j)
+                                                                   and self.order2_channels(j) > 0) else None)
+                  for j in range(g["J"])]
+        esz = 4 if self.dtype == torch.float32 else 8
+        need = sum(esz * s[0] * s[1] * s[2] * s[3] for s in shapes if s is not None)
+        if need == 0:
+            return None
+        with torch.cuda.device(self.device):
+            free, _ = torch.cuda.mem_get_info()
+        if need > 0.4 * free:
+            return None
+        return [torch.empty(s, dtype=self.dtype, device=self.device) if s is not None else None for s in shapes]
+
+    def forward_saving(self, x):
+        """forward + the saved first-order spectra (scat_plan2d_forward_save) -> (out, list or None)."""
+        B = x.shape[0]
+        saved = self.saved_u1_buffers(B) if B > 0 else None
+        if saved is None:
+            return self.forward(x), None
+        out = torch.empty((B, self.K, self.out_h, self.out_w), dtype=self.dtype, device=self.device)
+        ws = self.workspace(B)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        arr = (ctypes.c_void_p * len(saved))(*[(t.data_ptr() if t is not None else None) for t in saved])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.scat_plan2d_forward_save(self._plan, x.data_ptr(), out.data_ptr(), arr, ws.data_ptr(),
+                                                         ws.numel(), B, ctypes.c_void_p(stream)))
+        return out, saved
+
     def forward(self, x, out=None, peer_ptrs=None, multicast_ptr=None):
         """x: (B, M, N) contiguous on self.device -> (B, K, out_h, out_w).
 
@@ -170,10 +204,11 @@ class Engine2D:
         return gu0
 
     # -- backward --------------------------------------------------------------------
-    def backward(self, x, grad_out):
-        """Gradient of ``forward`` w.r.t. x: the cascade is recomputed on differentiable ops whose forward and
+    def backward(self, x, grad_out, saved_u1=None):
+        """Gradient of ``forward`` w.r.t. x: the cascade is rebuilt on differentiable ops whose forward and
         adjoint kernels are this library's own (ops2d.py) and back-propagated; processed in batch chunks to
-        bound the memory of the recomputed intermediates."""
+        bound the memory of the intermediates.  saved_u1 (forward_saving): the first-order spectra kept by the forward -
+        the fused first-order blocks then do not run their forward kernels again."""
         from .ops2d import eager_scattering2d, _Recompute
         g = self.geometry
         phi, psi = self._filters
@@ -182,23 +217,34 @@ class Engine2D:
             t, l = (self.Mp - g["M"]) // 2, (self.Np - g["N"]) // 2
             pads = (t, self.Mp - g["M"] - t, l, self.Np - g["N"] - l)
         per_img = self.K_paths_bytes()
-        chunk = max(1, min(x.shape[0], int((4 << 30) // max(1, per_img))))
+        B = x.shape[0]
+        chunk = max(1, min(B, int((8 << 30) // max(1, per_img))))
+        chunk = (B + (B + chunk - 1) // chunk - 1) // ((B + chunk - 1) // chunk)        # equal-sized chunks
         gx = torch.empty_like(x)
-        for b0 in range(0, x.shape[0], chunk):
+        L = g["L"]
+        for b0 in range(0, B, chunk):
             with torch.enable_grad():
                 xc = x[b0:b0 + chunk].detach().requires_grad_(True)
                 _Recompute.active = True
+                _Recompute.saved = None if saved_u1 is None else {
+                    j: t[b0 * L:(b0 + chunk) * L] for j, t in enumerate(saved_u1) if t is not None}
                 try:
                     y = eager_scattering2d(xc, g["J"], g["L"], g["max_order"], pads, phi, psi, eng=self)
                 finally:
                     _Recompute.active = False
+                    _Recompute.saved = None
                 gx[b0:b0 + chunk] = torch.autograd.grad(y, xc, grad_out[b0:b0 + chunk])[0]
         return gx
 
     def K_paths_bytes(self):
-        """Rough bytes of saved intermediates per image in the recomputed graph (complex fields per path)."""
+        """Rough bytes of live intermediates per image in the rebuilt graph."""
         g, esz = self.geometry, (4 if self.dtype == torch.float32 else 8)
         J, L = g["J"], g["L"]
+        fused = all(self.order1_mode(j) for j in range(J)) and (
+            g["max_order"] < 2 or all(self.order2_channels(j) > 0 for j in range(J - 1)))
+        if fused:
+            # fused blocks keep one spectrum per first-order path (U1), its gradient, and the first-order backward workspace
+            return sum(L * (self.Mp >> j) * (self.Np >> j) * 2 * esz for j in range(J)) * 5
         total = 0
         for j1 in range(J):
             n1 = (self.Mp >> j1) * (self.Np >> j1)

@@ -175,8 +175,10 @@ class PadReflect(torch.autograd.Function):
 class _Recompute:
     """Set while Engine2D.backward re-runs the cascade only to rebuild the autograd graph: the VALUES of the leaf outputs
     are then never read (their gradients come from the caller), so operators whose backward does not need their own
-    forward result skip the forward kernels."""
+    forward result skip the forward kernels.  ``saved``: {j1: U1 of that scale for the current chunk} kept by the forward
+    (Engine2D.forward_saving) - the first-order blocks then hand it out instead of computing it again."""
     active = False
+    saved = None
 
 
 class Order2(torch.autograd.Function):
@@ -208,7 +210,13 @@ class Order1Tile(torch.autograd.Function):
         U0 = U0.contiguous()
         ctx.eng, ctx.j1, ctx.batch, ctx.want_u1 = eng, j1, batch, want_u1
         ctx.save_for_backward(U0)
-        s1, u1 = eng.order1_forward(j1, U0, batch, want_u1)
+        kept = _Recompute.saved.get(j1) if (_Recompute.active and _Recompute.saved) else None
+        if _Recompute.active and (not want_u1 or kept is not None):
+            # graph rebuild: S1 is never read, U1 was kept by the forward (or is not needed) - no kernel runs
+            s1 = U0.new_empty((batch, eng.geometry["L"], eng.out_h, eng.out_w))
+            u1 = kept
+        else:
+            s1, u1 = eng.order1_forward(j1, U0, batch, want_u1)
         if not want_u1:
             u1 = U0.new_zeros((0,))
         ctx.mark_non_differentiable(*(() if want_u1 else (u1,)))
@@ -235,9 +243,11 @@ class Order1Stream(torch.autograd.Function):
         ctx.eng, ctx.j1, ctx.batch, ctx.want_u1 = eng, j1, batch, want_u1
         ctx.save_for_backward(U0)
         ctx.set_materialize_grads(False)
-        if _Recompute.active and not want_u1:      # graph rebuild of a leaf: neither value is read
+        kept = _Recompute.saved.get(j1) if (_Recompute.active and _Recompute.saved) else None
+        if _Recompute.active and (not want_u1 or kept is not None):
+            # graph rebuild: S1 is never read, U1 was kept by the forward (or is not needed) - no kernel runs
             s1 = U0.new_empty((batch, eng.geometry["L"], eng.out_h, eng.out_w))
-            u1 = U0.new_zeros((0,))
+            u1 = kept if want_u1 else U0.new_zeros((0,))
         else:
             s1, u1 = eng.order1_forward(j1, U0, batch, True, want_s1=not _Recompute.active)
             if s1 is None:
