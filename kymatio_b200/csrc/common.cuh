@@ -1,6 +1,7 @@
 // common.cuh - host-side helpers: error reporting, launch accounting, slab configuration.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -38,7 +39,19 @@ inline void check_launch(const char* what) {
 }
 
 // Run one kernel launch `f` on stream `st`; `bytes` = algorithmic bytes (reads + writes) of the launch.
+// SCAT_B200_NVTX=1: every launch is wrapped in an NVTX range named by its label (visible in Nsight timelines)
+inline bool nvtx_on() {
+    static const bool on = [] { const char* v = std::getenv("SCAT_B200_NVTX"); return v && v[0] == '1'; }();
+    return on;
+}
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const std::string& label) : on(nvtx_on()) { if (on) nvtxRangePushA(label.c_str()); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+
 template <typename F> inline void launch(const std::string& label, double bytes, cudaStream_t st, F&& f) {
+    NvtxRange range(label);
     if (timing_on()) {
         TimingRec r; r.label = label; r.bytes = bytes;
         SB_CUDA(cudaEventCreate(&r.e0)); SB_CUDA(cudaEventCreate(&r.e1));
