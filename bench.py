@@ -454,13 +454,15 @@ def run_b200_arm(args):
         # A double-buffered consumer: two sets of pinned host buffers, at most two steps in flight - step i+1 may start its
         # copies and kernels while the last device->host copies of step i drain, but step i+2 waits until step i has fully
         # landed in host memory (its buffers are reused).  Every step still moves all of its input and output.
+        # Each step is cut into half-batch chunks issued round-robin on three streams (measured: 2 chunks x 3 streams
+        # 40.7 k images/s, 2 x 2 38.6 k, 4 x 2 37.7 k, 1 x 2 37.7 k at a device-resident 41.1 k).
         xh = torch.randn(B, *SHAPE, dtype=torch.float32).pin_memory()
         yh = [torch.empty((B,) + tuple(y.shape[1:]), dtype=torch.float32).pin_memory() for _ in range(2)]
-        nchunk = int(os.environ.get("BENCH_E2E_CHUNKS", "4"))
+        nchunk = int(os.environ.get("BENCH_E2E_CHUNKS", "2"))
         if B % nchunk or B < 4 * nchunk:
             nchunk = 1
         cb = B // nchunk
-        streams = [torch.cuda.Stream(device=dev) for _ in range(min(int(os.environ.get("BENCH_E2E_STREAMS", "2")), nchunk))]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, int(os.environ.get("BENCH_E2E_STREAMS", "3"))))]
         yd_keep = torch.empty((cb,) + tuple(y.shape[1:]), dtype=torch.float32, device=dev)
         landed = [None, None]           # per host buffer set: events of the step that last wrote it
 
@@ -471,15 +473,14 @@ def run_b200_arm(args):
                     ev.synchronize()    # the host has this buffer set back (step i-2 fully landed)
             evs = []
             for c in range(nchunk):
-                st = streams[c % len(streams)]
+                st = streams[(i * nchunk + c) % len(streams)]      # consecutive chunks (and steps) alternate streams
                 with torch.cuda.stream(st):
                     xd = xh[c * cb:(c + 1) * cb].to(dev, non_blocking=True)
                     yd = S(xd) if compute else yd_keep
                     yh[buf][c * cb:(c + 1) * cb].copy_(yd, non_blocking=True)
-            for st in streams:
-                ev = torch.cuda.Event()
-                ev.record(st)
-                evs.append(ev)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    evs.append(ev)
             landed[buf] = evs
 
         def time_e2e(compute):
