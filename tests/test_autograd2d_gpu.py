@@ -114,3 +114,45 @@ def test_gradient_at_config_shapes_through_kymatio_plugin(J, shape, B):
         assert_parity(xb.grad.cpu().numpy()[:, None], xr.grad.cpu().numpy()[:, None], tol=1e-4, what="grad " + str((J, shape)))
     finally:
         plugin.uninstall()
+
+
+@pytest.mark.parametrize("J,shape,B", [(4, (224, 224), 3), (3, (256, 256), 2), (3, (40, 56), 5)])
+def test_kept_spectra_equal_recomputed(J, shape, B, monkeypatch):
+    """Training-mode forward (scat_plan2d_forward_save): same output as the inference forward, the kept first-order spectra
+    are the ones the first-order blocks would recompute, and the gradient does not depend on which of the two the backward
+    uses (atomics in the scatter: equal to float32 summation order)."""
+    from kymatio_b200 import Scattering2D
+    torch.manual_seed(3)
+    S = Scattering2D(J, shape).cuda()
+    x = torch.randn(B, *shape, device="cuda")
+    eng = S._engine(x.dtype, x.device)
+    with torch.no_grad():
+        y0 = S(x)
+    y1, saved = eng.forward_saving(x)
+    assert torch.equal(y0, y1)
+    if shape == (40, 56):            # no fused first-order blocks at generic sizes: nothing is kept, the backward recomputes
+        assert saved is None
+        return
+    assert saved is not None
+    U0 = None
+    for j1, kept in enumerate(saved):
+        if kept is None:
+            continue
+        if U0 is None:
+            from kymatio_b200.ops2d import PadReflect, Fft2, _to_complex
+            t, l = (eng.Mp - shape[0]) // 2, (eng.Np - shape[1]) // 2
+            U0 = Fft2.apply(_to_complex(PadReflect.apply(x, (t, eng.Mp - shape[0] - t, l, eng.Np - shape[1] - l))), False)
+        _, u1 = eng.order1_forward(j1, U0, B, True)
+        assert tuple(kept.shape) == tuple(u1.shape)
+        assert (kept - u1).abs().max() <= 2e-5 * u1.abs().max()
+    w = torch.randn_like(y0)
+
+    def grad():
+        xi = x.clone().requires_grad_(True)
+        (S(xi) * w).sum().backward()
+        return xi.grad
+
+    g_keep = grad()
+    monkeypatch.setenv("SCAT_B200_SAVE_U1", "0")
+    g_recompute = grad()
+    assert (g_keep - g_recompute).abs().max() <= 1e-5 * g_recompute.abs().max()
