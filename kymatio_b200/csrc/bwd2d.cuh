@@ -31,6 +31,10 @@ template <typename T> struct TileAdjArgs {
     T* R;                      // [G][n0][n1] real, storage order
     const cx<T>* tw0; const cx<T>* tw1;
     int G;
+    // runtime-size instance only (k2d_tile_adj_g): field size, transform plans and scramble tables
+    int n0, n1;
+    Plan1 plan0, plan1;
+    const int* pos0; const int* pos1;
 };
 template <typename T, int N0, int N1>
 __global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, N1)) k2d_tile_adj(TileAdjArgs<T> a) {
@@ -55,6 +59,37 @@ __global__ void __launch_bounds__(tile_max_threads(N0, N1), tile_min_blocks(N0, 
         T* __restrict__ ob = a.R + (size_t)g * N0 * N1;
         for (int it = tid; it < N0 * N1; it += nt) {
             const int q = it / N1, x = it - q * N1;
+            ob[it] = s[q * W + x].x;
+        }
+    }
+}
+
+// runtime-size variant for fields without a compiled instance: the generic backward tile (k2d_tile_bwd<T, 0, 0, 0>) keeps its
+// field in NATURAL order (decimation-in-time inverse fed through the scramble tables), so R is natural-order too
+template <typename T>
+__global__ void __launch_bounds__(tile_max_threads(0, 0), tile_min_blocks(0, 0)) k2d_tile_adj_g(TileAdjArgs<T> a) {
+    const int n0 = a.n0, n1 = a.n1, W = n1 | 1;
+    cx<T>* s = dyn_smem<cx<T>>();
+    cx<T>* tw0 = s + (size_t)n0 * W;
+    cx<T>* tw1 = tw0 + n0;
+    int* pos0 = reinterpret_cast<int*>(tw1 + n1);
+    int* pos1 = pos0 + n0;
+    const int tid = flat_tid(), nt = flat_nt();
+    stage(tw0, a.tw0, n0); stage(tw1, a.tw1, n1);
+    stage(pos0, a.pos0, n0); stage(pos1, a.pos1, n1);
+    for (int g = blockIdx.x; g < a.G; g += gridDim.x) {
+        const cx<T>* __restrict__ ib = a.gspec + (size_t)g * n0 * n1;
+        __syncthreads();
+        for (int it = tid; it < n0 * n1; it += nt) {
+            const int r = it / n1, e = it - r * n1;
+            s[pos0[r] * W + pos1[e]] = ib[it];
+        }
+        __syncthreads();
+        slab_fft<true, T>(s, n0, W, 1, a.plan1, tw1);
+        slab_fft<true, T>(s, n1, 1, W, a.plan0, tw0);
+        T* __restrict__ ob = a.R + (size_t)g * n0 * n1;
+        for (int it = tid; it < n0 * n1; it += nt) {
+            const int q = it / n1, x = it - q * n1;
             ob[it] = s[q * W + x].x;
         }
     }

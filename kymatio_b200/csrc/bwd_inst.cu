@@ -14,7 +14,7 @@ template <typename T> TileAdjKernel<T> tile_adj_lookup(int n0, int n1) {
         SB_TILE_SIZES(SB_CASE)
 #undef SB_CASE
     }
-    return nullptr;
+    return k2d_tile_adj_g<T>;           // runtime-size instance (natural-order R, pairs with k2d_tile_bwd<T, 0, 0, 0>)
 }
 template <typename T> BwdColKernel<T> bwd_col_lookup(int n) {
 #define SB_CASE(N) if (n == N) return k2d_bwd_col<T, N>;
@@ -32,6 +32,7 @@ template <typename T> void bwd_kernels_enable_smem() {
 #define SB_EN(N) enable_big_smem(k2d_tile_adj<T, N, N>);
     SB_TILE_SIZES(SB_EN)
 #undef SB_EN
+    enable_big_smem(k2d_tile_adj_g<T>);
 #define SB_EN(N) enable_big_smem(k2d_bwd_col<T, N>); enable_big_smem(k2d_bwd_row<T, N>);
     SB_STREAM_SIZES(SB_EN)
 #undef SB_EN

@@ -333,11 +333,7 @@ public:
     int order1_mode(int j1) const override {
         if (!bound_ || j1 < 0 || j1 >= d_.J) return 0;
         const int n0 = lev_[j1].a0.n, n1 = lev_[j1].a1.n;
-        if (tile_ok_[j1]) {
-            bool st = false;
-            tile_bwd_kernel_lookup<T>(n0, n1, 1 << j1, &st);
-            return (st && tile_adj_lookup<T>(n0, n1)) ? 1 : 0;
-        }
+        if (tile_ok_[j1]) return 1;         // compiled instances for the config sizes, runtime-size kernels otherwise
         if (j1 == 0 && hermitian_ok(0) && n0 == n1 && bwd_col_lookup<T>(n0) && bwd_row_lookup<T>(n1) && low_tile_ && fir_[0].ok)
             return 2;
         return 0;
@@ -383,9 +379,14 @@ public:
                 R = static_cast<T*>(ws);
                 TileAdjArgs<T> a{};
                 a.gspec = static_cast<const cx<T>*>(gu1); a.R = R; a.tw0 = tw(lev_[j1].a0); a.tw1 = tw(lev_[j1].a1); a.G = B * L;
+                a.n0 = n0; a.n1 = n1; a.plan0 = lev_[j1].a0.plan; a.plan1 = lev_[j1].a1.plan;
+                a.pos0 = pos(lev_[j1].a0); a.pos1 = pos(lev_[j1].a1);
                 auto kern = tile_adj_lookup<T>(n0, n1);
-                const size_t smem = ((size_t)n0 * (n1 | 1) + n0 + n1) * sizeof(cx<T>);
-                const int threads = tile_is_big(n0, n1) ? 512 : 256;
+                bool is_static = false;
+                tile_bwd_kernel_lookup<T>(n0, n1, 1 << j1, &is_static);
+                const size_t smem = ((size_t)n0 * (n1 | 1) + n0 + n1) * sizeof(cx<T>) + (size_t)(n0 + n1) * sizeof(int);
+                const int threads = is_static ? (tile_is_big(n0, n1) ? 512 : 256)
+                                              : std::max(64, std::min(512, (n0 * n1 / 4 + 31) / 32 * 32));
                 int occ = 0;
                 SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
                 const int grid = std::max(1, std::min(a.G, std::max(1, occ) * num_sms_));

@@ -96,11 +96,14 @@ class Engine2D:
         need = sum(esz * s[0] * s[1] * s[2] * s[3] for s in shapes if s is not None)
         if need == 0:
             return None
-        with torch.cuda.device(self.device):
-            free, _ = torch.cuda.mem_get_info()
-        if need > 0.4 * free:
+        # allocator counters, not cudaMemGetInfo: that driver call costs milliseconds and this runs on every training step
+        total = torch.cuda.get_device_properties(self.device).total_memory
+        if need > 0.4 * (total - torch.cuda.memory_allocated(self.device)):
             return None
-        return [torch.empty(s, dtype=self.dtype, device=self.device) if s is not None else None for s in shapes]
+        try:
+            return [torch.empty(s, dtype=self.dtype, device=self.device) if s is not None else None for s in shapes]
+        except torch.cuda.OutOfMemoryError:
+            return None
 
     def forward_saving(self, x):
         """forward + the saved first-order spectra (scat_plan2d_forward_save) -> (out, list or None)."""

@@ -130,10 +130,7 @@ def test_kept_spectra_equal_recomputed(J, shape, B, monkeypatch):
         y0 = S(x)
     y1, saved = eng.forward_saving(x)
     assert torch.equal(y0, y1)
-    if shape == (40, 56):            # no fused first-order blocks at generic sizes: nothing is kept, the backward recomputes
-        assert saved is None
-        return
-    assert saved is not None
+    assert saved is not None         # also at sizes without compiled instances (runtime-size tile kernels)
     U0 = None
     for j1, kept in enumerate(saved):
         if kept is None:
