@@ -752,8 +752,10 @@ private:
         bool is_static = false;
         TileKernel<T> kern = gparent ? tile_bwd_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static)
                                      : tile_kernel_lookup<T>(a.n0, a.n1, a.k, &is_static);
-        if (!gparent && spec_out && is_static)          // static instances with the forward transform compiled in
+        if (!gparent && spec_out && is_static) {        // static instances with the forward transform compiled in
             if (TileKernel<T> ks = tile_spec_kernel_lookup<T>(a.n0, a.n1, a.k)) kern = ks;
+            else kern = tile_kernel_lookup<T>(a.n0, a.n1, 0, &is_static);     // runtime alias count, spectrum store compiled in
+        }
         // CUDA-core low-pass of the static forward instances reads the taps from the [cnt][4] tables
         a.tt = (!gparent && is_static && (a.k == 2 || a.k == 4) && !a.use_mma && (a.o0p >> 2) * a.o1p <= 256 &&
                 (a.o0p >> 2) * a.o1p <= std::max(64, (a.n0 * a.n1 / 4 + 31) / 32 * 32)) ? 1 : 0;

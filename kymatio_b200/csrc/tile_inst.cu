@@ -1,12 +1,12 @@
 // tile_inst.cu - explicit instances of the fused tile kernel for the field sizes of the
 // BASELINE.json configurations, plus the generic runtime-size fallback.
-//   272-padded (256^2, J=3): 136, 68        256-padded (224^2, J=4): 128, 64, 32
+//   272-padded (256^2, J=3): 136, 68        256-padded (224^2, J=4): 128, 64, 32        40-padded (32^2, J=2): 40, 20
 #include "tile2d.cuh"
 #include "common.cuh"
 
 namespace sb {
 
-#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32)
+#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32) X(40) X(20)
 
 template <typename T> TileKernel<T> tile_kernel_lookup(int n0, int n1, int k, bool* is_static) {
     if (is_static) *is_static = true;
