@@ -146,3 +146,17 @@ def test_oracle3d_vs_live_reference(ref, kw):
     want = S(x)
     assert y.shape == want.shape
     assert np.abs(y - want).max() <= 1e-5 * np.abs(want).max()       # the reference casts its integrals to float32
+
+
+@pytest.mark.parametrize("key", ["8x10x12_J2_L3", "9x8x7_J1_L2"])
+def test_filter_bank_3d_closed_form_matches_reference(golden_dir, key):
+    """The closed form the device-side synthesis implements (oracle/filters3d.py) against banks generated by the reference
+    (kymatio/scattering3d/filter_bank.py:5-166; even and odd axis lengths)."""
+    from oracle import filters3d
+    g = np.load(os.path.join(golden_dir, "golden_filters_3d.npz"))
+    M, N, O, J, L, s0 = g[key + "_cfg"]
+    M, N, O, J, L = int(M), int(N), int(O), int(J), int(L)
+    bank = filters3d.solid_harmonic_filter_bank(M, N, O, J, L, float(s0))
+    for l in range(L + 1):
+        assert np.abs(bank[l] - g[key + f"_l{l}"]).max() <= 2e-7      # the reference rounds its grid and bank to float32
+    assert np.abs(filters3d.gaussian_filter_bank(M, N, O, J, float(s0)) - g[key + "_gauss"]).max() <= 2e-7
