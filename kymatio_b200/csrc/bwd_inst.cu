@@ -5,7 +5,7 @@
 
 namespace sb {
 
-#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32) X(40) X(20)
+#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32) X(40) X(20) X(36) X(18)
 #define SB_STREAM_SIZES(X) X(272) X(256) X(240)
 
 template <typename T> TileAdjKernel<T> tile_adj_lookup(int n0, int n1) {

@@ -947,6 +947,8 @@ template <typename T> TileKernel<T> tile_spec_kernel_lookup(int n0, int n1, int 
 template <typename T> void tile_spec_kernels_enable_smem();
 template <typename T> TileKernel<T> tile_bwd_kernel_lookup(int n0, int n1, int k, bool* is_static);
 template <typename T> void tile_kernels_enable_smem();
+template <typename T> void tile_bwd_kernels_enable_smem();
+void phase_prof_read_bwd(unsigned long long* out, bool reset);
 int phase_prof_read(unsigned long long* out, int max_n, bool reset);
 
 }  // namespace sb

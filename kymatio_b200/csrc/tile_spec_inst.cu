@@ -6,7 +6,7 @@
 
 namespace sb {
 
-#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32) X(40) X(20)
+#define SB_TILE_SIZES(X) X(136) X(68) X(128) X(64) X(32) X(40) X(20) X(36) X(18)
 
 template <typename T> TileKernel<T> tile_spec_kernel_lookup(int n0, int n1, int k) {
     if (n0 == n1) {
