@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_scattering2d_gpu.py tests/test_autograd2d_gpu.py -x -q 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_scattering2d_gpu.py tests/test_autograd2d_gpu.py -x -q 2>&1 | tail -2
+rm -f gpurun_out/r02k2.json
 timeout 200 python tools/kbench.py c2 > gpurun_out/r02k2.json 2>gpurun_out/r02k2.err; tail -2 gpurun_out/r02k2.err
 timeout 200 python tools/kbench.py c5 256 4 224 >> gpurun_out/r02k2.json 2>>gpurun_out/r02k2.err
 python - <<'PY'
