@@ -8,6 +8,7 @@ axis, periodisation <-> replication / k^2, modulus <-> ``x g / |x|`` (0 at 0, th
 Complex tensors use the torch backend's layout (trailing axis of size 2); everything is contiguous.
 """
 import ctypes
+import threading
 
 import torch
 
@@ -172,13 +173,17 @@ class PadReflect(torch.autograd.Function):
         return gx, None
 
 
-class _Recompute:
+class _RecomputeState(threading.local):
     """Set while Engine2D.backward re-runs the cascade only to rebuild the autograd graph: the VALUES of the leaf outputs
     are then never read (their gradients come from the caller), so operators whose backward does not need their own
     forward result skip the forward kernels.  ``saved``: {j1: U1 of that scale for the current chunk} kept by the forward
-    (Engine2D.forward_saving) - the first-order blocks then hand it out instead of computing it again."""
+    (Engine2D.forward_saving) - the first-order blocks then hand it out instead of computing it again.
+    Thread-local: autograd runs the backward of different devices (nn.DataParallel replicas) on different threads."""
     active = False
     saved = None
+
+
+_Recompute = _RecomputeState()
 
 
 class Order2(torch.autograd.Function):
