@@ -58,3 +58,27 @@ def test_second_device_in_one_process():
             b = s3(torch.ones(2, 16, 16, 16, device=dev))
             assert a.device == torch.device(dev) and b.device == torch.device(dev)
             assert torch.isfinite(a).all() and torch.isfinite(b).all()
+
+
+def test_data_parallel_replicas_forward_and_backward():
+    """nn.DataParallel over two GPUs (the reference's multi-GPU recipe: class-level backends shared by the replicas,
+    SURVEY 8(b) threading): replicas run on their own threads, in the forward and - through autograd's per-device
+    threads - in the backward, where each rebuilds its graph from its own kept spectra."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from kymatio_b200 import Scattering2D
+    torch.manual_seed(5)
+    S = Scattering2D(4, (224, 224)).cuda(0)
+    x = torch.randn(6, 224, 224, device="cuda:0")
+    w = torch.randn(6, S.forward(x[:1]).shape[1], 14, 14, device="cuda:0")
+
+    def run(module):
+        xi = x.clone().requires_grad_(True)
+        y = module(xi)
+        (y * w).sum().backward()
+        return y.detach(), xi.grad
+
+    y1, g1 = run(S)
+    y2, g2 = run(torch.nn.DataParallel(S, device_ids=[0, 1]))
+    assert torch.equal(y1, y2.to(y1.device))
+    assert (g1 - g2).abs().max() <= 1e-5 * g1.abs().max()
