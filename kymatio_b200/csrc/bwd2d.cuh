@@ -171,30 +171,66 @@ template <typename T, int NS> __global__ void __launch_bounds__(kBwdThreads, 3) 
     slab_fft_s<NS, false, +1, 1, kSLP, T>(s1, kSLines, tw);      // u   (rows scrambled)
     if (a.GX) slab_fft_s<NS, false, +1, 1, kSLP, T>(s2, kSLines, tw);      // F^H gU1, same positions
     const int mper = n0 / a.kl;                                  // outputs per period before unpadding (= o0 + 2)
-    for (int idx = tid; idx < n0 * kSLines; idx += nt) {
-        const int e = idx / kSLines, l = idx - e * kSLines;
+    auto modulus_bwd = [&](int e, int l, T gA) {
         const cx<T> v = s1[e * LP + l];
-        T gA = s2[e * LP + l].x;
-        if (a.Tl) {
-            // + sum_yo G0[y][yo] * Tl[yo][x]: G0[y][yo] = a0[(kl (yo+1) - y) mod n0] is nonzero within R of a multiple of kl
+        const T m2 = v.x * v.x + v.y * v.y;
+        T sc;
+        if constexpr (std::is_same<T, float>::value) sc = m2 > 0.f ? gA * rsqrtf(m2) : 0.f;
+        else sc = m2 > T(0) ? gA / sqrt(m2) : T(0);
+        s1[e * LP + l] = mk<T>(v.x * sc, v.y * sc);
+    };
+    constexpr int MT = 8;                                        // taps of a row kept in registers (banded low-pass)
+    if (a.Tl && 2 * a.R + 1 < n0 && (2 * a.R) / a.kl + 2 <= MT) {
+        // a thread owns one ROW of the slab: the (<= MT) outputs yo its sample y contributes to and their weights are
+        // found once, then applied to the 16 columns (G0[y][yo] = a0[(kl (yo+1) - y) mod n0], nonzero within R of a
+        // multiple of kl; lanes = different rows at the odd pitch LP: conflict-free)
+        for (int e = tid; e < n0; e += nt) {
             const int y = ipos[e];
             const T* __restrict__ g0 = a.G0 + (size_t)y * a.o0p;
-            if (2 * a.R + 1 >= n0) {
-                for (int yo = 0; yo < a.o0; ++yo) gA += g0[yo] * tl[yo * kSLines + l];
-            } else {
-                int j0 = y - a.R, j1 = y + a.R;                  // kl*(yo+1) in [j0, j1] (mod n0)
-                j0 = (j0 >= 0) ? (j0 + a.kl - 1) / a.kl : -((-j0) / a.kl);
-                j1 = (j1 >= 0) ? j1 / a.kl : -((-j1 + a.kl - 1) / a.kl);
-                for (int jj = j0; jj <= j1; ++jj) {
-                    int j = jj % mper; if (j < 0) j += mper;
-                    const int yo = j - 1;
-                    if (yo >= 0 && yo < a.o0) gA += g0[yo] * tl[yo * kSLines + l];
-                }
+            int j0 = y - a.R, j1 = y + a.R;                      // kl*(yo+1) in [j0, j1] (mod n0)
+            j0 = (j0 >= 0) ? (j0 + a.kl - 1) / a.kl : -((-j0) / a.kl);
+            j1 = (j1 >= 0) ? j1 / a.kl : -((-j1 + a.kl - 1) / a.kl);
+            T tap[MT]; int row[MT];
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+                const int jj = j0 + t;
+                int j = jj % mper; if (j < 0) j += mper;
+                const int yo = j - 1;
+                const bool ok = jj <= j1 && yo >= 0 && yo < a.o0;
+                tap[t] = ok ? g0[yo] : T(0);
+                row[t] = ok ? yo * kSLines : 0;
+            }
+#pragma unroll 4
+            for (int l = 0; l < kSLines; ++l) {
+                T gA = s2[e * LP + l].x;
+#pragma unroll
+                for (int t = 0; t < MT; ++t) gA += tap[t] * tl[row[t] + l];
+                modulus_bwd(e, l, gA);
             }
         }
-        const T mag = sqrt(v.x * v.x + v.y * v.y);
-        const T sc = mag > T(0) ? gA / mag : T(0);
-        s1[e * LP + l] = mk<T>(v.x * sc, v.y * sc);
+    } else {
+        for (int idx = tid; idx < n0 * kSLines; idx += nt) {
+            const int e = idx / kSLines, l = idx - e * kSLines;
+            T gA = s2[e * LP + l].x;
+            if (a.Tl) {
+                // + sum_yo G0[y][yo] * Tl[yo][x]
+                const int y = ipos[e];
+                const T* __restrict__ g0 = a.G0 + (size_t)y * a.o0p;
+                if (2 * a.R + 1 >= n0) {
+                    for (int yo = 0; yo < a.o0; ++yo) gA += g0[yo] * tl[yo * kSLines + l];
+                } else {
+                    int j0 = y - a.R, j1 = y + a.R;              // kl*(yo+1) in [j0, j1] (mod n0)
+                    j0 = (j0 >= 0) ? (j0 + a.kl - 1) / a.kl : -((-j0) / a.kl);
+                    j1 = (j1 >= 0) ? j1 / a.kl : -((-j1 + a.kl - 1) / a.kl);
+                    for (int jj = j0; jj <= j1; ++jj) {
+                        int j = jj % mper; if (j < 0) j += mper;
+                        const int yo = j - 1;
+                        if (yo >= 0 && yo < a.o0) gA += g0[yo] * tl[yo * kSLines + l];
+                    }
+                }
+            }
+            modulus_bwd(e, l, gA);
+        }
     }
     __syncthreads();
     slab_fft_s<NS, true, -1, 1, kSLP, T>(s1, kSLines, tw);       // cols-forward: scrambled in -> natural frequency out
