@@ -597,7 +597,8 @@ def run_b200_arm(args):
                 "copy_only_ceiling": world * B * args.steps / (copy_ms * 1e-3),
                 "note": f"pinned host in/out through {route}, {nchunk} chunks on {len(streams)} streams, two host buffer sets "
                         "(at most two steps in flight), wall clock over all K steps incl. the final drain, max over ranks; "
-                        "copy_only_ceiling = the same pinned transfers with the compute removed"},
+                        "copy_only_ceiling = the same pinned transfers with the compute removed; unlike `value`, the e2e steps "
+                        "run back to back without the 256 MB L2 flush between them, which is why e2e can sit slightly above value"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": top["pass_model_GBps"], "peak": hbm_peak, "unit": "GB/s",
                      "frac": top["pass_model_frac"], "traffic": top.get("dram_bytes_per_launch"), "kernel": top["label"],
