@@ -153,3 +153,32 @@ def test_kept_spectra_equal_recomputed(J, shape, B, monkeypatch):
     monkeypatch.setenv("SCAT_B200_SAVE_U1", "0")
     g_recompute = grad()
     assert (g_keep - g_recompute).abs().max() <= 1e-5 * g_recompute.abs().max()
+
+
+@pytest.mark.parametrize("kw,shape", [(dict(J=2, max_order=1), (32, 32)), (dict(J=2, pre_pad=True), (32, 32)),
+                                      (dict(J=3, L=4), (64, 64)), (dict(J=4, max_order=1), (224, 224)),
+                                      (dict(J=2, out_type="list"), (28, 28))])
+def test_gradient_variants_match_reference_torch_backend(kw, shape):
+    """max_order=1, pre_pad, other L, list output: the fused blocks (kept spectra, static and runtime-size tiles) against
+    the reference torch backend's autograd, through the unmodified kymatio frontend."""
+    if not import_reference():
+        pytest.skip("reference not installed under baseline/_ref")
+    import kymatio_b200.kymatio_plugin as plugin
+    plugin.install()
+    from kymatio.torch import Scattering2D
+    torch.manual_seed(1)
+    in_shape = tuple((n // 2 ** kw["J"] + 2) * 2 ** kw["J"] for n in shape) if kw.get("pre_pad") else shape   # already padded
+    x = torch.randn(2, *in_shape, device="cuda")
+    grads = []
+    for backend in ("torch", "torch_b200"):
+        S = Scattering2D(shape=shape, backend=backend, **kw).cuda()
+        xi = x.clone().requires_grad_(True)
+        y = S(xi)
+        if kw.get("out_type") == "list":
+            y = torch.stack([c["coef"] for c in y], dim=1)
+        torch.manual_seed(2)
+        w = torch.randn_like(y)
+        (y * w).sum().backward()
+        grads.append(xi.grad)
+    plugin.uninstall()
+    assert_parity(grads[1].cpu().numpy()[:, None], grads[0].cpu().numpy()[:, None], tol=1e-4, what=str(kw))
