@@ -116,3 +116,17 @@ def test_plugin_frontends_use_gpu_synthesis(golden_dir):
     y3 = S3(torch.from_numpy(g3["x"]).cuda()).double().cpu().numpy()
     assert np.abs(y3 - g3["Sx64"]).max() <= 1e-4 * np.abs(g3["Sx64"]).max()
     kymatio_plugin.uninstall()
+
+
+def test_gpu_bank_3d_matches_closed_form_oracle_at_larger_size():
+    """Element-wise against the float64 closed form (oracle/filters3d.py, itself pinned on the reference fixtures) at a
+    non-cubic size the fixtures do not cover in full."""
+    from oracle import filters3d
+    from kymatio_b200.filter_bank_gpu import solid_harmonic_filter_bank_gpu, gaussian_filter_bank_gpu
+    M, N, O, J, L, s0 = 64, 48, 40, 2, 3, 1.25
+    bank = solid_harmonic_filter_bank_gpu(M, N, O, J, L, s0, as_numpy=True)
+    ref = filters3d.solid_harmonic_filter_bank(M, N, O, J, L, s0)
+    for l in range(L + 1):
+        assert np.abs(bank[l] - ref[l]).max() <= 2e-7
+    g = gaussian_filter_bank_gpu(M, N, O, J, s0, as_numpy=True)
+    assert np.abs(g - filters3d.gaussian_filter_bank(M, N, O, J, s0)).max() <= 2e-7
