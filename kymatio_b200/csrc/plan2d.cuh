@@ -19,6 +19,7 @@
 #include "tile2d.cuh"
 #include "tile2h.cuh"
 #include "kernels2d_tma.cuh"
+#include "kernels2d_tmap.cuh"
 #include "bwd2d.cuh"
 #include "plan_host.h"
 
@@ -184,7 +185,7 @@ public:
             tile_spec_kernels_enable_smem<T>();
             tile2h_kernels_enable_smem<T>();
         });
-        once_per_device("tma_rows", [] { tma_kernels_enable_smem(); });
+        once_per_device("tma_rows", [] { tma_kernels_enable_smem(); tmap_kernels_enable_smem(); });
         once_per_device(sizeof(T) == 4 ? "bwd2d_f" : "bwd2d_d", [] { bwd_kernels_enable_smem<T>(); });
         {
             int dev = 0;
@@ -566,6 +567,14 @@ private:
         if constexpr (std::is_same<T, float>::value) {
             // TMA-fed persistent variant (kernels2d_tma.cuh): same-size product (no aliases), square static line length
             if (use_tma_ && a.k == 1 && chain_static(out_res) && a.n0 == a.n1 && a.n0 % kTmaRows == 0) {
+                if (a.n1 == 256 && use_tmap_) {
+                    // power-of-two lines: tensor copies with the hardware swizzle (kernels2d_tmap.cuh)
+                    const int npairs = NF * (a.n0 / kTmapRows);
+                    const int m = std::max(1, std::min(Bp, (2 * num_sms_) / npairs));
+                    bool ok = false;
+                    launch(label, bytes, st, [&] { ok = rowprod_tmap256_launch(a, Bp, m, npairs, st); });
+                    if (ok) return;
+                }
                 if (RowProdTmaKernel kt = rowprod_tma_lookup(a.n1)) {
                     // a CTA owns one (filter, 16-row block) pair and walks over the images: m CTAs per pair
                     const int npairs = NF * (a.n0 / kTmaRows);
@@ -904,6 +913,7 @@ private:
     int stagger_ns_ = env_int("SCAT_B200_STAGGER_NS", 0);
     bool use_tma_ = env_int("SCAT_B200_TMA", 1) != 0;             // TMA-fed persistent row passes (kernels2d_tma.cuh)
     int tma_ctas_per_sm_ = env_int("SCAT_B200_TMA_CTAS", 3);
+    bool use_tmap_ = env_int("SCAT_B200_TMAP", 1) != 0;           // tensor-map row pass for 256-long lines (kernels2d_tmap.cuh)
     int tile2h_mode_ = env_int("SCAT_B200_TILE2H", 0);            // 0 off, 1 big fields only, 2 every static size
     int tile2h_threads_ = env_int("SCAT_B200_TILE2H_THREADS", 384);
     int chunk_cap_ = env_int("SCAT_B200_CHUNK", 0);

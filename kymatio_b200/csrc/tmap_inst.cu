@@ -1,0 +1,167 @@
+// tmap_inst.cu - host side of the tensor-map (2-D TMA, hardware swizzle) row pass: descriptor encoding + launch.
+#include <cuda.h>
+#include "kernels2d_tmap.cuh"
+#include "common.cuh"
+
+namespace sb {
+
+namespace tma {
+// tensor copy global -> shared (coordinates: c0 = element index along the row, c1 = row), completion on `bar`
+__device__ __forceinline__ void tensor_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     saddr(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(saddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap* map, int c0, int c1, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(saddr(src_smem))
+                 : "memory");
+}
+}  // namespace tma
+
+// byte offset of complex element e (< 16) of row r (< 16) inside a swizzled box
+__device__ __forceinline__ uint32_t tmap_off(int r, int e) { return (uint32_t)(r * 128 + ((((e >> 1) ^ (r & 7)) << 4) | ((e & 1) << 3))); }
+
+// out[g][r][:] = inverse row transform (DIF: natural in, scrambled out) of parent[g / NF][r][:] * filt[g % NF][r][:] * scale
+// for 256 x 256 fields.  Work split as k2d_rowprod_tma: a CTA owns one (filter, 16-row block) pair and walks over the images
+// j, j + m, ...; its 16 filter values per thread stay in registers.
+__global__ void __launch_bounds__(kTmapThreads, 2)
+k2d_rowprod_tmap256(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map, RowProdArgs<float> a, int Bp,
+                    int m) {
+    using T = float;
+    constexpr int NS = 256, ROWS = kTmapRows, SPP = NS / ROWS;
+    extern __shared__ unsigned char tmap_smem_raw[];
+    unsigned char* base = tmap_smem_raw + ((1024u - (tma::saddr(tmap_smem_raw) & 1023u)) & 1023u);     // swizzle atom alignment
+    cx<T>* tw = reinterpret_cast<cx<T>*>(base + 2 * kTmapSlabBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tw + NS);
+    uint64_t* done = full + 2;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&full[0], 1); tma::mbar_init(&full[1], 1);
+        tma::mbar_init(&done[0], 1); tma::mbar_init(&done[1], 1);
+        tma::fence_mbar_init();
+    }
+    for (int i = tid; i < NS; i += kTmapThreads) tw[i] = a.tw[i];
+    __syncthreads();
+    const int npairs = a.NF * SPP;
+    const int pair = blockIdx.x % npairs, j = blockIdx.x / npairs;
+    const int fi = pair / SPP, r0 = (pair - fi * SPP) * ROWS;
+    const int n_my = j < Bp ? (Bp - j + m - 1) / m : 0;       // images j, j + m, ...
+
+    if (tid >= kTmapComputeThreads) {
+        // ---------------- producer warp: one lane issues the 16 box copies of every slab
+        if (tid != kTmapComputeThreads) return;
+        auto issue_load = [&](int i) {
+            const int b = i & 1;
+            const int row = (j + i * m) * NS + r0;
+            tma::mbar_arrive_expect_tx(&full[b], kTmapSlabBytes);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tma::tensor_load_2d(base + b * kTmapSlabBytes + k * kTmapBoxBytes, &in_map, 32 * k, row, &full[b]);
+        };
+        for (int i = 0; i < 2 && i < n_my; ++i) issue_load(i);
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
+            const int row = ((j + i * m) * a.NF + fi) * NS + r0;
+            tma::mbar_wait(&done[b], (i >> 1) & 1);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tma::tensor_store_2d(&out_map, 32 * k, row, base + b * kTmapSlabBytes + k * kTmapBoxBytes);
+            tma::bulk_commit();
+            if (i + 2 < n_my) { tma::bulk_wait_read<0>(); issue_load(i + 2); }
+        }
+        tma::bulk_wait<0>();
+        return;
+    }
+    // ---------------- compute warps
+    // pass 0: thread (row, e) owns elements e + 16 k, k < 16: the same offset in each of the 16 boxes
+    const int rowA = tid >> 4, eA = tid & 15;
+    const uint32_t offA = tmap_off(rowA, eA);
+    T f0[16];
+    if (a.filt) {
+        const T* __restrict__ frow = a.filt[fi] + (size_t)(r0 + rowA) * NS + eA;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f0[k] = __ldg(frow + 16 * k) * a.scale;
+    } else {                                                    // unit filter (adjoint row pass of the backward chain)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f0[k] = a.scale;
+    }
+    // pass 1: thread (box, row) with the row fastest across lanes
+    const int boxB = tid >> 4, rowB = tid & 15;
+    for (int i = 0; i < n_my; ++i) {
+        const int b = i & 1;
+        unsigned char* s = base + b * kTmapSlabBytes;
+        tma::mbar_wait(&full[b], (i >> 1) & 1);
+        {
+            cx<T> v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = scal(*reinterpret_cast<const cx<T>*>(s + k * kTmapBoxBytes + offA), f0[k]);
+            butterfly_v<16, false, +1, 16, T>(v, eA, tw);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) *reinterpret_cast<cx<T>*>(s + k * kTmapBoxBytes + offA) = v[k];
+        }
+        tma::named_sync<1>(kTmapComputeThreads);
+        {
+            cx<T> v[16];
+            unsigned char* bx = s + boxB * kTmapBoxBytes + rowB * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 q = *reinterpret_cast<const float4*>(bx + ((c ^ (rowB & 7)) << 4));
+                v[2 * c] = mk<T>(q.x, q.y); v[2 * c + 1] = mk<T>(q.z, q.w);
+            }
+            butterfly_v<16, false, +1, 1, T>(v, 0, tw);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 q; q.x = v[2 * c].x; q.y = v[2 * c].y; q.z = v[2 * c + 1].x; q.w = v[2 * c + 1].y;
+                *reinterpret_cast<float4*>(bx + ((c ^ (rowB & 7)) << 4)) = q;
+            }
+        }
+        tma::fence_proxy_async();
+        tma::named_sync<1>(kTmapComputeThreads);
+        if (tid == 0) tma::mbar_arrive(&done[b]);
+    }
+}
+
+
+namespace {
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+EncodeFn encode_fn() {
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    return fn;
+}
+// [rows][256 complex] float array as a 2-D tensor of floats, box = 16 complex x 16 rows, 128-byte swizzle
+bool encode_rows256(CUtensorMap* map, const void* base, size_t rows) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {512, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {512 * sizeof(float)};
+    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t es[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+bool rowprod_tmap256_launch(const RowProdArgs<float>& a, int Bp, int m, int npairs, cudaStream_t st) {
+    if (a.n0 != 256 || a.n1 != 256 || a.k != 1) return false;
+    if ((reinterpret_cast<uintptr_t>(a.parent) | reinterpret_cast<uintptr_t>(a.out)) & 15) return false;
+    CUtensorMap in_map, out_map;
+    if (!encode_rows256(&in_map, a.parent, (size_t)Bp * 256)) return false;
+    if (!encode_rows256(&out_map, a.out, (size_t)Bp * a.NF * 256)) return false;
+    k2d_rowprod_tmap256<<<(unsigned)(npairs * m), kTmapThreads, tmap_row_smem_bytes(), st>>>(in_map, out_map, a, Bp, m);
+    return true;
+}
+
+void tmap_kernels_enable_smem() { enable_big_smem(k2d_rowprod_tmap256); }
+
+}  // namespace sb
