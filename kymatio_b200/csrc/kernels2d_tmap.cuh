@@ -30,6 +30,8 @@ constexpr size_t tmap_row_smem_bytes() { return 1024 + 2 * (size_t)kTmapSlabByte
 
 // host side (tmap_inst.cu): encode the two tensor maps and launch; false when the driver entry point is unavailable
 bool rowprod_tmap256_launch(const RowProdArgs<float>& a, int Bp, int m, int npairs, cudaStream_t st);
+// Hermitian forward row pass (in place) of G paths; grid = persistent CTAs
+bool rowfwdh_tmap256_launch(const RowArgs<float>& a, int G, int grid, cudaStream_t st);
 void tmap_kernels_enable_smem();
 
 }  // namespace sb

@@ -645,6 +645,13 @@ private:
             dim3 grid((unsigned)G, ceil_div(n0 / 2 + 1, kSLines));
             const std::string label = "rowpass_fwd_herm:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_));
             if constexpr (std::is_same<T, float>::value) {
+                if (use_tma_ && use_tmap_ && n0 == 256 && n1 == 256) {
+                    const int nslabs = G * 9;
+                    const int grid_t = std::max(1, std::min(nslabs, tma_ctas_per_sm_ * num_sms_));
+                    bool ok = false;
+                    launch(label, 1.5 * G * n0 * n1 * sizeof(cx<T>), st, [&] { ok = rowfwdh_tmap256_launch(a, G, grid_t, st); });
+                    if (ok) return;
+                }
                 if (use_tma_) {
                     if (RowFwdhTmaKernel kt = rowfwdh_tma_lookup(n1)) {
                         const int nslabs = G * ceil_div(n0 / 2 + 1, kTmaRows);

@@ -122,6 +122,145 @@ k2d_rowprod_tmap256(const __grid_constant__ CUtensorMap in_map, const __grid_con
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------
+// Hermitian forward row pass for 256 x 256 fields (see k2d_rowfwdh_tma, kernels2d_tma.cuh): rows v <= 128 of `data` hold
+// scrambled spatial rows; forward DIT -> natural-order Fourier rows; row v goes back through the tensor map, its conjugate
+// mirror row 256 - v is written by the compute warps, and (optionally) both feed the row-folded low-pass product.
+// A path has 129 such rows = 8 full slabs + one slab with a single valid row, which is stored through a second tensor map
+// whose box is one row high (rows 129.. of the slab are other slabs' mirror rows and must not be overwritten).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tmap_pos(int l, int col) { return (uint32_t)((col >> 4) * kTmapBoxBytes) + tmap_off(l, col & 15); }
+
+__global__ void __launch_bounds__(kTmapThreads, 3)
+k2d_rowfwdh_tmap256(const __grid_constant__ CUtensorMap map16, const __grid_constant__ CUtensorMap map1, RowArgs<float> a, int nslabs) {
+    using T = float;
+    constexpr int NS = 256, ROWS = kTmapRows, n1 = NS, H = NS / 2;
+    constexpr int SPP = (H + 1 + ROWS - 1) / ROWS;             // 9 slabs per path (the last one holds row 128 only)
+    extern __shared__ unsigned char tmap_smem_raw[];
+    unsigned char* base = tmap_smem_raw + ((1024u - (tma::saddr(tmap_smem_raw) & 1023u)) & 1023u);
+    cx<T>* tw = reinterpret_cast<cx<T>*>(base + 2 * kTmapSlabBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tw + NS);
+    uint64_t* done = full + 2;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&full[0], 1); tma::mbar_init(&full[1], 1);
+        tma::mbar_init(&done[0], 1); tma::mbar_init(&done[1], 1);
+        tma::fence_mbar_init();
+    }
+    for (int i = tid; i < NS; i += kTmapThreads) tw[i] = a.tw[i];
+    __syncthreads();
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_my = first < nslabs ? (nslabs - first + stride - 1) / stride : 0;
+
+    if (tid >= kTmapComputeThreads) {
+        if (tid != kTmapComputeThreads) return;
+        auto issue_load = [&](int i) {
+            const int t = first + i * stride, g = t / SPP, r0 = (t - g * SPP) * ROWS, b = i & 1;
+            // the short slab also loads a full box (rows 129.. are in bounds and ignored)
+            tma::mbar_arrive_expect_tx(&full[b], kTmapSlabBytes);
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                tma::tensor_load_2d(base + b * kTmapSlabBytes + k * kTmapBoxBytes, &map16, 32 * k, g * NS + r0, &full[b]);
+        };
+        for (int i = 0; i < 2 && i < n_my; ++i) issue_load(i);
+        for (int i = 0; i < n_my; ++i) {
+            const int t = first + i * stride, g = t / SPP, r0 = (t - g * SPP) * ROWS, b = i & 1;
+            tma::mbar_wait(&done[b], (i >> 1) & 1);
+            if (r0 + ROWS <= H + 1) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    tma::tensor_store_2d(&map16, 32 * k, g * NS + r0, base + b * kTmapSlabBytes + k * kTmapBoxBytes);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    tma::tensor_store_2d(&map1, 32 * k, g * NS + r0, base + b * kTmapSlabBytes + k * kTmapBoxBytes);
+            }
+            tma::bulk_commit();
+            if (i + 2 < n_my) { tma::bulk_wait_read<0>(); issue_load(i + 2); }
+        }
+        tma::bulk_wait<0>();
+        return;
+    }
+    const int rowA = tid >> 4, eA = tid & 15;                   // stride-16 pass: the same offset in each box
+    const uint32_t offA = tmap_off(rowA, eA);
+    const int boxB = tid >> 4, rowB = tid & 15;                 // contiguous pass: (box, row), row fastest across lanes
+    constexpr int half = n1 / 2;
+    for (int i = 0; i < n_my; ++i) {
+        const int t = first + i * stride, g = t / SPP, r0 = (t - g * SPP) * ROWS, b = i & 1;
+        const int nl = min(ROWS, H + 1 - r0);
+        unsigned char* s = base + b * kTmapSlabBytes;
+        cx<T>* ob = a.out + (size_t)g * a.n0 * n1;
+        tma::mbar_wait(&full[b], (i >> 1) & 1);
+        {   // forward DIT, first pass: radix 16 on the 16 contiguous elements of a box row (no twiddles)
+            cx<T> v[16];
+            unsigned char* bx = s + boxB * kTmapBoxBytes + rowB * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 q = *reinterpret_cast<const float4*>(bx + ((c ^ (rowB & 7)) << 4));
+                v[2 * c] = mk<T>(q.x, q.y); v[2 * c + 1] = mk<T>(q.z, q.w);
+            }
+            butterfly_v<16, true, -1, 1, T>(v, 0, tw);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 q; q.x = v[2 * c].x; q.y = v[2 * c].y; q.z = v[2 * c + 1].x; q.w = v[2 * c + 1].y;
+                *reinterpret_cast<float4*>(bx + ((c ^ (rowB & 7)) << 4)) = q;
+            }
+        }
+        tma::named_sync<1>(kTmapComputeThreads);
+        {   // second pass: radix 16 at stride 16 with the twiddles
+            cx<T> v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = *reinterpret_cast<const cx<T>*>(s + k * kTmapBoxBytes + offA);
+            butterfly_v<16, true, -1, 16, T>(v, eA, tw);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) *reinterpret_cast<cx<T>*>(s + k * kTmapBoxBytes + offA) = v[k];
+        }
+        tma::named_sync<1>(kTmapComputeThreads);
+        // the write-back of rows v may start while the mirrors are built: nothing below writes shared memory
+        tma::fence_proxy_async();
+        auto at = [&](int l, int col) { return *reinterpret_cast<const cx<T>*>(s + tmap_pos(l, col)); };
+        // conjugate mirror rows: U[n0 - v][w] = conj(U[v][(n1 - w) % n1]), two columns per thread
+        for (int idx = tid; idx < nl * half; idx += kTmapComputeThreads) {
+            const int l = idx / half, e = 2 * (idx - l * half);
+            const int v = r0 + l;
+            if (v > 0 && v < H) {
+                const cx<T> m0 = at(l, e == 0 ? 0 : n1 - e), m1 = at(l, n1 - e - 1);
+                cxpair<T> om; om.a = mk<T>(m0.x, -m0.y); om.b = mk<T>(m1.x, -m1.y);
+                *reinterpret_cast<cxpair<T>*>(ob + (size_t)(a.n0 - v) * n1 + e) = om;
+            }
+        }
+        if (a.low_out) {
+            // row-folded low-pass product: low_out[g][u][e] = sum_d U[u][e + d*m1] * phi[u][e + d*m1] for u = v and n0 - v
+            const int m1 = a.low_m1, kf = n1 / m1;
+            for (int idx = tid; idx < 2 * nl * m1; idx += kTmapComputeThreads) {
+                const int mir = idx / (nl * m1), rem = idx - mir * nl * m1;
+                const int l = rem / m1, e = rem - l * m1;
+                const int v = r0 + l;
+                if (mir && !(v > 0 && v < H)) continue;
+                const int u = mir ? a.n0 - v : v;
+                const int2 sp = a.low_supp[u];
+                T ax = T(0), ay = T(0);
+                if (sp.y > 0) {
+                    const T* __restrict__ fr = a.low_filt + (size_t)u * n1;
+                    for (int d = 0; d < kf; ++d) {
+                        const int C = e + d * m1;
+                        int rel = C - sp.x;
+                        if (rel < 0) rel += n1;
+                        if (rel < sp.y) {
+                            const cx<T> tv = at(l, mir ? (C == 0 ? 0 : n1 - C) : C);
+                            const T f = fr[C];
+                            ax += tv.x * f; ay += (mir ? -tv.y : tv.y) * f;
+                        }
+                    }
+                }
+                a.low_out[((size_t)g * a.n0 + u) * m1 + e] = mk<T>(ax, ay);
+            }
+        }
+        tma::named_sync<1>(kTmapComputeThreads);
+        if (tid == 0) tma::mbar_arrive(&done[b]);
+    }
+}
+
 namespace {
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -139,12 +278,12 @@ EncodeFn encode_fn() {
     return fn;
 }
 // [rows][256 complex] float array as a 2-D tensor of floats, box = 16 complex x 16 rows, 128-byte swizzle
-bool encode_rows256(CUtensorMap* map, const void* base, size_t rows) {
+bool encode_rows256(CUtensorMap* map, const void* base, size_t rows, unsigned box_rows = 16) {
     EncodeFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {512, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {512 * sizeof(float)};
-    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t box[2] = {32, box_rows};
     const cuuint32_t es[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -162,6 +301,16 @@ bool rowprod_tmap256_launch(const RowProdArgs<float>& a, int Bp, int m, int npai
     return true;
 }
 
-void tmap_kernels_enable_smem() { enable_big_smem(k2d_rowprod_tmap256); }
+bool rowfwdh_tmap256_launch(const RowArgs<float>& a, int G, int grid, cudaStream_t st) {
+    if (a.n0 != 256 || a.n1 != 256 || a.in != a.out) return false;
+    if (reinterpret_cast<uintptr_t>(a.in) & 15) return false;
+    CUtensorMap map16, map1;
+    if (!encode_rows256(&map16, a.in, (size_t)G * 256, 16)) return false;
+    if (!encode_rows256(&map1, a.in, (size_t)G * 256, 1)) return false;
+    k2d_rowfwdh_tmap256<<<(unsigned)grid, kTmapThreads, tmap_row_smem_bytes(), st>>>(map16, map1, a, G * 9);
+    return true;
+}
+
+void tmap_kernels_enable_smem() { enable_big_smem(k2d_rowprod_tmap256); enable_big_smem(k2d_rowfwdh_tmap256); }
 
 }  // namespace sb
