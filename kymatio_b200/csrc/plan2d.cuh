@@ -632,9 +632,16 @@ private:
             // prime-factor lengths: the kernel wants the prime-factor INPUT position table (kernels2d.cuh)
             if (pfa_ok(n0)) a.pos = reinterpret_cast<const int*>(cbuf_ + lev_[res].a0.pin_off);
             dim3 grid((unsigned)G, n1 / kSLines);
-            launch("colpass_inv_mod_rfwd:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_)),
-                   1.5 * G * n0 * n1 * sizeof(cx<T>), st,
-                   [&] { skern(n0, c).col_imrf<<<grid, c.block, c.smem, st>>>(a); });
+            const std::string clabel = "colpass_inv_mod_rfwd:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_));
+            bool done = false;
+            if constexpr (std::is_same<T, float>::value) {
+                if (use_tma_ && imrf_tmap_ && n0 == 272 && n1 == 272)
+                    launch(clabel, 1.5 * G * n0 * n1 * sizeof(cx<T>), st,
+                           [&] { done = colpass_imrf_tmap272_launch(a, G, 3, num_sms_, st); });
+            }
+            if (!done)
+                launch(clabel, 1.5 * G * n0 * n1 * sizeof(cx<T>), st,
+                       [&] { skern(n0, c).col_imrf<<<grid, c.block, c.smem, st>>>(a); });
         }
         {
             RowArgs<T> a{};
@@ -920,6 +927,7 @@ private:
     int stagger_ns_ = env_int("SCAT_B200_STAGGER_NS", 0);
     bool use_tma_ = env_int("SCAT_B200_TMA", 1) != 0;             // TMA-fed persistent row passes (kernels2d_tma.cuh)
     int tma_ctas_per_sm_ = env_int("SCAT_B200_TMA_CTAS", 3);
+    bool imrf_tmap_ = env_int("SCAT_B200_IMRF_TMAP", 1) != 0;     // tensor-copy staged column pass (kernels2d_tmap.cuh)
     bool use_tmap_ = env_int("SCAT_B200_TMAP", 1) != 0;           // tensor-map row pass for 256-long lines (kernels2d_tmap.cuh)
     int tile2h_mode_ = env_int("SCAT_B200_TILE2H", 0);            // 0 off, 1 big fields only, 2 every static size
     int tile2h_threads_ = env_int("SCAT_B200_TILE2H_THREADS", 384);

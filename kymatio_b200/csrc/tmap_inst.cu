@@ -261,6 +261,76 @@ k2d_rowfwdh_tmap256(const __grid_constant__ CUtensorMap map16, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Column pass of the full-resolution chain (k2d_colpass_imrf, kernels2d.cuh: column inverse, modulus, one complex forward
+// transform per pair of real columns, Hermitian half stored) for 272 x 272 fields, staged by TMA tensor copies:
+// a slab = 16 adjacent columns x 272 rows = two boxes {16 complex = 128 B, 136 rows}, dense 128-byte rows in shared memory
+// (the butterflies run with the 16 columns across a half-warp: conflict-free without padding); the 137 stored rows go
+// back as one box.  Persistent CTAs, two buffers; thread 0 issues the copies of the NEXT slab before the transforms of the
+// current one - no staging loops, no per-slab twiddle staging.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kImrfN = 272, kImrfH = kImrfN / 2;
+constexpr uint32_t kImrfSlabBytes = kImrfN * 16 * sizeof(cx<float>);            // 34 816
+constexpr size_t imrf_tmap_smem_bytes() { return 128 + 2 * (size_t)kImrfSlabBytes + kImrfN * sizeof(cx<float>) + 2 * sizeof(uint64_t); }
+
+__global__ void __launch_bounds__(288, 3)
+k2d_colpass_imrf_tmap272(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map, ColArgs<float> a,
+                         int nslabs) {
+    using T = float;
+    constexpr int NS = kImrfN, n0 = NS, LP = 16, H = kImrfH;
+    extern __shared__ unsigned char tmap_smem_raw[];
+    unsigned char* base = tmap_smem_raw + ((128u - (tma::saddr(tmap_smem_raw) & 127u)) & 127u);
+    cx<T>* tw = reinterpret_cast<cx<T>*>(base + 2 * kImrfSlabBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tw + NS);
+    const int tid = flat_tid(), nt = flat_nt();
+    if (tid == 0) { tma::mbar_init(&full[0], 1); tma::mbar_init(&full[1], 1); tma::fence_mbar_init(); }
+    for (int i = tid; i < NS; i += nt) tw[i] = a.tw[i];
+    __syncthreads();
+    const int nsl = a.n1 / kSLines;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_my = first < nslabs ? (nslabs - first + stride - 1) / stride : 0;
+    auto issue_load = [&](int i) {                              // thread 0 only
+        const int t = first + i * stride, g = t / nsl, c0 = (t - g * nsl) * kSLines, b = i & 1;
+        unsigned char* dst = base + b * kImrfSlabBytes;
+        tma::mbar_arrive_expect_tx(&full[b], kImrfSlabBytes);
+        tma::tensor_load_2d(dst, &in_map, 2 * c0, g * n0, &full[b]);
+        tma::tensor_load_2d(dst + kImrfSlabBytes / 2, &in_map, 2 * c0, g * n0 + H, &full[b]);
+    };
+    if (tid == 0 && n_my > 0) issue_load(0);
+    for (int i = 0; i < n_my; ++i) {
+        const int t = first + i * stride, g = t / nsl, c0 = (t - g * nsl) * kSLines, b = i & 1;
+        cx<T>* s = reinterpret_cast<cx<T>*>(base + b * kImrfSlabBytes);
+        if (tid == 0 && i + 1 < n_my) {
+            tma::bulk_wait_read<0>();                           // the store of slab i-1 has finished reading buffer b^1
+            issue_load(i + 1);
+        }
+        tma::mbar_wait(&full[b], (i >> 1) & 1);
+        slab_fft_s<NS, false, +1, 1, LP, T, 1, false>(s, kSLines, tw);          // inverse + modulus -> (|u|, 0), rows scrambled
+        // pack column pairs: (|u|_{2m}, |u|_{2m+1}) -> one complex column at lane 2m
+        for (int idx = tid; idx < n0 * (kSLines / 2); idx += nt) {
+            const int e = idx / (kSLines / 2), l = 2 * (idx - e * (kSLines / 2));
+            s[e * LP + l].y = s[e * LP + l + 1].x;
+        }
+        __syncthreads();
+        slab_fft_s<NS, true, -1, 2, LP, T, 0, false>(s, kSLines / 2, tw);       // forward on the 8 packed columns
+        // untangle in place: A[v] = (Z[v] + conj Z[n-v]) / 2,  B[v] = (Z[v] - conj Z[n-v]) / (2i);  rows v = 0..n0/2
+        // (row v is read only by the thread that rewrites it; rows n0 - v > n0/2 are never written)
+        for (int idx = tid; idx < (H + 1) * (kSLines / 2); idx += nt) {
+            const int v = idx / (kSLines / 2), l = 2 * (idx - v * (kSLines / 2));
+            const int vm = v == 0 ? 0 : n0 - v;
+            const cx<T> z = s[v * LP + l], zm = s[vm * LP + l];
+            cxpair<T> o;
+            o.a = mk<T>(T(0.5) * (z.x + zm.x), T(0.5) * (z.y - zm.y));
+            o.b = mk<T>(T(0.5) * (z.y + zm.y), T(0.5) * (zm.x - z.x));
+            *reinterpret_cast<cxpair<T>*>(s + v * LP + l) = o;
+        }
+        tma::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { tma::tensor_store_2d(&out_map, 2 * c0, g * n0, s); tma::bulk_commit(); }
+    }
+    if (tid == 0) tma::bulk_wait<0>();
+}
+
 namespace {
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -278,6 +348,18 @@ EncodeFn encode_fn() {
     return fn;
 }
 // [rows][256 complex] float array as a 2-D tensor of floats, box = 16 complex x 16 rows, 128-byte swizzle
+// [rows][n complex] float array, box = 16 complex x box_rows rows, dense (no swizzle)
+bool encode_cols(CUtensorMap* map, const void* base, size_t rows, int n, unsigned box_rows) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * n, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)2 * n * sizeof(float)};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t es[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 bool encode_rows256(CUtensorMap* map, const void* base, size_t rows, unsigned box_rows = 16) {
     EncodeFn fn = encode_fn();
     if (!fn) return false;
@@ -311,6 +393,20 @@ bool rowfwdh_tmap256_launch(const RowArgs<float>& a, int G, int grid, cudaStream
     return true;
 }
 
-void tmap_kernels_enable_smem() { enable_big_smem(k2d_rowprod_tmap256); enable_big_smem(k2d_rowfwdh_tmap256); }
+bool colpass_imrf_tmap272_launch(const ColArgs<float>& a, int G, int ctas_per_sm, int num_sms, cudaStream_t st) {
+    if (a.n0 != 272 || a.n1 != 272 || a.in != a.out) return false;
+    if (reinterpret_cast<uintptr_t>(a.in) & 15) return false;
+    CUtensorMap in_map, out_map;
+    if (!encode_cols(&in_map, a.in, (size_t)G * 272, 272, 136)) return false;
+    if (!encode_cols(&out_map, a.out, (size_t)G * 272, 272, 137)) return false;
+    const int nslabs = G * (272 / kSLines);
+    const int grid = std::max(1, std::min(nslabs, ctas_per_sm * num_sms));
+    k2d_colpass_imrf_tmap272<<<(unsigned)grid, dim3(16, 17), imrf_tmap_smem_bytes(), st>>>(in_map, out_map, a, nslabs);
+    return true;
+}
+
+void tmap_kernels_enable_smem() {
+    enable_big_smem(k2d_colpass_imrf_tmap272);
+    enable_big_smem(k2d_rowprod_tmap256); enable_big_smem(k2d_rowfwdh_tmap256); }
 
 }  // namespace sb

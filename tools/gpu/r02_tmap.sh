@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 rm -f gpurun_out/r02tm.json
-SCAT_B200_TMAP=0 timeout 200 python tools/kbench.py c5_off 256 4 224 >> gpurun_out/r02tm.json 2>gpurun_out/r02tm.err
-SCAT_B200_TMAP=1 timeout 200 python tools/kbench.py c5_on 256 4 224 >> gpurun_out/r02tm.json 2>>gpurun_out/r02tm.err
+SCAT_B200_IMRF_TMAP=0 timeout 200 python tools/kbench.py c2_off >> gpurun_out/r02tm.json 2>gpurun_out/r02tm.err
+SCAT_B200_IMRF_TMAP=1 timeout 200 python tools/kbench.py c2_on >> gpurun_out/r02tm.json 2>>gpurun_out/r02tm.err
 tail -3 gpurun_out/r02tm.err
 python - <<'PY'
 import json
@@ -11,4 +11,3 @@ for l in open('gpurun_out/r02tm.json'):
     print(d['label'], '%.3f ms %.0f img/s chk %.10e'%(d['ms_median'], d['img_per_s'], d['checksum']))
     print('     ', ' '.join('%s=%.3f'%(k.split(':G')[0],v) for k,v in list(ks.items())[:8]))
 PY
-timeout 600 python -m pytest tests/test_autograd2d_gpu.py tests/test_scattering2d_gpu.py -x -q 2>&1 | tail -2
