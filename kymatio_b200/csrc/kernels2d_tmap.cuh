@@ -32,8 +32,8 @@ constexpr size_t tmap_row_smem_bytes() { return 1024 + 2 * (size_t)kTmapSlabByte
 bool rowprod_tmap256_launch(const RowProdArgs<float>& a, int Bp, int m, int npairs, cudaStream_t st);
 // Hermitian forward row pass (in place) of G paths; grid = persistent CTAs
 bool rowfwdh_tmap256_launch(const RowArgs<float>& a, int G, int grid, cudaStream_t st);
-// column pass (inverse, modulus, real forward) of G 272 x 272 paths, in place, staged by dense tensor copies
-bool colpass_imrf_tmap272_launch(const ColArgs<float>& a, int G, int ctas_per_sm, int num_sms, cudaStream_t st);
+// column pass (inverse, modulus, real forward) of G 272 x 272 or 256 x 256 paths, in place, staged by dense tensor copies
+bool colpass_imrf_tmap_launch(const ColArgs<float>& a, int G, int ctas_per_sm, int num_sms, cudaStream_t st);
 void tmap_kernels_enable_smem();
 
 }  // namespace sb

@@ -635,9 +635,9 @@ private:
             const std::string clabel = "colpass_inv_mod_rfwd:L" + std::to_string(res) + ":G" + std::to_string(G / std::max(1, last_B_));
             bool done = false;
             if constexpr (std::is_same<T, float>::value) {
-                if (use_tma_ && imrf_tmap_ && n0 == 272 && n1 == 272)
+                if (use_tma_ && imrf_tmap_ && n0 == n1 && (n0 == 272 || n0 == 256))
                     launch(clabel, 1.5 * G * n0 * n1 * sizeof(cx<T>), st,
-                           [&] { done = colpass_imrf_tmap272_launch(a, G, 3, num_sms_, st); });
+                           [&] { done = colpass_imrf_tmap_launch(a, G, 3, num_sms_, st); });
             }
             if (!done)
                 launch(clabel, 1.5 * G * n0 * n1 * sizeof(cx<T>), st,

@@ -263,21 +263,23 @@ k2d_rowfwdh_tmap256(const __grid_constant__ CUtensorMap map16, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // Column pass of the full-resolution chain (k2d_colpass_imrf, kernels2d.cuh: column inverse, modulus, one complex forward
-// transform per pair of real columns, Hermitian half stored) for 272 x 272 fields, staged by TMA tensor copies:
-// a slab = 16 adjacent columns x 272 rows = two boxes {16 complex = 128 B, 136 rows}, dense 128-byte rows in shared memory
-// (the butterflies run with the 16 columns across a half-warp: conflict-free without padding); the 137 stored rows go
-// back as one box.  Persistent CTAs, two buffers; thread 0 issues the copies of the NEXT slab before the transforms of the
+// transform per pair of real columns, Hermitian half stored) for 272 x 272 and 256 x 256 fields, staged by TMA tensor copies:
+// a slab = 16 adjacent columns x NS rows = two boxes {16 complex = 128 B, NS/2 rows}, dense 128-byte rows in shared memory
+// (the butterflies run with the 16 columns across a half-warp: conflict-free without padding, also for NS = 256); the
+// NS/2 + 1 stored rows go back as one box.  Persistent CTAs, two buffers; thread 0 issues the copies of the NEXT slab before the transforms of the
 // current one - no staging loops, no per-slab twiddle staging.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kImrfN = 272, kImrfH = kImrfN / 2;
-constexpr uint32_t kImrfSlabBytes = kImrfN * 16 * sizeof(cx<float>);            // 34 816
-constexpr size_t imrf_tmap_smem_bytes() { return 128 + 2 * (size_t)kImrfSlabBytes + kImrfN * sizeof(cx<float>) + 2 * sizeof(uint64_t); }
+template <int NS> constexpr size_t imrf_tmap_smem_bytes() {
+    return 128 + 2 * (size_t)NS * 16 * sizeof(cx<float>) + NS * sizeof(cx<float>) + 2 * sizeof(uint64_t);
+}
 
+template <int NS>
 __global__ void __launch_bounds__(288, 3)
-k2d_colpass_imrf_tmap272(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map, ColArgs<float> a,
-                         int nslabs) {
+k2d_colpass_imrf_tmap(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map, ColArgs<float> a,
+                      int nslabs) {
     using T = float;
-    constexpr int NS = kImrfN, n0 = NS, LP = 16, H = kImrfH;
+    constexpr int n0 = NS, LP = 16, H = NS / 2;
+    constexpr uint32_t kImrfSlabBytes = NS * 16 * sizeof(cx<float>);            // 34 816 at 272
     extern __shared__ unsigned char tmap_smem_raw[];
     unsigned char* base = tmap_smem_raw + ((128u - (tma::saddr(tmap_smem_raw) & 127u)) & 127u);
     cx<T>* tw = reinterpret_cast<cx<T>*>(base + 2 * kImrfSlabBytes);
@@ -393,20 +395,24 @@ bool rowfwdh_tmap256_launch(const RowArgs<float>& a, int G, int grid, cudaStream
     return true;
 }
 
-bool colpass_imrf_tmap272_launch(const ColArgs<float>& a, int G, int ctas_per_sm, int num_sms, cudaStream_t st) {
-    if (a.n0 != 272 || a.n1 != 272 || a.in != a.out) return false;
+bool colpass_imrf_tmap_launch(const ColArgs<float>& a, int G, int ctas_per_sm, int num_sms, cudaStream_t st) {
+    const int n = a.n0;
+    if ((n != 272 && n != 256) || a.n1 != n || a.in != a.out) return false;
     if (reinterpret_cast<uintptr_t>(a.in) & 15) return false;
     CUtensorMap in_map, out_map;
-    if (!encode_cols(&in_map, a.in, (size_t)G * 272, 272, 136)) return false;
-    if (!encode_cols(&out_map, a.out, (size_t)G * 272, 272, 137)) return false;
-    const int nslabs = G * (272 / kSLines);
+    if (!encode_cols(&in_map, a.in, (size_t)G * n, n, n / 2)) return false;
+    if (!encode_cols(&out_map, a.out, (size_t)G * n, n, n / 2 + 1)) return false;
+    const int nslabs = G * (n / kSLines);
     const int grid = std::max(1, std::min(nslabs, ctas_per_sm * num_sms));
-    k2d_colpass_imrf_tmap272<<<(unsigned)grid, dim3(16, 17), imrf_tmap_smem_bytes(), st>>>(in_map, out_map, a, nslabs);
+    if (n == 272)
+        k2d_colpass_imrf_tmap<272><<<(unsigned)grid, dim3(16, 17), imrf_tmap_smem_bytes<272>(), st>>>(in_map, out_map, a, nslabs);
+    else
+        k2d_colpass_imrf_tmap<256><<<(unsigned)grid, dim3(16, 16), imrf_tmap_smem_bytes<256>(), st>>>(in_map, out_map, a, nslabs);
     return true;
 }
 
 void tmap_kernels_enable_smem() {
-    enable_big_smem(k2d_colpass_imrf_tmap272);
+    enable_big_smem(k2d_colpass_imrf_tmap<272>); enable_big_smem(k2d_colpass_imrf_tmap<256>);
     enable_big_smem(k2d_rowprod_tmap256); enable_big_smem(k2d_rowfwdh_tmap256); }
 
 }  // namespace sb

@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 rm -f gpurun_out/r02tm.json
-SCAT_B200_IMRF_TMAP=0 timeout 200 python tools/kbench.py c2_off >> gpurun_out/r02tm.json 2>gpurun_out/r02tm.err
-SCAT_B200_IMRF_TMAP=1 timeout 200 python tools/kbench.py c2_on >> gpurun_out/r02tm.json 2>>gpurun_out/r02tm.err
+SCAT_B200_IMRF_TMAP=0 timeout 200 python tools/kbench.py c5_off 256 4 224 >> gpurun_out/r02tm.json 2>gpurun_out/r02tm.err
+SCAT_B200_IMRF_TMAP=1 timeout 200 python tools/kbench.py c5_on 256 4 224 >> gpurun_out/r02tm.json 2>>gpurun_out/r02tm.err
+timeout 200 python tools/kbench.py c2 >> gpurun_out/r02tm.json 2>>gpurun_out/r02tm.err
 tail -3 gpurun_out/r02tm.err
 python - <<'PY'
 import json
